@@ -1,0 +1,39 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def weights():
+    return load_golden("weights_calibrated.npz")
+
+
+@pytest.fixture(scope="session")
+def case_a():
+    return load_golden("case_a.npz")
+
+
+@pytest.fixture(scope="session")
+def case_b():
+    return load_golden("case_b.npz")
+
+
+@pytest.fixture(scope="session")
+def case_bwd():
+    return load_golden("case_bwd.npz")
