@@ -1,0 +1,130 @@
+/*
+ * mvsnet_b200.h -- C ABI of the B200-native MVSNet depth-inference hot path.
+ *
+ * One shared library (libmvsnet_b200.so, hand-written CUDA for sm_100a) exports exactly these
+ * symbols.  Signatures use plain pointers and sizes only -- no torch types -- so the same library
+ * is bound from Python (ctypes, see scene_3dreconstruction_mvsnet_b200/_lib.py and INTEGRATION.md),
+ * C or C++.  Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository olivier-2018/scene_3Dreconstruction_MVSNet).
+ *
+ * Conventions
+ *   - All tensors are dense fp32 in the reference's layouts: feature maps NCHW, volumes NCDHW,
+ *     projection matrices row-major 4x4 with K[R|t] in rows 0-2 (datasets/dataloader_eval.py:158-159).
+ *   - Pointers named *_host are host memory; every other data pointer is DEVICE memory on the
+ *     current device.  `stream` is a cudaStream_t (NULL = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless the name ends in _host.
+ *   - Inputs are borrowed and never written.  Outputs/workspaces are caller-allocated.
+ *   - Every function returns MVS_OK (0) or a negative mvs_status; mvs_last_error() gives the
+ *     message for the calling thread.  Nothing aborts the process.  There is no CPU fallback.
+ *   - Re-entrant: no global mutable state except an atomic launch counter; safe to call from
+ *     several host threads on several devices (nn.DataParallel calls the reference's forward
+ *     from one thread per device, train.py:125).
+ */
+#ifndef MVSNET_B200_H
+#define MVSNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSNET_B200_ABI_VERSION 1
+
+typedef enum {
+    MVS_OK = 0,
+    MVS_ERR_INVALID_ARG = -1, /* shape / pointer / alignment contract violated (the reference would raise) */
+    MVS_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+    MVS_ERR_UNSUPPORTED = -3  /* valid for the reference but outside this build's scope */
+} mvs_status;
+
+/* Precision of the CostRegNet contraction.  FP32 = CUDA-core fp32 FMA, matches the reference to
+ * fp32 rounding.  BF16 = tcgen05 tensor-core implicit GEMM with bf16 operands, fp32 accumulate
+ * (looser, separately stated tolerance). */
+typedef enum { MVS_PRECISION_FP32 = 0, MVS_PRECISION_BF16 = 1 } mvs_precision;
+
+int mvs_abi_version(void);
+const char *mvs_last_error(void);
+/* Number of kernels this library has launched so far in this process (all threads). */
+uint64_t mvs_launch_count(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+const char *mvs_arch(void);
+
+/* ---- (a2) homo_warping(src_fea, src_proj, ref_proj, depth_values)      models/module.py:96-139
+ * src_fea [B,C,H,W], src_proj/ref_proj [B,4,4], depth_values [B,D]  ->  out [B,C,D,H,W].
+ * Bilinear, zero padding, the reference's align_corners mismatch reproduced (module.py:130-136). */
+int mvs_homo_warping(const float *src_fea, const float *src_proj, const float *ref_proj, const float *depth_values,
+                     float *out, int B, int C, int D, int H, int W, void *stream);
+
+/* Backward of homo_warping w.r.t. src_fea (the grid carries no gradient, module.py:106).
+ * grad_out [B,C,D,H,W] -> grad_src [B,C,H,W] (overwritten). */
+int mvs_homo_warping_bwd(const float *grad_out, const float *src_proj, const float *ref_proj,
+                         const float *depth_values, float *grad_src, int B, int C, int D, int H, int W,
+                         void *stream);
+
+/* ---- (a2+a3) fused plane-sweep warp + variance cost volume             models/mvsnet.py:145-177
+ * fea [B,V,C,H,W] (view 0 = reference view), proj [B,V,4,4], depth_values [B,D]
+ *   -> var [B,C,D,H,W] = sum(x^2)/V - (sum(x)/V)^2 over the V views; per-view warped volumes are
+ * never written to memory.  C must be 32 (FeatureNet's width, mvsnet.py:24).
+ * workspace: mvs_warp_variance_workspace_bytes() bytes of device memory (channels-last copy of the
+ * source-view features + the composed homographies). */
+size_t mvs_warp_variance_workspace_bytes(int B, int V, int C, int H, int W);
+int mvs_warp_variance_fwd(const float *fea, const float *proj, const float *depth_values, float *var,
+                          void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
+
+/* ---- (a8) backward of the fused op (autograd through mvsnet.py:167-177 + grid_sample)
+ * grad_var [B,C,D,H,W] -> grad_fea [B,V,C,H,W] (overwritten; view 0 = reference view).
+ * workspace: mvs_warp_variance_bwd_workspace_bytes() bytes. */
+size_t mvs_warp_variance_bwd_workspace_bytes(int B, int V, int C, int H, int W);
+int mvs_warp_variance_bwd(const float *grad_var, const float *fea, const float *proj, const float *depth_values,
+                          float *grad_fea, void *workspace, int B, int V, int C, int D, int H, int W,
+                          void *stream);
+
+/* ---- (a4) CostRegNet building blocks                    models/module.py:26-33, models/mvsnet.py:33-73
+ * Conv3d k=3 pad=1 stride 1|2 with eval-mode BatchNorm folded by the caller:
+ *   y = act( conv(x, w) + shift ),  w [Cout,Cin,3,3,3] already multiplied by gamma/sqrt(var+eps),
+ *   shift [Cout] = beta - mean*gamma/sqrt(var+eps) (or the conv bias for the final prob layer). */
+int mvs_conv3d_bn_relu(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin,
+                       int Cout, int D, int H, int W, int stride, void *stream);
+/* ConvTranspose3d k=3 stride=2 pad=1 output_padding=1 (mvsnet.py:46-59), BN folded the same way,
+ * w [Cin,Cout,3,3,3]; y = skip + act(convT(x,w) + shift) with skip optional (mvsnet.py:69-71).
+ * x [B,Cin,D,H,W] -> y [B,Cout,2D,2H,2W]. */
+int mvs_conv_transpose3d_bn_relu(const float *x, const float *w, const float *shift, int relu, const float *skip,
+                                 float *y, int B, int Cin, int Cout, int D, int H, int W, void *stream);
+
+/* Whole CostRegNet.forward (mvsnet.py:64-73), eval mode.  Layer order in the arrays:
+ * conv0..conv6, conv7, conv9, conv11, prob.  volume [B,32,D,H,W] -> logits [B,D,H,W]. */
+#define MVS_COSTREG_LAYERS 11
+typedef struct {
+    const float *w[MVS_COSTREG_LAYERS];     /* folded weights, layouts as above (device) */
+    const float *shift[MVS_COSTREG_LAYERS]; /* folded shifts (device) */
+} mvs_costreg_params;
+size_t mvs_costreg_workspace_bytes(int B, int D, int H, int W, int precision);
+int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *params, float *logits, void *workspace, int B,
+                    int D, int H, int W, int precision, void *stream);
+
+/* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
+ *                                                        models/mvsnet.py:192-193,204,214-218
+ * logits [B,D,H,W], depth_values [B,D] -> depth [B,H,W], conf [B,H,W]; prob [B,D,H,W] optional. */
+int mvs_softmax_depth_conf(const float *logits, const float *depth_values, float *depth, float *conf, float *prob,
+                           int B, int D, int H, int W, void *stream);
+
+/* ---- (a6) depth_regression(p, depth_values)                           models/module.py:144-147
+ * p [B,D,H,W]; depth_values [B,D] (dv_batch_stride = D) or a shared [D] vector (dv_batch_stride = 0,
+ * the call at mvsnet.py:217) -> out [B,H,W]. */
+int mvs_depth_regression(const float *p, const float *depth_values, int dv_batch_stride, float *out, int B, int D,
+                         int H, int W, void *stream);
+
+/* ---- Host-buffer entry point: features to depth map, everything this library owns in one call.
+ * Copies fea/proj/depth_values host->device, runs warp+variance -> CostRegNet -> softmax/depth/conf,
+ * copies depth/conf device->host and synchronises.  params_host holds HOST pointers to the folded
+ * weights (element counts implied by the layer table).  Allocates and frees its own device memory. */
+int mvs_depth_from_features_host(const float *fea_host, const float *proj_host, const float *depth_values_host,
+                                 const mvs_costreg_params *params_host, float *depth_host, float *conf_host, int B,
+                                 int V, int D, int H, int W, int precision, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSNET_B200_H */

@@ -1,0 +1,306 @@
+// CostRegNet building blocks, fp32 CUDA-core path (bit-for-tolerance parity with the reference).
+//
+// Replaces, for the reference:
+//   models/module.py:26-33   ConvBnReLU3D  = nn.Conv3d(k3,p1,s1|2,bias=False) + BatchNorm3d + ReLU
+//   models/mvsnet.py:46-59   nn.ConvTranspose3d(k3,s2,p1,op1,bias=False) + BatchNorm3d + ReLU
+//   models/mvsnet.py:62      prob = nn.Conv3d(8,1,3,padding=1)  (bias, no BN/ReLU)
+//   models/mvsnet.py:69-71   skip additions  conv4 + conv7(x) ...
+// Eval-mode BatchNorm is folded into the weights/shift by the caller, so BN, ReLU and the skip add
+// cost no extra pass over the activation (the reference runs each as a separate kernel).
+//
+// This file is the strict-precision (fp32 FMA) path.  The tensor-core path is conv3d_tc.cu.
+#include "common.cuh"
+
+namespace mvs {
+
+// ------------------------------------------------------------------------------------------------
+// Direct 3x3x3 convolution, NCDHW.  One CTA: TZ x TY x 32 output voxels x COUT_T output channels.
+// Thread: 4 consecutive x outputs x COUT_T channels in registers.  Input channels are processed in
+// chunks of CK through a shared-memory halo tile; weights of the chunk are broadcast from smem.
+// ------------------------------------------------------------------------------------------------
+template <int S, int TZ, int TY>
+struct ConvTile {
+    static constexpr int IZ = (TZ - 1) * S + 3;
+    static constexpr int IY = (TY - 1) * S + 3;
+    static constexpr int IX = 31 * S + 3;
+    static constexpr int IXP = (IX + 3) / 4 * 4;
+    static constexpr int PER_CH = IZ * IY * IXP;
+    static constexpr int THREADS = TZ * TY * 8;
+};
+
+template <int S, int CK, int TZ, int TY, int COUT_T>
+__global__ void __launch_bounds__(TZ *TY * 8)
+conv3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ shift, int relu,
+                   float *__restrict__ y, int Cin, int Cout, int Din, int Hin, int Win, int Do, int Ho, int Wo,
+                   int tiles_x) {
+    using T = ConvTile<S, TZ, TY>;
+    extern __shared__ __align__(16) float smem[];
+    float *s_in = smem;                      // [CK][IZ][IY][IXP]
+    float *s_w = smem + CK * T::PER_CH;      // [CK][27][COUT_T]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = (tid >> 3) % TY, tz = tid / (8 * TY);
+    const int cgroups = (Cout + COUT_T - 1) / COUT_T;
+    const int b = blockIdx.z / cgroups;
+    const int co0 = (blockIdx.z % cgroups) * COUT_T;
+    const int ox0 = (blockIdx.x % tiles_x) * 32, oy0 = (blockIdx.x / tiles_x) * TY, oz0 = blockIdx.y * TZ;
+    const int ix0 = ox0 * S - 1, iy0 = oy0 * S - 1, iz0 = oz0 * S - 1;
+    const size_t in_cs = (size_t)Din * Hin * Win;
+
+    float acc[4][COUT_T];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < COUT_T; ++c) acc[o][c] = 0.f;
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += CK) {
+        __syncthreads();
+        for (int idx = tid; idx < CK * T::IZ * T::IY * T::IX; idx += T::THREADS) {
+            const int xx = idx % T::IX;
+            const int r = idx / T::IX;
+            const int yy = r % T::IY;
+            const int r2 = r / T::IY;
+            const int zz = r2 % T::IZ;
+            const int c = r2 / T::IZ;
+            const int gx = ix0 + xx, gy = iy0 + yy, gz = iz0 + zz;
+            float v = 0.f;
+            if (ci0 + c < Cin && gx >= 0 && gx < Win && gy >= 0 && gy < Hin && gz >= 0 && gz < Din)
+                v = __ldg(x + ((size_t)b * Cin + ci0 + c) * in_cs + ((size_t)gz * Hin + gy) * Win + gx);
+            s_in[((c * T::IZ + zz) * T::IY + yy) * T::IXP + xx] = v;
+        }
+        for (int idx = tid; idx < CK * 27 * COUT_T; idx += T::THREADS) {
+            const int co = idx % COUT_T;
+            const int tap = (idx / COUT_T) % 27;
+            const int c = idx / (COUT_T * 27);
+            float v = 0.f;
+            if (co0 + co < Cout && ci0 + c < Cin) v = __ldg(w + ((size_t)(co0 + co) * Cin + ci0 + c) * 27 + tap);
+            s_w[idx] = v;
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int c = 0; c < CK; ++c) {
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const float *row = s_in + ((c * T::IZ + tz * S + kd) * T::IY + ty * S + kh) * T::IXP + tx * 4 * S;
+                    float in[4 * S + 4];
+                    if (S == 1) {
+                        const float4 a = *reinterpret_cast<const float4 *>(row);
+                        const float2 e = *reinterpret_cast<const float2 *>(row + 4);
+                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = e.x; in[5] = e.y;
+                    } else {
+                        const float4 a = *reinterpret_cast<const float4 *>(row);
+                        const float4 e = *reinterpret_cast<const float4 *>(row + 4);
+                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
+                        in[4] = e.x; in[5] = e.y; in[6] = e.z; in[7] = e.w;
+                        in[8] = row[8];
+                    }
+                    const float *wp = s_w + (c * 27 + (kd * 3 + kh) * 3) * COUT_T;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        float wr[COUT_T];
+                        if (COUT_T % 4 == 0) {
+#pragma unroll
+                            for (int q = 0; q < COUT_T / 4; ++q) {
+                                const float4 t = *reinterpret_cast<const float4 *>(wp + kw * COUT_T + 4 * q);
+                                wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < COUT_T; ++q) wr[q] = wp[kw * COUT_T + q];
+                        }
+#pragma unroll
+                        for (int o = 0; o < 4; ++o)
+#pragma unroll
+                            for (int q = 0; q < COUT_T; ++q) acc[o][q] = fmaf(in[o * S + kw], wr[q], acc[o][q]);
+                    }
+                }
+            }
+        }
+    }
+
+    const int oz = oz0 + tz, oy = oy0 + ty, ox = ox0 + tx * 4;
+    if (oz >= Do || oy >= Ho || ox >= Wo) return;
+    const size_t out_cs = (size_t)Do * Ho * Wo;
+#pragma unroll
+    for (int q = 0; q < COUT_T; ++q) {
+        if (co0 + q >= Cout) break;
+        const float sh = __ldg(shift + co0 + q);
+        float v[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            v[o] = acc[o][q] + sh;
+            if (relu) v[o] = fmaxf(v[o], 0.f);
+        }
+        float *op = y + ((size_t)b * Cout + co0 + q) * out_cs + ((size_t)oz * Ho + oy) * Wo + ox;
+        if ((Wo & 3) == 0) {
+            *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (ox + o < Wo) op[o] = v[o];
+        }
+    }
+}
+
+template <int S, int CK, int TZ, int TY, int COUT_T>
+static int launch_conv(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin, int Cout,
+                       int D, int H, int W, cudaStream_t st) {
+    using T = ConvTile<S, TZ, TY>;
+    const int Do = (D - 1) / S + 1, Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+    const int tiles_x = cdiv(Wo, 32), tiles_y = cdiv(Ho, TY), tiles_z = cdiv(Do, TZ);
+    const int cgroups = cdiv(Cout, COUT_T);
+    MVS_REQUIRE(tiles_z <= 65535 && (long long)B * cgroups <= 65535, "conv3d: grid too large");
+    const size_t smem = (size_t)(CK * T::PER_CH + CK * 27 * COUT_T) * sizeof(float);
+    auto kern = conv3d_fp32_kernel<S, CK, TZ, TY, COUT_T>;
+    if (smem > 48 * 1024) MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(tiles_x * tiles_y, tiles_z, B * cgroups), T::THREADS, smem, st>>>(x, w, shift, relu, y, Cin, Cout, D, H, W,
+                                                                                 Do, Ho, Wo, tiles_x);
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transposed convolution k3 s2 p1 op1 as a gather: out[o] = sum_{i,k : o = 2i - 1 + k} in[i] w[k].
+// Per dimension an even output (parity 0) sees tap k=1 of input i=o/2; an odd output (parity 1)
+// sees k=2 of input (o-1)/2 and k=0 of input (o+1)/2.  One thread owns one low-resolution position
+// and produces its 2x2x2 output block for COUT_T channels from the 2x2x2 input neighbourhood.
+// ------------------------------------------------------------------------------------------------
+template <int COUT_T, int CK>
+__global__ void __launch_bounds__(128)
+convT3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ shift, int relu,
+                    const float *__restrict__ skip, float *__restrict__ y, int Cin, int Cout, int D, int H, int W) {
+    __shared__ __align__(16) float s_w[CK * 27 * COUT_T];  // [ci][tap][co]
+    const int tid = threadIdx.x;
+    const int cgroups = (Cout + COUT_T - 1) / COUT_T;
+    const int b = blockIdx.z / cgroups;
+    const int co0 = (blockIdx.z % cgroups) * COUT_T;
+    const int z = blockIdx.y;
+    const int pos = blockIdx.x * 128 + tid;
+    const bool live = pos < H * W;
+    const int yy = live ? pos / W : 0, xx = live ? pos % W : 0;
+    const size_t in_cs = (size_t)D * H * W;
+    const bool hz = z + 1 < D, hy = yy + 1 < H, hx = xx + 1 < W;
+
+    float acc[8][COUT_T];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+        for (int q = 0; q < COUT_T; ++q) acc[p][q] = 0.f;
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += CK) {
+        __syncthreads();
+        for (int idx = tid; idx < CK * 27 * COUT_T; idx += 128) {
+            const int co = idx % COUT_T;
+            const int tap = (idx / COUT_T) % 27;
+            const int c = idx / (COUT_T * 27);
+            float v = 0.f;
+            if (co0 + co < Cout && ci0 + c < Cin) v = __ldg(w + ((size_t)(ci0 + c) * Cout + co0 + co) * 27 + tap);
+            s_w[idx] = v;
+        }
+        __syncthreads();
+        if (!live) continue;
+#pragma unroll 1
+        for (int c = 0; c < CK; ++c) {
+            if (ci0 + c >= Cin) break;
+            const float *ip = x + ((size_t)b * Cin + ci0 + c) * in_cs + ((size_t)z * H + yy) * W + xx;
+            float in[8];  // [dz][dy][dx]
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int dz = n >> 2, dy = (n >> 1) & 1, dx = n & 1;
+                const bool ok = (!dz || hz) && (!dy || hy) && (!dx || hx);
+                in[n] = ok ? __ldg(ip + ((size_t)dz * H + dy) * W + dx) : 0.f;
+            }
+            const float *wc = s_w + c * 27 * COUT_T;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {           // output parity (pz,py,px)
+                const int pz = p >> 2, py = (p >> 1) & 1, px = p & 1;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {       // input offset (dz,dy,dx)
+                    const int dz = n >> 2, dy = (n >> 1) & 1, dx = n & 1;
+                    if ((dz && !pz) || (dy && !py) || (dx && !px)) continue;  // even outputs only see offset 0
+                    const int kd = pz ? (dz ? 0 : 2) : 1;
+                    const int kh = py ? (dy ? 0 : 2) : 1;
+                    const int kw = px ? (dx ? 0 : 2) : 1;
+                    const float *wt = wc + ((kd * 3 + kh) * 3 + kw) * COUT_T;
+#pragma unroll
+                    for (int q = 0; q < COUT_T; ++q) acc[p][q] = fmaf(in[n], wt[q], acc[p][q]);
+                }
+            }
+        }
+    }
+    if (!live) return;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const size_t out_cs = (size_t)8 * in_cs;
+#pragma unroll
+    for (int q = 0; q < COUT_T; ++q) {
+        if (co0 + q >= Cout) break;
+        const float sh = __ldg(shift + co0 + q);
+#pragma unroll
+        for (int pzy = 0; pzy < 4; ++pzy) {
+            const int pz = pzy >> 1, py = pzy & 1;
+            const size_t o = ((size_t)b * Cout + co0 + q) * out_cs + ((size_t)(2 * z + pz) * Ho + 2 * yy + py) * Wo + 2 * xx;
+            float v0 = acc[pzy * 2 + 0][q] + sh, v1 = acc[pzy * 2 + 1][q] + sh;
+            if (relu) {
+                v0 = fmaxf(v0, 0.f);
+                v1 = fmaxf(v1, 0.f);
+            }
+            if (skip) {  // skip + relu(bn(convT))   (mvsnet.py:69-71)
+                const float2 s = __ldg(reinterpret_cast<const float2 *>(skip + o));
+                v0 += s.x;
+                v1 += s.y;
+            }
+            *reinterpret_cast<float2 *>(y + o) = make_float2(v0, v1);
+        }
+    }
+}
+
+int conv3d_fp32(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin, int Cout, int D,
+                int H, int W, int stride, cudaStream_t st) {
+    if (stride == 1) {
+        if (Cout < 8) return launch_conv<1, 4, 4, 8, 1>(x, w, shift, relu, y, B, Cin, Cout, D, H, W, st);
+        return launch_conv<1, 4, 4, 8, 8>(x, w, shift, relu, y, B, Cin, Cout, D, H, W, st);
+    }
+    if (Cout < 8) return launch_conv<2, 2, 2, 8, 1>(x, w, shift, relu, y, B, Cin, Cout, D, H, W, st);
+    return launch_conv<2, 2, 2, 8, 8>(x, w, shift, relu, y, B, Cin, Cout, D, H, W, st);
+}
+
+int convT3d_fp32(const float *x, const float *w, const float *shift, int relu, const float *skip, float *y, int B,
+                 int Cin, int Cout, int D, int H, int W, cudaStream_t st) {
+    MVS_REQUIRE(D <= 65535, "conv_transpose3d: D too large");
+    if (Cout < 8) {
+        const int cg = Cout;
+        MVS_REQUIRE((long long)B * cg <= 65535, "conv_transpose3d: grid too large");
+        convT3d_fp32_kernel<1, 16><<<dim3(cdiv((long long)H * W, 128), D, B * cg), 128, 0, st>>>(x, w, shift, relu, skip, y,
+                                                                                               Cin, Cout, D, H, W);
+    } else {
+        const int cg = cdiv(Cout, 8);
+        MVS_REQUIRE((long long)B * cg <= 65535, "conv_transpose3d: grid too large");
+        convT3d_fp32_kernel<8, 16><<<dim3(cdiv((long long)H * W, 128), D, B * cg), 128, 0, st>>>(x, w, shift, relu, skip, y,
+                                                                                               Cin, Cout, D, H, W);
+    }
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+extern "C" int mvs_conv3d_bn_relu(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin,
+                                  int Cout, int D, int H, int W, int stride, void *stream) {
+    MVS_REQUIRE(x && w && shift && y, "null pointer argument");
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    MVS_REQUIRE(stride == 1 || stride == 2, "conv3d: stride must be 1 or 2, got %d", stride);
+    return conv3d_fp32(x, w, shift, relu, y, B, Cin, Cout, D, H, W, stride, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_conv_transpose3d_bn_relu(const float *x, const float *w, const float *shift, int relu,
+                                            const float *skip, float *y, int B, int Cin, int Cout, int D, int H, int W,
+                                            void *stream) {
+    MVS_REQUIRE(x && w && shift && y, "null pointer argument");
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    return convT3d_fp32(x, w, shift, relu, skip, y, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
+}

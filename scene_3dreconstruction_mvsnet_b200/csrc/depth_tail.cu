@@ -1,0 +1,148 @@
+// Depth-axis softmax + depth expectation + 4-plane photometric confidence in one kernel.
+//
+// Replaces, for the reference:
+//   models/mvsnet.py:192-193   F.softmax(cost_reg.squeeze(1), dim=1)
+//   models/module.py:144-147   depth_regression  (sum_d p * depth_values)
+//   models/mvsnet.py:214-218   pad + avg_pool3d(4,1,1)*4 + depth_regression(arange).long() + gather
+// which in the reference are ~8 ATen kernels and five [B,D,H,W] temporaries.
+//
+// HBM-bound: the logits are read exactly once (4*B*D*H*W bytes) and 8*B*H*W bytes are written.
+// A CTA owns 32 consecutive pixels; its 8 warps split the depth axis into 8 slices so every global
+// load is a full 128-byte line (lanes run along x, the contiguous axis) and 8 independent load
+// streams per pixel hide HBM latency.  The logits tile is kept in shared memory between the max
+// pass and the exp/sum pass, exactly the reference's  exp(l - max) / sum  formulation.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace mvs {
+
+constexpr int kSlices = 8;
+
+template <bool CACHE>
+__global__ void __launch_bounds__(32 * kSlices)
+softmax_depth_conf_kernel(const float *__restrict__ logits, const float *__restrict__ depth_values,
+                          float *__restrict__ depth, float *__restrict__ conf, float *__restrict__ prob, int D,
+                          int HW) {
+    extern __shared__ float s_tile[];  // CACHE: [D][32] logits
+    __shared__ float s_red[4][kSlices][32];
+
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * 32 + lane;
+    const bool live = pix < HW;
+    const int dq = (D + kSlices - 1) / kSlices;
+    const int d0 = slice * dq, d1 = min(D, d0 + dq);
+    const float *lp = logits + (size_t)b * D * HW + (live ? pix : 0);
+    const float *dv = depth_values + (size_t)b * D;
+
+    // pass 1: max over depth
+    float m = -FLT_MAX;
+#pragma unroll 8
+    for (int d = d0; d < d1; ++d) {
+        const float l = live ? __ldcs(lp + (size_t)d * HW) : 0.f;
+        if (CACHE) s_tile[d * 32 + lane] = l;
+        m = fmaxf(m, l);
+    }
+    s_red[0][slice][lane] = m;
+    __syncthreads();
+    float M = s_red[0][0][lane];
+#pragma unroll
+    for (int s = 1; s < kSlices; ++s) M = fmaxf(M, s_red[0][s][lane]);
+
+    // pass 2: e = exp(l - M); partial sums of e, e*depth, e*index
+    float se = 0.f, sd = 0.f, si = 0.f;
+#pragma unroll 4
+    for (int d = d0; d < d1; ++d) {
+        const float l = CACHE ? s_tile[d * 32 + lane] : (live ? __ldg(lp + (size_t)d * HW) : 0.f);
+        const float e = expf(l - M);
+        if (CACHE) s_tile[d * 32 + lane] = e;
+        se += e;
+        sd = fmaf(e, __ldg(dv + d), sd);
+        si = fmaf(e, (float)d, si);
+    }
+    s_red[1][slice][lane] = se;
+    s_red[2][slice][lane] = sd;
+    s_red[3][slice][lane] = si;
+    __syncthreads();
+    float sum = 0.f, sumd = 0.f, sumi = 0.f;
+#pragma unroll
+    for (int s = 0; s < kSlices; ++s) {  // fixed order: deterministic
+        sum += s_red[1][s][lane];
+        sumd += s_red[2][s][lane];
+        sumi += s_red[3][s][lane];
+    }
+
+    if (slice == 0 && live) {
+        const float idxf = sumi / sum;  // sum_d p[d] * d
+        int i = (int)idxf;              // .long() truncation (mvsnet.py:217)
+        i = min(max(i, 0), D - 1);
+        float c4 = 0.f;
+#pragma unroll
+        for (int k = -1; k <= 2; ++k) {  // p[i-1] + p[i] + p[i+1] + p[i+2], zero padded (mvsnet.py:216)
+            const int kk = i + k;
+            if (kk >= 0 && kk < D) {
+                const float e = CACHE ? s_tile[kk * 32 + lane] : expf(__ldg(lp + (size_t)kk * HW) - M);
+                c4 += e / sum;
+            }
+        }
+        depth[(size_t)b * HW + pix] = sumd / sum;
+        conf[(size_t)b * HW + pix] = c4;
+    }
+    if (prob != nullptr && live) {
+        float *pp = prob + (size_t)b * D * HW + pix;
+        for (int d = d0; d < d1; ++d) {
+            const float e = CACHE ? s_tile[d * 32 + lane] : expf(__ldg(lp + (size_t)d * HW) - M);
+            pp[(size_t)d * HW] = e / sum;
+        }
+    }
+}
+
+__global__ void depth_regression_kernel(const float *__restrict__ p, const float *__restrict__ depth_values,
+                                        int dv_stride, float *__restrict__ out, int D, int HW) {
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const float *pp = p + (size_t)b * D * HW + pix;
+    const float *dv = depth_values + (size_t)b * dv_stride;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; ++d) acc = fmaf(__ldg(pp + (size_t)d * HW), __ldg(dv + d), acc);
+    out[(size_t)b * HW + pix] = acc;
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+extern "C" int mvs_softmax_depth_conf(const float *logits, const float *depth_values, float *depth, float *conf,
+                                      float *prob, int B, int D, int H, int W, void *stream) {
+    MVS_REQUIRE(logits && depth_values && depth && conf, "null pointer argument");
+    MVS_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0, "bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H * W;
+    dim3 grid(cdiv(HW, 32), B);
+    const size_t smem = (size_t)D * 32 * sizeof(float);
+    if (smem <= 96 * 1024) {
+        if (smem > 48 * 1024)
+            MVS_CUDA(cudaFuncSetAttribute(softmax_depth_conf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+        softmax_depth_conf_kernel<true><<<grid, 32 * kSlices, smem, st>>>(logits, depth_values, depth, conf, prob, D, HW);
+    } else {
+        softmax_depth_conf_kernel<false><<<grid, 32 * kSlices, 0, st>>>(logits, depth_values, depth, conf, prob, D, HW);
+    }
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+
+extern "C" int mvs_depth_regression(const float *p, const float *depth_values, int dv_batch_stride, float *out, int B,
+                                    int D, int H, int W, void *stream) {
+    MVS_REQUIRE(p && depth_values && out, "null pointer argument");
+    MVS_REQUIRE(B > 0 && B <= 65535 && D > 0 && H > 0 && W > 0, "bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    MVS_REQUIRE(dv_batch_stride == 0 || dv_batch_stride >= D, "depth_values batch stride must be 0 or >= D");
+    const int HW = H * W;
+    depth_regression_kernel<<<dim3(cdiv(HW, 128), B), 128, 0, (cudaStream_t)stream>>>(p, depth_values, dv_batch_stride,
+                                                                                      out, D, HW);
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}

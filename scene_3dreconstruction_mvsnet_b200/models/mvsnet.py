@@ -1,0 +1,182 @@
+"""Mirror of the reference's models/mvsnet.py: MVSNet.forward(imgs, proj_matrices, depth_values).
+
+Same constructor, same forward signature, same output dict and the same parameter / buffer names
+as the reference (so `load_state_dict` of a reference checkpoint is strict-clean), but the body of
+the forward is the B200 path:
+
+    FeatureNet (cuDNN, out of scope)                              reference mvsnet.py:125
+ -> fused plane-sweep warp + variance volume   [mvs_warp_variance_fwd]      :145-177
+ -> CostRegNet as fused conv+BN+ReLU(+skip) kernels [mvs_costreg_fwd]        :180
+ -> softmax + depth expectation + confidence  [mvs_softmax_depth_conf]      :192-218
+
+In train() mode (or whenever autograd is recording) BatchNorm needs batch statistics and autograd
+needs a graph, so CostRegNet and the softmax run as nn.Modules / torch ops on cuDNN, and only the
+fused warp+variance op (forward and backward kernels) is ours -- exactly the split north_star asks
+for.  The per-view warped volumes are never materialised in either mode.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .module import ConvBnReLU, ConvBnReLU3D, depth_regression, fold_bn, homo_warping  # noqa: F401
+
+
+class FeatureNet(nn.Module):
+    """8-layer 2-D CNN, 3 -> 32 channels at 1/4 resolution (reference mvsnet.py:10-30)."""
+
+    def __init__(self):
+        super().__init__()
+        self.inplanes = 32
+        self.conv0 = ConvBnReLU(3, 8, 3, 1, 1)
+        self.conv1 = ConvBnReLU(8, 8, 3, 1, 1)
+        self.conv2 = ConvBnReLU(8, 16, 5, 2, 2)
+        self.conv3 = ConvBnReLU(16, 16, 3, 1, 1)
+        self.conv4 = ConvBnReLU(16, 16, 3, 1, 1)
+        self.conv5 = ConvBnReLU(16, 32, 5, 2, 2)
+        self.conv6 = ConvBnReLU(32, 32, 3, 1, 1)
+        self.feature = nn.Conv2d(32, 32, 3, 1, 1)
+
+    def forward(self, x):
+        x = self.conv1(self.conv0(x))
+        x = self.conv4(self.conv3(self.conv2(x)))
+        return self.feature(self.conv6(self.conv5(x)))
+
+
+def _up(cin, cout):
+    return nn.Sequential(
+        nn.ConvTranspose3d(cin, cout, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+        nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
+
+
+class CostRegNet(nn.Module):
+    """3-D conv U-Net (reference mvsnet.py:33-73)."""
+
+    _ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = ConvBnReLU3D(32, 8)
+        self.conv1 = ConvBnReLU3D(8, 16, stride=2)
+        self.conv2 = ConvBnReLU3D(16, 16)
+        self.conv3 = ConvBnReLU3D(16, 32, stride=2)
+        self.conv4 = ConvBnReLU3D(32, 32)
+        self.conv5 = ConvBnReLU3D(32, 64, stride=2)
+        self.conv6 = ConvBnReLU3D(64, 64)
+        self.conv7 = _up(64, 32)
+        self.conv9 = _up(32, 16)
+        self.conv11 = _up(16, 8)
+        self.prob = nn.Conv3d(8, 1, 3, stride=1, padding=1)
+        self._folded = None
+        self._folded_key = None
+
+    def forward(self, x):
+        """Autograd / training path (cuDNN)."""
+        conv0 = self.conv0(x)
+        conv2 = self.conv2(self.conv1(conv0))
+        conv4 = self.conv4(self.conv3(conv2))
+        x = self.conv6(self.conv5(conv4))
+        x = conv4 + self.conv7(x)
+        x = conv2 + self.conv9(x)
+        x = conv0 + self.conv11(x)
+        return self.prob(x)
+
+    def folded_params(self):
+        """[(weight, shift)] x 11 with eval-mode BN folded in; cached until a parameter or buffer
+        is modified in place or replaced (load_state_dict, optimizer step, .to())."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._folded is None or key != self._folded_key:
+            with torch.no_grad():
+                out = [getattr(self, n).folded() for n in self._ORDER]
+                for n in ("conv7", "conv9", "conv11"):
+                    seq = getattr(self, n)
+                    out.append(fold_bn(seq[0].weight, seq[1], out_dim=1))
+                out.append((self.prob.weight.detach().contiguous(), self.prob.bias.detach().contiguous()))
+            self._folded, self._folded_key = out, key
+        return self._folded
+
+    def infer(self, volume, precision="fp32"):
+        """Inference path: 11 fused CUDA launches, logits [B,D,h,w]."""
+        return ops.cost_regularization(volume, self.folded_params(), precision)
+
+
+class MVSNet(nn.Module):
+    """Drop-in for the reference MVSNet (mvsnet.py:91-239).
+
+    refine: kept for constructor compatibility.  The reference's RefineNet is dead code (F.cat does
+            not exist, mvsnet.py:85; eval hard-codes refine=False, eval.py:308); refine=True raises.
+    debug:  the reference's cv2.imshow bitmask; accepted and ignored (needs a display).
+    precision: "fp32" (default, matches the reference to fp32 rounding) or "bf16" (tensor cores).
+    """
+
+    def __init__(self, refine=True, debug=0, precision="fp32"):
+        super().__init__()
+        self.refine = refine
+        self.debug = debug
+        self.precision = precision
+        self.feature = FeatureNet()
+        self.cost_regularization = CostRegNet()
+        self.stage_events = None  # set to a list to collect per-stage CUDA events (bench.py roofline legs)
+        if self.refine:
+            raise NotImplementedError(
+                "refine=True: the reference RefineNet cannot run (F.cat, mvsnet.py:85); use refine=False like "
+                "eval.py:308 and scripts/train_DTU.sh")
+
+    # -- feature extraction ----------------------------------------------------------------------
+    def extract_features(self, imgs):
+        """imgs [B,V,3,H,W] -> [B,V,32,H/4,W/4].  Eval: one batched pass over all views (identical
+        math with running BN statistics).  Train: one pass per view, like the reference
+        (mvsnet.py:125), because train-mode BN statistics are per call."""
+        B, V = imgs.shape[:2]
+        if self.training:
+            return torch.stack([self.feature(img) for img in torch.unbind(imgs, 1)], 1)
+        f = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        return f.view(B, V, *f.shape[1:])
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        if imgs.shape[1] != proj_matrices.shape[1]:
+            raise AssertionError("Different number of images and projection matrices")  # mvsnet.py:106
+        if not imgs.is_cuda:
+            raise RuntimeError("MVSNet (B200 build) runs on CUDA devices only; there is no CPU fallback")
+        marks = [] if self.stage_events is not None else None
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(imgs.device))
+                marks.append((name, e))
+
+        mark("start")
+        fea = self.extract_features(imgs)
+        mark("features")
+        proj_matrices = proj_matrices.float()
+        depth_values = depth_values.float()
+        volume_variance = ops.warp_variance(fea, proj_matrices, depth_values)
+        mark("warp_variance")
+
+        if not torch.is_grad_enabled():
+            if self.training:  # train-mode BN under no_grad (e.g. BN re-calibration): keep nn.Module semantics
+                logits = self.cost_regularization(volume_variance).squeeze(1)
+            else:
+                logits = self.cost_regularization.infer(volume_variance, self.precision)
+            mark("cost_regularization")
+            depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
+            mark("depth_tail")
+            if marks is not None:
+                self.stage_events.append(marks)
+            return {"depth": depth, "photometric_confidence": photometric_confidence}
+
+        # autograd path (training): graph through cuDNN CostRegNet and torch softmax, ours elsewhere
+        logits = self.cost_regularization(volume_variance).squeeze(1)
+        prob_volume = F.softmax(logits, dim=1)
+        depth = depth_regression(prob_volume, depth_values)
+        with torch.no_grad():
+            _, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
+        return {"depth": depth, "photometric_confidence": photometric_confidence}
+
+
+def mvsnet_loss(depth_est, depth_gt, mask):
+    """Smooth-L1 over valid pixels (reference mvsnet.py:242-244)."""
+    mask = mask > 0.5
+    return F.smooth_l1_loss(depth_est[mask], depth_gt[mask], reduction="mean")

@@ -1,0 +1,277 @@
+"""Torch-tensor front end of the C ABI: device memory, streams and autograd plumbing only.
+
+Every function here takes CUDA fp32 tensors, hands raw device pointers and the current CUDA
+stream to libmvsnet_b200.so, and returns freshly allocated tensors.  Nothing is computed in
+PyTorch on the forward path; non-CUDA inputs raise (there is no CPU fallback).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _prep(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: the B200 path has no CPU fallback (move inputs to a CUDA device)"
+                           % (name, t.device))
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError("%s must have %d dims, got shape %s" % (name, ndim, tuple(t.shape)))
+    return t.detach().contiguous()
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a2) homo_warping                                             reference models/module.py:96-139
+# ------------------------------------------------------------------------------------------------
+def homo_warping_fwd(src_fea, src_proj, ref_proj, depth_values):
+    src_fea = _prep(src_fea, "src_fea", 4)
+    src_proj = _prep(src_proj, "src_proj", 3)
+    ref_proj = _prep(ref_proj, "ref_proj", 3)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    B, C, H, W = src_fea.shape
+    D = depth_values.shape[1]
+    if src_proj.shape != (B, 4, 4) or ref_proj.shape != (B, 4, 4) or depth_values.shape[0] != B:
+        raise RuntimeError("homo_warping: batch/shape mismatch: src_fea %s src_proj %s ref_proj %s depth_values %s"
+                           % (tuple(src_fea.shape), tuple(src_proj.shape), tuple(ref_proj.shape),
+                              tuple(depth_values.shape)))
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=src_fea.device)
+    with torch.cuda.device(src_fea.device):
+        rc = _lib.load().mvs_homo_warping(_ptr(src_fea), _ptr(src_proj), _ptr(ref_proj), _ptr(depth_values), _ptr(out),
+                                          B, C, D, H, W, _stream(src_fea))
+    _lib.check(rc, "mvs_homo_warping")
+    return out
+
+
+def homo_warping_bwd(grad_out, src_proj, ref_proj, depth_values, H, W):
+    grad_out = _prep(grad_out, "grad_out", 5)
+    B, C, D = grad_out.shape[:3]
+    grad_src = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        rc = _lib.load().mvs_homo_warping_bwd(_ptr(grad_out), _ptr(src_proj), _ptr(ref_proj), _ptr(depth_values),
+                                              _ptr(grad_src), B, C, D, H, W, _stream(grad_out))
+    _lib.check(rc, "mvs_homo_warping_bwd")
+    return grad_src
+
+
+class _HomoWarping(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_fea, src_proj, ref_proj, depth_values):
+        sp, rp, dv = (_prep(src_proj, "src_proj", 3), _prep(ref_proj, "ref_proj", 3),
+                      _prep(depth_values, "depth_values", 2))
+        ctx.save_for_backward(sp, rp, dv)
+        ctx.hw = src_fea.shape[2:]
+        return homo_warping_fwd(src_fea, sp, rp, dv)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sp, rp, dv = ctx.saved_tensors
+        # gradient flows to the features only: the grid is built under no_grad in the reference (module.py:106)
+        return homo_warping_bwd(grad_out, sp, rp, dv, ctx.hw[0], ctx.hw[1]), None, None, None
+
+
+def homo_warping(src_fea, src_proj, ref_proj, depth_values):
+    if torch.is_grad_enabled() and src_fea.requires_grad:
+        return _HomoWarping.apply(src_fea, src_proj, ref_proj, depth_values)
+    return homo_warping_fwd(src_fea, src_proj, ref_proj, depth_values)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a2+a3, a8) fused warp + variance                              reference models/mvsnet.py:145-177
+# ------------------------------------------------------------------------------------------------
+def warp_variance_fwd(fea, proj, depth_values):
+    fea = _prep(fea, "features", 5)
+    proj = _prep(proj, "proj_matrices", 4)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    B, V, C, H, W = fea.shape
+    D = depth_values.shape[1]
+    if proj.shape != (B, V, 4, 4):
+        raise RuntimeError("Different number of images and projection matrices: features %s proj %s"
+                           % (tuple(fea.shape), tuple(proj.shape)))
+    if depth_values.shape[0] != B:
+        raise RuntimeError("depth_values batch %d != %d" % (depth_values.shape[0], B))
+    lib = _lib.load()
+    var = torch.empty((B, C, D, H, W), dtype=torch.float32, device=fea.device)
+    ws = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
+    with torch.cuda.device(fea.device):
+        rc = lib.mvs_warp_variance_fwd(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(var), _ptr(ws), B, V, C, D, H, W,
+                                       _stream(fea))
+    _lib.check(rc, "mvs_warp_variance_fwd")
+    return var
+
+
+def warp_variance_bwd(grad_var, fea, proj, depth_values):
+    grad_var = _prep(grad_var, "grad_var", 5)
+    B, V, C, H, W = fea.shape
+    D = depth_values.shape[1]
+    lib = _lib.load()
+    grad_fea = torch.empty_like(fea)
+    ws = _ws(lib.mvs_warp_variance_bwd_workspace_bytes(B, V, C, H, W), fea.device)
+    with torch.cuda.device(fea.device):
+        rc = lib.mvs_warp_variance_bwd(_ptr(grad_var), _ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(grad_fea),
+                                       _ptr(ws), B, V, C, D, H, W, _stream(fea))
+    _lib.check(rc, "mvs_warp_variance_bwd")
+    return grad_fea
+
+
+class _WarpVariance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fea, proj, depth_values):
+        f, p, dv = _prep(fea, "features", 5), _prep(proj, "proj_matrices", 4), _prep(depth_values, "depth_values", 2)
+        ctx.save_for_backward(f, p, dv)  # features only: no warped volume is kept alive for backward
+        return warp_variance_fwd(f, p, dv)
+
+    @staticmethod
+    def backward(ctx, grad_var):
+        f, p, dv = ctx.saved_tensors
+        return warp_variance_bwd(grad_var, f, p, dv), None, None
+
+
+def warp_variance(fea, proj, depth_values):
+    """fea [B,V,32,h,w] (view 0 = reference view) -> variance cost volume [B,32,D,h,w]."""
+    if torch.is_grad_enabled() and fea.requires_grad:
+        return _WarpVariance.apply(fea, proj, depth_values)
+    return warp_variance_fwd(fea, proj, depth_values)
+
+
+# ------------------------------------------------------------------------------------------------
+# (a4) CostRegNet                                    reference models/mvsnet.py:33-73, module.py:26-33
+# ------------------------------------------------------------------------------------------------
+def conv3d_bn_relu(x, w_folded, shift, relu=True, stride=1):
+    x = _prep(x, "x", 5)
+    w_folded = _prep(w_folded, "weight", 5)
+    shift = _prep(shift, "shift", 1)
+    B, Cin, D, H, W = x.shape
+    Cout = w_folded.shape[0]
+    if w_folded.shape != (Cout, Cin, 3, 3, 3) or shift.shape[0] != Cout:
+        raise RuntimeError("conv3d: weight %s / shift %s do not match input %s" % (tuple(w_folded.shape),
+                                                                                   tuple(shift.shape), tuple(x.shape)))
+    Do, Ho, Wo = [(n - 1) // stride + 1 for n in (D, H, W)]
+    y = torch.empty((B, Cout, Do, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mvs_conv3d_bn_relu(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(y), B, Cin, Cout, D, H,
+                                            W, stride, _stream(x))
+    _lib.check(rc, "mvs_conv3d_bn_relu")
+    return y
+
+
+def conv_transpose3d_bn_relu(x, w_folded, shift, relu=True, skip=None):
+    x = _prep(x, "x", 5)
+    w_folded = _prep(w_folded, "weight", 5)
+    shift = _prep(shift, "shift", 1)
+    B, Cin, D, H, W = x.shape
+    Cout = w_folded.shape[1]
+    if w_folded.shape != (Cin, Cout, 3, 3, 3) or shift.shape[0] != Cout:
+        raise RuntimeError("conv_transpose3d: weight %s does not match input %s" % (tuple(w_folded.shape),
+                                                                                    tuple(x.shape)))
+    if skip is not None:
+        skip = _prep(skip, "skip", 5)
+        if skip.shape != (B, Cout, 2 * D, 2 * H, 2 * W):
+            raise RuntimeError("conv_transpose3d: skip shape %s != output shape" % (tuple(skip.shape),))
+    y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mvs_conv_transpose3d_bn_relu(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(skip), _ptr(y),
+                                                      B, Cin, Cout, D, H, W, _stream(x))
+    _lib.check(rc, "mvs_conv_transpose3d_bn_relu")
+    return y
+
+
+def cost_regularization(volume, folded, precision="fp32"):
+    """volume [B,32,D,h,w]; folded = list of 11 (weight, shift) CUDA tensors in the order
+    conv0..conv6, conv7, conv9, conv11, prob  ->  logits [B,D,h,w]."""
+    volume = _prep(volume, "volume", 5)
+    B, C, D, H, W = volume.shape
+    if C != 32:
+        raise RuntimeError("cost_regularization expects 32 channels, got %d" % C)
+    if len(folded) != _lib.COSTREG_LAYERS:
+        raise RuntimeError("cost_regularization expects %d folded layers" % _lib.COSTREG_LAYERS)
+    prec = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
+    lib = _lib.load()
+    params = _lib.CostRegParams()
+    keep = []
+    for i, (w, s) in enumerate(folded):
+        w, s = _prep(w, "weight%d" % i), _prep(s, "shift%d" % i)
+        keep += [w, s]
+        params.w[i] = w.data_ptr()
+        params.shift[i] = s.data_ptr()
+    nbytes = lib.mvs_costreg_workspace_bytes(B, D, H, W, prec)
+    if nbytes == 0:
+        raise RuntimeError("CostRegNet needs D, H, W divisible by 8 (got D=%d H=%d W=%d)" % (D, H, W))
+    ws = _ws(nbytes, volume.device)
+    logits = torch.empty((B, D, H, W), dtype=torch.float32, device=volume.device)
+    with torch.cuda.device(volume.device):
+        rc = lib.mvs_costreg_fwd(_ptr(volume), ctypes.byref(params), _ptr(logits), _ptr(ws), B, D, H, W, prec,
+                                 _stream(volume))
+    _lib.check(rc, "mvs_costreg_fwd")
+    return logits
+
+
+# ------------------------------------------------------------------------------------------------
+# (a5-a7) softmax + depth + confidence     reference models/mvsnet.py:192-218, module.py:144-147
+# ------------------------------------------------------------------------------------------------
+def softmax_depth_conf(logits, depth_values, want_prob=False):
+    logits = _prep(logits, "logits", 4)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    B, D, H, W = logits.shape
+    if depth_values.shape != (B, D):
+        raise RuntimeError("depth_values %s does not match logits %s" % (tuple(depth_values.shape), tuple(logits.shape)))
+    depth = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+    conf = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+    prob = torch.empty_like(logits) if want_prob else None
+    with torch.cuda.device(logits.device):
+        rc = _lib.load().mvs_softmax_depth_conf(_ptr(logits), _ptr(depth_values), _ptr(depth), _ptr(conf), _ptr(prob), B,
+                                                D, H, W, _stream(logits))
+    _lib.check(rc, "mvs_softmax_depth_conf")
+    return (depth, conf, prob) if want_prob else (depth, conf)
+
+
+def depth_regression_fwd(p, depth_values):
+    p = _prep(p, "p", 4)
+    depth_values = _prep(depth_values, "depth_values")
+    B, D, H, W = p.shape
+    if depth_values.dim() == 1 and depth_values.shape[0] == D:
+        stride = 0
+    elif depth_values.dim() == 2 and depth_values.shape == (B, D):
+        stride = D
+    else:
+        raise RuntimeError("depth_values must be [B,D] or [D]; got %s for p %s" % (tuple(depth_values.shape),
+                                                                                tuple(p.shape)))
+    out = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = _lib.load().mvs_depth_regression(_ptr(p), _ptr(depth_values), stride, _ptr(out), B, D, H, W, _stream(p))
+    _lib.check(rc, "mvs_depth_regression")
+    return out
+
+
+class _DepthRegression(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, depth_values):
+        ctx.save_for_backward(depth_values)
+        return depth_regression_fwd(p, depth_values)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dv,) = ctx.saved_tensors
+        dvb = dv.view(1, -1, 1, 1) if dv.dim() == 1 else dv.view(dv.shape[0], dv.shape[1], 1, 1)
+        return g.unsqueeze(1) * dvb, None
+
+
+def depth_regression(p, depth_values):
+    if torch.is_grad_enabled() and p.requires_grad:
+        return _DepthRegression.apply(p, depth_values)
+    return depth_regression_fwd(p, depth_values)

@@ -1,0 +1,108 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side argument
+checking, the nn.Module surface (state-dict compatibility, BN folding), view sharding."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from scene_3dreconstruction_mvsnet_b200 import _lib, ops
+from scene_3dreconstruction_mvsnet_b200.models import MVSNet, mvsnet_loss
+from scene_3dreconstruction_mvsnet_b200.models.module import fold_bn
+
+
+def test_header_symbols_are_exported_and_bound():
+    """Every function declared in include/mvsnet_b200.h is exported by the .so and bound in _lib.py."""
+    hdr = open(os.path.join(ROOT, "include", "mvsnet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mvs_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.mvs_abi_version() == 1
+    assert lib.mvs_arch() == b"sm_100a"
+
+
+def test_workspace_queries_no_gpu():
+    lib = _lib.load()
+    n = lib.mvs_warp_variance_workspace_bytes(1, 5, 32, 288, 400)
+    assert n >= 4 * 4 * 288 * 400 * 32
+    assert lib.mvs_costreg_workspace_bytes(1, 192, 288, 400, 0) == int(23.75 * 192 * 288 * 400) * 4
+    assert lib.mvs_costreg_workspace_bytes(1, 190, 288, 400, 0) == 0  # D % 8 != 0
+    # argument validation happens before any CUDA call
+    rc = lib.mvs_warp_variance_fwd(None, None, None, None, None, 1, 3, 32, 8, 8, 8, None)
+    assert rc == -1 and b"null" in lib.mvs_last_error()
+
+
+def test_state_dict_keys_match_reference(weights):
+    m = MVSNet(refine=False)
+    assert set(m.state_dict().keys()) == set(weights.keys())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 338129
+    # DataParallel-style prefix round trip (reference train.py:141, eval.py:315)
+    sd = {"module." + k: v for k, v in m.state_dict().items()}
+    torch.nn.DataParallel(MVSNet(refine=False)).load_state_dict(sd, strict=True)
+
+
+def test_refine_true_is_rejected():
+    with pytest.raises(NotImplementedError):
+        MVSNet(refine=True)
+
+
+def test_no_cpu_fallback():
+    m = MVSNet(refine=False).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 3, 32, 32), torch.zeros(1, 3, 4, 4), torch.zeros(1, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.homo_warping(torch.zeros(1, 32, 8, 8), torch.zeros(1, 4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 4))
+    with pytest.raises(AssertionError):
+        m(torch.zeros(1, 3, 3, 32, 32), torch.zeros(1, 2, 4, 4), torch.zeros(1, 8))
+
+
+def test_bn_folding_matches_unfolded(weights):
+    m = MVSNet(refine=False)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    m.eval()
+    layer = m.cost_regularization.conv2
+    x = torch.randn(1, 16, 4, 6, 8)
+    w, shift = layer.folded()
+    y = torch.relu(torch.nn.functional.conv3d(x, w, None, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    assert torch.allclose(y, layer(x), atol=1e-5)
+    seq = m.cost_regularization.conv9
+    w, shift = fold_bn(seq[0].weight, seq[1], out_dim=1)
+    x = torch.randn(1, 32, 2, 3, 4)
+    y = torch.relu(torch.nn.functional.conv_transpose3d(x, w, None, stride=2, padding=1, output_padding=1) +
+                   shift.view(1, -1, 1, 1, 1))
+    assert torch.allclose(y, seq(x), atol=1e-5)
+    # cache invalidation on in-place parameter update
+    f1 = m.cost_regularization.folded_params()
+    assert m.cost_regularization.folded_params() is f1
+    with torch.no_grad():
+        m.cost_regularization.conv0.conv.weight.mul_(2.0)
+    assert m.cost_regularization.folded_params() is not f1
+
+
+def test_mvsnet_loss_matches_definition():
+    g = torch.Generator().manual_seed(0)
+    est, gt = torch.randn(2, 5, 7, generator=g) * 3, torch.randn(2, 5, 7, generator=g)
+    mask = (torch.rand(2, 5, 7, generator=g) > 0.4).float()
+    d = (est - gt)[mask > 0.5].abs()
+    ref = torch.where(d < 1, 0.5 * d * d, d - 0.5).mean()
+    assert torch.allclose(mvsnet_loss(est, gt, mask), ref, atol=1e-6)
+
+
+def test_oracle_is_not_imported_by_product():
+    import subprocess
+    import sys
+    code = ("import sys; import scene_3dreconstruction_mvsnet_b200.models, scene_3dreconstruction_mvsnet_b200.ops, "
+            "models; bad=[m for m in sys.modules if m.split('.')[0]=='oracle']; assert not bad, bad")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scene_3dreconstruction_mvsnet_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/mvsnet_oracle.c:orc_compose_homography", ""), f
