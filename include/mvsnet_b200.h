@@ -93,6 +93,17 @@ int mvs_conv3d_bn_relu(const float *x, const float *w, const float *shift, int r
 int mvs_conv_transpose3d_bn_relu(const float *x, const float *w, const float *shift, int relu, const float *skip,
                                  float *y, int B, int Cin, int Cout, int D, int H, int W, void *stream);
 
+/* Tensor-core variants of the two building blocks (tcgen05 implicit GEMM, bf16 operands, fp32
+ * accumulate; same fp32 NCDHW interface, converted internally).  Cin % 8 == 0, Cout % 8 == 0 or 1. */
+int mvs_conv3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin,
+                          int Cout, int D, int H, int W, int stride, void *stream);
+int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, const float *skip,
+                                    float *y, int B, int Cin, int Cout, int D, int H, int W, void *stream);
+
+/* Diagnostics (no GPU needed): describes the tile/ring/grid plan of one tensor-core layer.
+ * kind: 0 = conv stride 1, 1 = conv stride 2, 2 = transposed conv. */
+int mvs_tc_plan_describe(int kind, int B, int Cin, int Cout, int D, int H, int W, int num_sms, char *buf, int buflen);
+
 /* Whole CostRegNet.forward (mvsnet.py:64-73), eval mode.  Layer order in the arrays:
  * conv0..conv6, conv7, conv9, conv11, prob.  volume [B,32,D,H,W] -> logits [B,D,H,W]. */
 #define MVS_COSTREG_LAYERS 11

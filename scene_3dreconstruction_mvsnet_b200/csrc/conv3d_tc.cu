@@ -1,13 +1,717 @@
-// CostRegNet tensor-core path (tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate).
-// Placeholder until the kernels land: the entry points report MVS_ERR_UNSUPPORTED.
+// CostRegNet on the 5th-generation tensor cores: one warp-specialised implicit-GEMM kernel
+// (TMA -> shared-memory plane ring -> tcgen05.mma with TMEM accumulators -> fused epilogue) that
+// covers all three layer kinds of models/mvsnet.py:33-73 through a per-layer "op table":
+//   * Conv3d k3 s1 p1 (+BN+ReLU)                      conv0, conv2, conv4, conv6, prob
+//   * Conv3d k3 s2 p1 (+BN+ReLU)                      conv1, conv3, conv5
+//   * ConvTranspose3d k3 s2 p1 op1 (+BN+ReLU, +skip)  conv7, conv9, conv11  (8 output-parity classes)
+//
+// Activations live in HBM as bf16 "CP8":  [B][C/8][D][H][W][8]  -- channel chunks of 8 (16 bytes)
+// are the innermost unit, so (a) a TMA box {8ch, P cols, R rows, 1 plane, C/8 chunks} lands in shared
+// memory as [chunk][row][col][8ch], i.e. consecutive voxels 16 bytes apart, which is exactly the
+// no-swizzle K-major UMMA operand layout (8-row core matrices of 16-byte rows); (b) im2col is free:
+// the A operand of filter tap (kd,kh,kw) is the same shared-memory plane addressed at a byte offset
+// (kh*P + kw)*16, and a run of 128 consecutive flattened (row, col) positions is one M=128 tile;
+// (c) zero padding is TMA out-of-bounds fill; (d) stride-2 layers load the four (y,x)-parity
+// sub-planes with elementStrides = 2 so that every tap is again a unit-stride operand; (e) the
+// epilogue thread of TMEM lane m owns output voxel m and writes one 16-byte chunk per 8 output
+// channels -- fully coalesced across the warp.
+//
+// A CTA (persistent, one per SM) walks a column of the volume along z: each new input plane is
+// loaded exactly once into a ring of NSLOT planes and reused by the 3 (or 2) z-steps that need it.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue.
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mvs {
 
-size_t costreg_tc_workspace_bytes(int, int, int, int) { return 0; }
+tmap_encode_fn get_tmap_encode() {
+    static tmap_encode_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)p;
+    });
+    return fn;
+}
 
-int costreg_tc(const float *, const mvs_costreg_params *, float *, void *, int, int, int, int, cudaStream_t) {
-    return set_error(MVS_ERR_UNSUPPORTED, "MVS_PRECISION_BF16 (tcgen05 path) is not built in this version");
+constexpr int kMaxOps = 112;
+constexpr int kMaxAcc = 8;
+constexpr int kTcThreads = 192;
+
+struct TcOp {
+    uint32_t a_off;     // byte offset of the A operand inside its ring plane (sub-plane + tap + chunk pair)
+    uint32_t lbo;       // byte distance between the two 16-byte K chunks of this K=16 instruction
+    uint16_t widx;      // index of the packed B block
+    uint8_t plane_rel;  // which of the NEED planes of this step
+    uint8_t acc;        // accumulator group
+};
+
+struct TcLayer {
+    // tile space (conv: output voxels; convT: input = low-resolution voxels)
+    int B, Dt, Ht, Wt;
+    int tiles_x, tiles_y, zsegs, zseg_len, ngroups, n_items;
+    int TXB, TY, P, MT;
+    // ring
+    int nsub, chunks, sub_bytes, sub_stride, slot_bytes, need, adv, nslot, pz0, zscale;
+    int in_scale, sub_xoff[4], sub_yoff[4];
+    // gemm
+    int nops, nacc, npad, wbytes_group;
+    int acc_first[kMaxAcc + 1];  // op range of each accumulator group
+    // epilogue
+    int out_scale, acc_pz[kMaxAcc], acc_py[kMaxAcc], acc_px[kMaxAcc];
+    int cout_group, cout_total, relu, out_f32;
+    int Dout, Hout, Wout;
+    void *out;
+    const uint4 *skip;
+    const float *shift;
+    const uint4 *wpacked;
+    TcOp ops[kMaxOps];
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // [0,256): mbarriers + tmem address; then packed weights; then the plane ring (128-byte aligned)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    const uint32_t bar_base = ptx::smem_u32(smem);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
+    uint8_t *w_smem = smem + 256;
+    const uint32_t w_base = bar_base + 256;
+    const uint32_t ring_base = (w_base + L.wbytes_group + 127u) & ~127u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncols_buf = L.nacc * L.MT * NPAD;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * ncols_buf) tmem_cols <<= 1;
+
+    // ---- one-time setup
+    // Items are ordered so that a CTA keeps the same n-group for all of its items: group = blockIdx.x % ngroups.
+    const int group = blockIdx.x % L.ngroups;
+    {
+        const uint4 *src = L.wpacked + (size_t)group * (L.wbytes_group / 16);
+        uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
+        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < L.nslot; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(tfull_bar(b), 1);
+            ptx::mbar_init(tempty_bar(b), 4);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmap);
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
+    ptx::fence_proxy_async_smem();  // weights were written with generic stores, read by the MMA (async proxy)
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int items_per_group = L.n_items / L.ngroups;
+    const int cta_in_group = blockIdx.x / L.ngroups;
+    const int ctas_per_group = (gridDim.x - group + L.ngroups - 1) / L.ngroups;
+
+    auto decode = [&](int it, int &b, int &x0, int &y0, int &zs, int &T) {
+        int r = it;
+        const int zseg = r % L.zsegs; r /= L.zsegs;
+        const int tx = r % L.tiles_x; r /= L.tiles_x;
+        const int ty = r % L.tiles_y; r /= L.tiles_y;
+        b = r;
+        x0 = tx * L.TXB;
+        y0 = ty * L.TY;
+        zs = zseg * L.zseg_len;
+        T = min(L.zseg_len, L.Dt - zs);
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            const uint32_t tx_bytes = (uint32_t)L.nsub * L.sub_bytes;
+            for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
+                int b, x0, y0, zs, T;
+                decode(it, b, x0, y0, zs, T);
+                const int nplanes = L.adv * (T - 1) + L.need;
+                for (int j = 0; j < nplanes; ++j, ++g) {
+                    const int slot = g % L.nslot;
+                    ptx::mbar_wait(empty_bar(slot), ((g / L.nslot) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(full_bar(slot), tx_bytes);
+                    const int pz = L.zscale * zs + L.pz0 + j;
+                    for (int s = 0; s < L.nsub; ++s)
+                        ptx::tma_load_5d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot), 0,
+                                         L.in_scale * x0 + L.sub_xoff[s], L.in_scale * y0 + L.sub_yoff[s], pz,
+                                         b * L.chunks);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_bf16_m128(NPAD);
+            uint32_t g = 0, st = 0;
+            for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
+                int b, x0, y0, zs, T;
+                decode(it, b, x0, y0, zs, T);
+                for (int t = 0; t < T; ++t, ++st) {
+                    const uint32_t g0 = g + (uint32_t)L.adv * t;
+                    for (int r = 0; r < L.need; ++r) {
+                        const uint32_t gi = g0 + r;
+                        ptx::mbar_wait(full_bar(gi % L.nslot), (gi / L.nslot) & 1);
+                    }
+                    const uint32_t buf = st & 1;
+                    ptx::mbar_wait(tempty_bar(buf), ((st >> 1) & 1) ^ 1);
+                    ptx::tcgen05_fence_after();
+                    for (int mt = 0; mt < L.MT; ++mt) {
+                        for (int a = 0; a < L.nacc; ++a) {
+                            const uint32_t d = tmem_base + buf * ncols_buf + (a * L.MT + mt) * NPAD;
+                            for (int o = L.acc_first[a]; o < L.acc_first[a + 1]; ++o) {
+                                const TcOp op = L.ops[o];
+                                const uint32_t slot = (g0 + op.plane_rel) % L.nslot;
+                                const uint32_t a_addr = ring_base + slot * L.slot_bytes + op.a_off + mt * 2048;
+                                const uint64_t ad = ptx::make_smem_desc(a_addr, op.lbo, 128);
+                                const uint64_t bd = ptx::make_smem_desc(w_base + op.widx * (NPAD * 32), NPAD * 16, 128);
+                                ptx::mma_bf16_ss(d, ad, bd, idesc, o != L.acc_first[a]);
+                            }
+                        }
+                    }
+                    for (int r = 0; r < L.adv; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
+                    if (t == T - 1)
+                        for (int r = L.adv; r < L.need; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
+                    ptx::tcgen05_commit(tfull_bar(buf));
+                }
+                g += (uint32_t)(L.adv * (T - 1) + L.need);
+            }
+        }
+    } else {
+        // ================= epilogue (4 warps = 128 TMEM lanes) =================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const uint4 *skip = L.skip;
+        uint32_t st = 0;
+        for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
+            int b, x0, y0, zs, T;
+            decode(it, b, x0, y0, zs, T);
+            for (int t = 0; t < T; ++t, ++st) {
+                const uint32_t buf = st & 1;
+                ptx::mbar_wait(tfull_bar(buf), (st >> 1) & 1);
+                ptx::tcgen05_fence_after();
+                const int z = zs + t;
+                for (int mt = 0; mt < L.MT; ++mt) {
+                    const int pos = mt * 128 + q * 32 + lane;
+                    const int y = pos / L.P, x = pos - y * L.P;
+                    const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
+                    for (int a = 0; a < L.nacc; ++a) {
+                        const uint32_t taddr =
+                            tmem_base + ((uint32_t)(q * 32) << 16) + buf * ncols_buf + (a * L.MT + mt) * NPAD;
+                        const int oz = L.out_scale * z + L.acc_pz[a];
+                        const int oy = L.out_scale * (y0 + y) + L.acc_py[a];
+                        const int ox = L.out_scale * (x0 + x) + L.acc_px[a];
+                        const size_t vox = ((size_t)oz * L.Hout + oy) * L.Wout + ox;
+                        const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
+#pragma unroll
+                        for (int c8 = 0; c8 < NPAD / 8; ++c8) {
+                            if (c8 * 8 >= L.cout_group) break;   // padded accumulator columns (warp-uniform)
+                            uint32_t r[8];
+                            ptx::tmem_ld_x8(taddr + c8 * 8, r);  // warp-collective: outside the validity branch
+                            ptx::tmem_ld_wait();
+                            const int co = group * L.cout_group + c8 * 8;  // first real output channel of this chunk
+                            if (!valid) continue;
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int ch = min(co + e, L.cout_total - 1);
+                                v[e] = __uint_as_float(r[e]) + __ldg(L.shift + ch);
+                                if (L.relu) v[e] = fmaxf(v[e], 0.f);
+                            }
+                            if (L.out_f32) {  // single-channel fp32 output (the prob layer): [B][D][H][W]
+                                reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
+                            } else {
+                                const size_t o16 = ((size_t)b * (L.cout_total / 8) + co / 8) * plane + vox;
+                                if (skip != nullptr) {  // skip + relu(bn(convT))  (mvsnet.py:69-71)
+                                    const uint4 s = __ldg(skip + o16);
+                                    const __nv_bfloat162 *sp = reinterpret_cast<const __nv_bfloat162 *>(&s);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __bfloat1622float2(sp[e]);
+                                        v[2 * e] += f.x;
+                                        v[2 * e + 1] += f.y;
+                                    }
+                                }
+                                uint4 pk;
+                                pk.x = pack_bf16x2(v[0], v[1]);
+                                pk.y = pack_bf16x2(v[2], v[3]);
+                                pk.z = pack_bf16x2(v[4], v[5]);
+                                pk.w = pack_bf16x2(v[6], v[7]);
+                                reinterpret_cast<uint4 *>(L.out)[o16] = pk;
+                            }
+                        }
+                    }
+                }
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+            }
+        }
+    }
+
+    // ---- teardown
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+    (void)bars;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion and weight packing kernels
+// ------------------------------------------------------------------------------------------------
+// fp32 NCDHW [B][C][N] -> bf16 CP8 [B][C/8][N][8]     (N = D*H*W voxels)
+__global__ void ncdhw_to_cp8_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int C, size_t N) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int bc = blockIdx.y;  // b * (C/8) + chunk
+    if (v >= N) return;
+    const int b = bc / (C / 8), chunk = bc % (C / 8);
+    const float *src = in + ((size_t)b * C + chunk * 8) * N + v;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __ldcs(src + (size_t)e * N);
+    uint4 pk;
+    pk.x = pack_bf16x2(f[0], f[1]);
+    pk.y = pack_bf16x2(f[2], f[3]);
+    pk.z = pack_bf16x2(f[4], f[5]);
+    pk.w = pack_bf16x2(f[6], f[7]);
+    out[(size_t)bc * N + v] = pk;
+}
+
+// bf16 CP8 -> fp32 NCDHW (tests / mixed-precision fallbacks)
+__global__ void cp8_to_ncdhw_kernel(const uint4 *__restrict__ in, float *__restrict__ out, int C, size_t N) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int bc = blockIdx.y;
+    if (v >= N) return;
+    const int b = bc / (C / 8), chunk = bc % (C / 8);
+    const uint4 pk = __ldg(in + (size_t)bc * N + v);
+    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+    float *dst = out + ((size_t)b * C + chunk * 8) * N + v;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(p[e]);
+        dst[(size_t)(2 * e) * N] = f.x;
+        dst[(size_t)(2 * e + 1) * N] = f.y;
+    }
+}
+
+// One packed B block per op: [2 K-chunks][NPAD rows][8 bf16].  src describes where each chunk comes from.
+struct WSrc {
+    int16_t tap[2];   // filter tap index kd*9+kh*3+kw of each chunk, -1 = zero chunk
+    int16_t cin0[2];  // first input channel of each chunk
+};
+struct WPackParams {
+    int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
+    WSrc src[kMaxOps];
+};
+
+__global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ out,
+                                    const __grid_constant__ WPackParams p) {
+    const int per_group = p.nblocks * 2 * p.npad * 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_group * p.ngroups) return;
+    const int g = idx / per_group;
+    int r = idx % per_group;
+    const int e = r % 8; r /= 8;
+    const int n = r % p.npad; r /= p.npad;
+    const int c = r % 2;
+    const int blk = r / 2;
+    const int tap = p.src[blk].tap[c];
+    const int cin = p.src[blk].cin0[c] + e;
+    const int co = g * p.cout_group + n;
+    float v = 0.f;
+    if (tap >= 0 && n < p.cout_group && co < p.cout_total && cin < p.cin_total)
+        v = p.transposed ? w[((size_t)cin * p.cout_total + co) * 27 + tap] : w[((size_t)co * p.cin_total + cin) * 27 + tap];
+    out[idx] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: per-layer configuration
+// ------------------------------------------------------------------------------------------------
+enum TcKind { TC_CONV_S1 = 0, TC_CONV_S2 = 1, TC_CONVT = 2 };
+
+struct TcPlan {
+    TcLayer L;
+    WPackParams W;
+    CUtensorMap tmap;
+    int npad;
+    size_t smem_bytes;
+    size_t wpacked_bytes;
+    int grid;
+};
+
+static constexpr int kSmemLimit = 227 * 1024;
+
+// Builds the plan for one layer.  in: bf16 CP8 [B][cin/8][Din][Hin][Win][8].
+static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din, int Hin, int Win, const void *in_ptr,
+                     int num_sms, bool encode = true) {
+    TcLayer &L = pl.L;
+    memset(&pl, 0, sizeof(pl));
+    MVS_REQUIRE(cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
+    const int chunks = cin / 8;
+    // tile space
+    int Dt, Ht, Wt;
+    if (kind == TC_CONV_S2) { Dt = Din / 2; Ht = Hin / 2; Wt = Win / 2; }
+    else { Dt = Din; Ht = Hin; Wt = Win; }
+    // N (padded cout) per CTA: keep resident weights <= ~112 KB
+    const int kpairs_tap = (cin >= 16) ? cin / 16 : 1;
+    int ntaps_ops;  // MMA instructions per step
+    if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
+    else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
+    MVS_REQUIRE(!(kind == TC_CONVT && cin < 16), "tc convT needs Cin >= 16");
+    MVS_REQUIRE(ntaps_ops <= kMaxOps, "tc conv: too many ops");
+    int ngroups = 1;
+    int cout_group = cout;
+    while (true) {
+        const int npad_try = cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64);
+        if ((size_t)ntaps_ops * npad_try * 32 <= 112 * 1024 && cout_group <= 64) break;
+        ngroups *= 2;
+        cout_group = cout / ngroups;
+        MVS_REQUIRE(cout_group >= 8 && cout % ngroups == 0, "tc conv: cannot split Cout=%d", cout);
+    }
+    const int npad = cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64);
+    const int nacc = (kind == TC_CONVT) ? 8 : 1;
+    const int wbytes = ntaps_ops * npad * 32;
+    // ring geometry
+    const int need = (kind == TC_CONVT) ? 2 : 3;
+    const int adv = (kind == TC_CONV_S2) ? 2 : 1;
+    const int nsub = (kind == TC_CONV_S2) ? 4 : 1;
+    const int halo = (kind == TC_CONV_S1) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
+    // choose the tile: TXB columns, TY rows, MT M-tiles of 128 flattened positions
+    const int max_cols = (kind == TC_CONV_S2) ? 128 - halo : 254;  // boxDim <= 256 (x2 for elementStrides = 2)
+    int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
+    double best_score = -1;
+    const int tmem_budget = 256 / (nacc * npad);  // MT limit: 2 buffers x nacc x MT x npad <= 512 columns
+    for (int nx = 1; nx <= 64; ++nx) {
+        const int TXB = (Wt + nx - 1) / nx;
+        if (TXB > max_cols) continue;
+        const int P = TXB + halo;
+        for (int MT = 1; MT <= 4 && MT <= tmem_budget; ++MT) {
+            const int TY = std::min((MT * 128) / P, Ht);
+            if (TY < 1) continue;
+            const int rows = TY + halo;
+            const size_t sub_bytes = (size_t)chunks * rows * P * 16;
+            const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
+            for (int nslot = need + adv; nslot >= need; --nslot) {
+                const size_t total = 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+                if (total > (size_t)kSmemLimit) continue;
+                // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
+                const double useful = (double)(TY * TXB) / (MT * 128.0);
+                const double xeff = (double)Wt / (nx * TXB);
+                const double yeff = (double)Ht / (((Ht + TY - 1) / TY) * TY);
+                const double pipe = (nslot == need + adv) ? 1.0 : 0.8;
+                const double score = useful * xeff * yeff * pipe * (0.9 + 0.1 * (double)TY / rows);
+                if (score > best_score) {
+                    best_score = score; best_TXB = TXB; best_TY = TY; best_MT = MT; best_nslot = nslot;
+                }
+                break;
+            }
+        }
+        if (nx > 1 && best_score > 0 && (Wt + nx - 1) / nx < 24) break;
+    }
+    MVS_REQUIRE(best_score > 0, "tc conv: no tile configuration fits shared memory (cin=%d cout=%d)", cin, cout);
+    const int TXB = best_TXB, TY = best_TY, MT = best_MT, P = TXB + halo, rows = TY + halo;
+
+    L.B = B; L.Dt = Dt; L.Ht = Ht; L.Wt = Wt;
+    L.TXB = TXB; L.TY = TY; L.P = P; L.MT = MT;
+    L.tiles_x = (Wt + TXB - 1) / TXB;
+    L.tiles_y = (Ht + TY - 1) / TY;
+    L.ngroups = ngroups;
+    L.nsub = nsub; L.chunks = chunks;
+    L.sub_bytes = chunks * rows * P * 16;
+    L.sub_stride = (L.sub_bytes + 127) & ~127;
+    L.slot_bytes = nsub * L.sub_stride;
+    L.need = need; L.adv = adv; L.nslot = best_nslot;
+    L.pz0 = (kind == TC_CONVT) ? 0 : -1;
+    L.zscale = (kind == TC_CONV_S2) ? 2 : 1;
+    L.in_scale = (kind == TC_CONV_S2) ? 2 : 1;
+    if (kind == TC_CONV_S1) { L.sub_xoff[0] = -1; L.sub_yoff[0] = -1; }
+    else if (kind == TC_CONVT) { L.sub_xoff[0] = 0; L.sub_yoff[0] = 0; }
+    else {
+        for (int s = 0; s < 4; ++s) {  // s = ypar*2 + xpar; parity 1 = odd input index, starts one element earlier
+            L.sub_yoff[s] = (s >> 1) ? -1 : 0;
+            L.sub_xoff[s] = (s & 1) ? -1 : 0;
+        }
+    }
+    // z segmentation: enough work items for ~2 per SM
+    const int cols = B * L.tiles_x * L.tiles_y * ngroups;
+    int zsegs = 1;
+    {
+        double best = -1;
+        for (int zs = 1; zs <= std::max(1, Dt / 4); ++zs) {
+            const int len = (Dt + zs - 1) / zs, nseg = (Dt + len - 1) / len;
+            const long long items = (long long)cols * nseg;
+            const double wave = (double)items / ((double)((items + num_sms - 1) / num_sms) * num_sms);
+            const double haloeff = (double)(adv * len) / (adv * (len - 1) + need);
+            const double sc = wave * haloeff;
+            if (sc > best + 1e-9) { best = sc; zsegs = zs; }
+        }
+    }
+    L.zseg_len = (Dt + zsegs - 1) / zsegs;
+    L.zsegs = (Dt + L.zseg_len - 1) / L.zseg_len;
+    L.n_items = cols * L.zsegs;
+    L.nacc = nacc; L.npad = npad; L.wbytes_group = wbytes;
+    L.cout_group = cout_group; L.cout_total = cout;
+    L.out_scale = (kind == TC_CONVT) ? 2 : 1;
+    L.Dout = L.out_scale * Dt; L.Hout = L.out_scale * Ht; L.Wout = L.out_scale * Wt;
+
+    // ---- op table + weight sources
+    WPackParams &W = pl.W;
+    W.npad = npad; W.cout_group = cout_group; W.cout_total = cout; W.cin_total = cin; W.ngroups = ngroups;
+    W.transposed = (kind == TC_CONVT);
+    const int chunk_stride = rows * P * 16;
+    int nops = 0;
+    auto tap_off = [&](int kh, int kw) -> int {  // byte offset of a conv tap inside its plane (chunk 0)
+        if (kind == TC_CONV_S1) return (kh * P + kw) * 16;
+        const int ypar = (kh != 1), xpar = (kw != 1);
+        return (ypar * 2 + xpar) * L.sub_stride + ((kh == 2 ? 1 : 0) * P + (kw == 2 ? 1 : 0)) * 16;
+    };
+    if (kind != TC_CONVT) {
+        L.acc_first[0] = 0;
+        for (int kd = 0; kd < 3; ++kd) {
+            if (cin >= 16) {
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw)
+                        for (int kc = 0; kc < cin / 16; ++kc) {
+                            TcOp &op = L.ops[nops];
+                            op.a_off = tap_off(kh, kw) + 2 * kc * chunk_stride;
+                            op.lbo = chunk_stride;
+                            op.widx = nops; op.plane_rel = kd; op.acc = 0;
+                            const int tap = kd * 9 + kh * 3 + kw;
+                            W.src[nops] = WSrc{{(int16_t)tap, (int16_t)tap}, {(int16_t)(16 * kc), (int16_t)(16 * kc + 8)}};
+                            ++nops;
+                        }
+            } else {  // cin == 8: one K=16 instruction covers two taps of the same plane (sorted by offset)
+                int order[9];
+                for (int i = 0; i < 9; ++i) order[i] = i;
+                std::sort(order, order + 9, [&](int a, int b) { return tap_off(a / 3, a % 3) < tap_off(b / 3, b % 3); });
+                for (int i = 0; i < 9; i += 2) {
+                    TcOp &op = L.ops[nops];
+                    const int t0 = order[i], t1 = (i + 1 < 9) ? order[i + 1] : -1;
+                    op.a_off = tap_off(t0 / 3, t0 % 3);
+                    op.lbo = (t1 >= 0) ? tap_off(t1 / 3, t1 % 3) - op.a_off : 0;
+                    op.widx = nops; op.plane_rel = kd; op.acc = 0;
+                    W.src[nops] = WSrc{{(int16_t)(kd * 9 + t0), (int16_t)(t1 >= 0 ? kd * 9 + t1 : -1)}, {0, 0}};
+                    ++nops;
+                }
+            }
+        }
+        L.acc_first[1] = nops;
+        L.acc_pz[0] = L.acc_py[0] = L.acc_px[0] = 0;
+    } else {
+        // 8 output-parity classes; per dimension: parity 0 -> (k=1, d=0); parity 1 -> (k=2, d=0), (k=0, d=1)
+        for (int a = 0; a < 8; ++a) {
+            const int pz = a >> 2, py = (a >> 1) & 1, px = a & 1;
+            L.acc_first[a] = nops;
+            L.acc_pz[a] = pz; L.acc_py[a] = py; L.acc_px[a] = px;
+            for (int dz = 0; dz <= pz; ++dz)
+                for (int dy = 0; dy <= py; ++dy)
+                    for (int dx = 0; dx <= px; ++dx) {
+                        const int kd = pz ? (dz ? 0 : 2) : 1, kh = py ? (dy ? 0 : 2) : 1, kw = px ? (dx ? 0 : 2) : 1;
+                        for (int kc = 0; kc < cin / 16; ++kc) {
+                            TcOp &op = L.ops[nops];
+                            op.a_off = (dy * P + dx) * 16 + 2 * kc * chunk_stride;
+                            op.lbo = chunk_stride;
+                            op.widx = nops; op.plane_rel = dz; op.acc = a;
+                            const int tap = kd * 9 + kh * 3 + kw;
+                            W.src[nops] = WSrc{{(int16_t)tap, (int16_t)tap}, {(int16_t)(16 * kc), (int16_t)(16 * kc + 8)}};
+                            ++nops;
+                        }
+                    }
+        }
+        L.acc_first[8] = nops;
+    }
+    MVS_REQUIRE(nops == ntaps_ops, "tc conv: internal op count mismatch (%d vs %d)", nops, ntaps_ops);
+    L.nops = nops;
+    W.nblocks = nops;
+    pl.npad = npad;
+    pl.wpacked_bytes = (size_t)ngroups * wbytes;
+    pl.smem_bytes = 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+    pl.grid = std::min(L.n_items, num_sms);
+    pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
+
+    if (!encode) return MVS_OK;
+    // ---- tensor map over the input: dims (8ch, x, y, z, B*chunks)
+    tmap_encode_fn enc = get_tmap_encode();
+    MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const int es = (kind == TC_CONV_S2) ? 2 : 1;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, (cuuint64_t)B * chunks};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)Win * 16, (cuuint64_t)Win * Hin * 16, (cuuint64_t)Win * Hin * Din * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)(P * es), (cuuint32_t)(rows * es), 1, (cuuint32_t)chunks};
+    cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+    CUresult cr = enc(&pl.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in_ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_error(MVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return MVS_OK;
+}
+
+static int run_layer(TcKind kind, const void *in, const float *w_fp32, const float *shift, int relu, const void *skip,
+                     void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
+                     int num_sms, cudaStream_t st) {
+    static thread_local TcPlan pl;  // ~3 KB; not kept across calls
+    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms)) return rc;
+    pl.L.out = out;
+    pl.L.skip = (const uint4 *)skip;
+    pl.L.shift = shift;
+    pl.L.relu = relu;
+    pl.L.out_f32 = out_f32;
+    pl.L.wpacked = (const uint4 *)wpacked_scratch;
+    const int nw = (int)(pl.wpacked_bytes / 2);
+    pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)wpacked_scratch, pl.W);
+    MVS_LAUNCH_CHECK(1);
+    auto launch = [&](auto kern) -> int {
+        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        kern<<<pl.grid, kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
+        MVS_LAUNCH_CHECK(1);
+        return MVS_OK;
+    };
+    if (pl.npad == 16) return launch(conv3d_tc_kernel<16>);
+    if (pl.npad == 32) return launch(conv3d_tc_kernel<32>);
+    return launch(conv3d_tc_kernel<64>);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CostRegNet.forward (mvsnet.py:64-73) on tensor cores.
+// workspace (bytes): bf16 CP8 activations  vol 64 N0 | c0 16 | c1 4 | c2 4 | c3 1 | c4 1 | c5 .25 | c6 .25 |
+//                    u7 1 | u9 4 | u11 16   (N0 = B*D*H*W voxels; bytes per voxel shown) + packed weights
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+static constexpr size_t kWScratch = 512 * 1024;
+
+size_t costreg_tc_workspace_bytes(int B, int D, int H, int W) {
+    const size_t n0 = (size_t)B * D * H * W;
+    const size_t act = n0 * 64 + n0 * 16 + n0 * 4 + n0 * 4 + n0 + n0 + n0 / 4 + n0 / 4 + n0 + n0 * 4 + n0 * 16;
+    return align_up(act, 1024) + 11 * kWScratch + 16 * 1024;
+}
+
+int costreg_tc(const float *volume, const mvs_costreg_params *p, float *logits, void *workspace, int B, int D, int H,
+               int W, cudaStream_t st) {
+    int dev = 0, num_sms = 148;
+    MVS_CUDA(cudaGetDevice(&dev));
+    MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t n0 = (size_t)B * D * H * W;
+    uint8_t *ws = (uint8_t *)workspace;
+    auto take = [&](size_t bytes) { uint8_t *r = ws; ws += align_up(bytes, 1024); return r; };
+    void *vol = take(n0 * 64), *c0 = take(n0 * 16), *c1 = take(n0 * 4), *c2 = take(n0 * 4), *c3 = take(n0),
+         *c4 = take(n0), *c5 = take(n0 / 4), *c6 = take(n0 / 4), *u7 = take(n0), *u9 = take(n0 * 4),
+         *u11 = take(n0 * 16);
+    uint8_t *wsc = take(11 * kWScratch);
+    const size_t N = (size_t)D * H * W;
+    ncdhw_to_cp8_kernel<<<dim3(cdiv(N, 256), B * 4), 256, 0, st>>>(volume, (uint4 *)vol, 32, N);
+    MVS_LAUNCH_CHECK(1);
+    int rc;
+#define RUN(expr) if ((rc = (expr)) != MVS_OK) return rc
+    RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st));
+    RUN(run_layer(TC_CONV_S2, c0, p->w[1], p->shift[1], 1, nullptr, c1, 0, wsc + 1 * kWScratch, B, 8, 16, D, H, W, num_sms, st));
+    RUN(run_layer(TC_CONV_S1, c1, p->w[2], p->shift[2], 1, nullptr, c2, 0, wsc + 2 * kWScratch, B, 16, 16, D / 2, H / 2, W / 2, num_sms, st));
+    RUN(run_layer(TC_CONV_S2, c2, p->w[3], p->shift[3], 1, nullptr, c3, 0, wsc + 3 * kWScratch, B, 16, 32, D / 2, H / 2, W / 2, num_sms, st));
+    RUN(run_layer(TC_CONV_S1, c3, p->w[4], p->shift[4], 1, nullptr, c4, 0, wsc + 4 * kWScratch, B, 32, 32, D / 4, H / 4, W / 4, num_sms, st));
+    RUN(run_layer(TC_CONV_S2, c4, p->w[5], p->shift[5], 1, nullptr, c5, 0, wsc + 5 * kWScratch, B, 32, 64, D / 4, H / 4, W / 4, num_sms, st));
+    RUN(run_layer(TC_CONV_S1, c5, p->w[6], p->shift[6], 1, nullptr, c6, 0, wsc + 6 * kWScratch, B, 64, 64, D / 8, H / 8, W / 8, num_sms, st));
+    RUN(run_layer(TC_CONVT, c6, p->w[7], p->shift[7], 1, c4, u7, 0, wsc + 7 * kWScratch, B, 64, 32, D / 8, H / 8, W / 8, num_sms, st));
+    RUN(run_layer(TC_CONVT, u7, p->w[8], p->shift[8], 1, c2, u9, 0, wsc + 8 * kWScratch, B, 32, 16, D / 4, H / 4, W / 4, num_sms, st));
+    RUN(run_layer(TC_CONVT, u9, p->w[9], p->shift[9], 1, c0, u11, 0, wsc + 9 * kWScratch, B, 16, 8, D / 2, H / 2, W / 2, num_sms, st));
+    RUN(run_layer(TC_CONV_S1, u11, p->w[10], p->shift[10], 0, nullptr, logits, 1, wsc + 10 * kWScratch, B, 8, 1, D, H, W, num_sms, st));
+#undef RUN
+    return MVS_OK;
+}
+
+// Single-layer entry for tests: fp32 NCDHW in/out, converts around one tensor-core layer.
+int tc_layer_ncdhw(int kind, const float *x, const float *w, const float *shift, int relu, const float *skip, float *y,
+                   int B, int cin, int cout, int D, int H, int W, cudaStream_t st) {
+    int dev = 0, num_sms = 148;
+    MVS_CUDA(cudaGetDevice(&dev));
+    MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t Nin = (size_t)D * H * W;
+    int Do = D, Ho = H, Wo = W;
+    if (kind == TC_CONV_S2) { Do = D / 2; Ho = H / 2; Wo = W / 2; }
+    if (kind == TC_CONVT) { Do = 2 * D; Ho = 2 * H; Wo = 2 * W; }
+    const size_t Nout = (size_t)Do * Ho * Wo;
+    const int cout_pad = (cout + 7) / 8 * 8;
+    const size_t in_b = align_up((size_t)B * cin * Nin * 2, 1024), out_b = align_up((size_t)B * cout_pad * Nout * 2, 1024);
+    uint8_t *ws = nullptr;
+    MVS_CUDA(cudaMallocAsync((void **)&ws, in_b + 2 * out_b + kWScratch, st));
+    void *xin = ws, *yout = ws + in_b, *sk = ws + in_b + out_b, *wsc = ws + in_b + 2 * out_b;
+    int rc = MVS_OK;
+    ncdhw_to_cp8_kernel<<<dim3(cdiv(Nin, 256), B * cin / 8), 256, 0, st>>>(x, (uint4 *)xin, cin, Nin);
+    if (skip) ncdhw_to_cp8_kernel<<<dim3(cdiv(Nout, 256), B * cout / 8), 256, 0, st>>>(skip, (uint4 *)sk, cout, Nout);
+    const bool f32out = (cout == 1);
+    rc = run_layer((TcKind)kind, xin, w, shift, relu, skip ? sk : nullptr, f32out ? (void *)y : yout, f32out, wsc, B, cin,
+                   cout, D, H, W, num_sms, st);
+    if (rc == MVS_OK && !f32out)
+        cp8_to_ncdhw_kernel<<<dim3(cdiv(Nout, 256), B * cout / 8), 256, 0, st>>>((const uint4 *)yout, y, cout, Nout);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (rc != MVS_OK) return rc;
+    if (e != cudaSuccess) return set_error(MVS_ERR_CUDA, "tc_layer launch failed: %s", cudaGetErrorString(e));
+    count_launches(3);
+    return MVS_OK;
 }
 
 }  // namespace mvs
+
+using namespace mvs;
+
+extern "C" int mvs_conv3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int B,
+                                     int Cin, int Cout, int D, int H, int W, int stride, void *stream) {
+    MVS_REQUIRE(x && w && shift && y, "null pointer argument");
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    MVS_REQUIRE(stride == 1 || stride == 2, "conv3d: stride must be 1 or 2, got %d", stride);
+    MVS_REQUIRE(Cin % 8 == 0 && (Cout % 8 == 0 || Cout == 1), "tensor-core conv3d needs Cin %% 8 == 0 and Cout %% 8 == 0 (or 1)");
+    MVS_REQUIRE(stride == 1 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "stride-2 tensor-core conv3d needs even D, H, W");
+    return tc_layer_ncdhw(stride == 1 ? TC_CONV_S1 : TC_CONV_S2, x, w, shift, relu, nullptr, y, B, Cin, Cout, D, H, W,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu,
+                                               const float *skip, float *y, int B, int Cin, int Cout, int D, int H,
+                                               int W, void *stream) {
+    MVS_REQUIRE(x && w && shift && y, "null pointer argument");
+    MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+    MVS_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "tensor-core conv_transpose3d needs Cin %% 16 == 0 and Cout %% 8 == 0");
+    return tc_layer_ncdhw(TC_CONVT, x, w, shift, relu, skip, y, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
+}
+
+// Diagnostics: the tile / ring / grid configuration the planner picks for one layer (no GPU needed).
+extern "C" int mvs_tc_plan_describe(int kind, int B, int Cin, int Cout, int D, int H, int W, int num_sms, char *buf,
+                                    int buflen) {
+    static thread_local TcPlan pl;
+    MVS_REQUIRE(buf && buflen > 0 && kind >= 0 && kind <= 2, "bad argument");
+    if (int rc = make_plan(pl, (TcKind)kind, B, Cin, Cout, D, H, W, nullptr, num_sms, false)) return rc;
+    const TcLayer &L = pl.L;
+    snprintf(buf, buflen,
+             "kind=%d cin=%d cout=%d tile=%dx%d (P=%d) MT=%d nslot=%d need=%d adv=%d nsub=%d slot=%dB w=%dB smem=%zuB "
+             "npad=%d groups=%d nacc=%d ops=%d tiles=%dx%d zsegs=%d(len %d) items=%d grid=%d useful=%.3f",
+             kind, Cin, Cout, L.TXB, L.TY, L.P, L.MT, L.nslot, L.need, L.adv, L.nsub, L.slot_bytes, L.wbytes_group,
+             pl.smem_bytes, L.npad, L.ngroups, L.nacc, L.nops, L.tiles_x, L.tiles_y, L.zsegs, L.zseg_len, L.n_items,
+             pl.grid, (double)L.Wt * L.Ht / ((double)L.tiles_x * L.tiles_y * L.MT * 128));
+    return MVS_OK;
+}

@@ -152,7 +152,7 @@ def warp_variance(fea, proj, depth_values):
 # ------------------------------------------------------------------------------------------------
 # (a4) CostRegNet                                    reference models/mvsnet.py:33-73, module.py:26-33
 # ------------------------------------------------------------------------------------------------
-def conv3d_bn_relu(x, w_folded, shift, relu=True, stride=1):
+def conv3d_bn_relu(x, w_folded, shift, relu=True, stride=1, tensor_cores=False):
     x = _prep(x, "x", 5)
     w_folded = _prep(w_folded, "weight", 5)
     shift = _prep(shift, "shift", 1)
@@ -164,13 +164,13 @@ def conv3d_bn_relu(x, w_folded, shift, relu=True, stride=1):
     Do, Ho, Wo = [(n - 1) // stride + 1 for n in (D, H, W)]
     y = torch.empty((B, Cout, Do, Ho, Wo), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.load().mvs_conv3d_bn_relu(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(y), B, Cin, Cout, D, H,
-                                            W, stride, _stream(x))
+        fn = _lib.load().mvs_conv3d_bn_relu_tc if tensor_cores else _lib.load().mvs_conv3d_bn_relu
+        rc = fn(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(y), B, Cin, Cout, D, H, W, stride, _stream(x))
     _lib.check(rc, "mvs_conv3d_bn_relu")
     return y
 
 
-def conv_transpose3d_bn_relu(x, w_folded, shift, relu=True, skip=None):
+def conv_transpose3d_bn_relu(x, w_folded, shift, relu=True, skip=None, tensor_cores=False):
     x = _prep(x, "x", 5)
     w_folded = _prep(w_folded, "weight", 5)
     shift = _prep(shift, "shift", 1)
@@ -185,8 +185,8 @@ def conv_transpose3d_bn_relu(x, w_folded, shift, relu=True, skip=None):
             raise RuntimeError("conv_transpose3d: skip shape %s != output shape" % (tuple(skip.shape),))
     y = torch.empty((B, Cout, 2 * D, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.load().mvs_conv_transpose3d_bn_relu(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(skip), _ptr(y),
-                                                      B, Cin, Cout, D, H, W, _stream(x))
+        fn = _lib.load().mvs_conv_transpose3d_bn_relu_tc if tensor_cores else _lib.load().mvs_conv_transpose3d_bn_relu
+        rc = fn(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(skip), _ptr(y), B, Cin, Cout, D, H, W, _stream(x))
     _lib.check(rc, "mvs_conv_transpose3d_bn_relu")
     return y
 

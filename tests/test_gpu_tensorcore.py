@@ -1,0 +1,85 @@
+"""GPU parity of the tcgen05 (bf16 operand) CostRegNet path against the oracle.
+
+Tolerance (stated separately from the fp32 path, as north_star allows): operands are rounded to bf16
+(8-bit mantissa), accumulation is fp32.  Per layer the oracle is evaluated on the SAME bf16-rounded inputs
+and weights, so the remaining difference is accumulation order plus the bf16 rounding of the stored output:
+|y - ref| <= 2^-8 |ref| + 2e-3.  End to end (11 layers) logits are compared at 3e-2 absolute on logits of
+std ~0.5, and the depth map at 5e-3 x depth range."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from scene_3dreconstruction_mvsnet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def check(y, ref, what):
+    y = y.cpu().numpy().astype(np.float64)
+    err = np.abs(y - ref)
+    tol = np.abs(ref) * 2.0 ** -8 + 2e-3
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d outside tolerance, max err %.4g at %s (ref %.4g got %.4g)" % (
+        what, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape), ref.flat[err.argmax()],
+        y.flat[err.argmax()])
+
+
+CONV_CASES = [
+    # cin, cout, stride, (D,H,W)
+    (32, 8, 1, (6, 7, 40)),      # conv0-like, one tile, partial rows
+    (32, 8, 1, (10, 24, 230)),   # several x/y tiles, z segments
+    (16, 16, 1, (5, 9, 33)),
+    (8, 1, 1, (9, 10, 50)),      # prob layer: paired taps, fp32 single-channel output
+    (32, 32, 1, (4, 20, 27)),
+    (64, 64, 1, (3, 9, 13)),     # two output-channel groups
+    (8, 16, 2, (8, 12, 40)),     # stride 2 with paired taps across parity sub-planes
+    (16, 32, 2, (6, 10, 44)),
+    (32, 64, 2, (4, 8, 12)),
+]
+
+
+@pytest.mark.parametrize("cin,cout,stride,dims", CONV_CASES)
+def test_tc_conv3d(cin, cout, stride, dims):
+    g = torch.Generator().manual_seed(cin * 7 + cout + dims[2])
+    x = bf16_round(torch.randn(1, cin, *dims, generator=g))
+    w = bf16_round(torch.randn(cout, cin, 3, 3, 3, generator=g) * (1.0 / (27 * cin) ** 0.5))
+    shift = torch.randn(cout, generator=g) * 0.3
+    relu = cout != 1
+    y = ops.conv3d_bn_relu(x.to(DEV), w.to(DEV), shift.to(DEV), relu=relu, stride=stride, tensor_cores=True)
+    ref = orc.conv3d(x.numpy(), w.numpy(), shift.numpy(), None, relu, stride).astype(np.float64)
+    assert tuple(y.shape) == ref.shape
+    check(y, ref, "conv %d->%d s%d %s" % (cin, cout, stride, dims))
+
+
+@pytest.mark.parametrize("cin,cout,dims,with_skip", [(16, 8, (4, 6, 30), True), (32, 16, (3, 5, 21), True),
+                                                     (64, 32, (2, 4, 9), True), (16, 8, (5, 13, 120), False)])
+def test_tc_conv_transpose3d(cin, cout, dims, with_skip):
+    g = torch.Generator().manual_seed(cin + dims[2])
+    x = bf16_round(torch.randn(1, cin, *dims, generator=g))
+    w = bf16_round(torch.randn(cin, cout, 3, 3, 3, generator=g) * (1.0 / (8 * cin) ** 0.5))
+    shift = torch.randn(cout, generator=g) * 0.3
+    skip = bf16_round(torch.randn(1, cout, *[2 * d for d in dims], generator=g)) if with_skip else None
+    y = ops.conv_transpose3d_bn_relu(x.to(DEV), w.to(DEV), shift.to(DEV), relu=True,
+                                     skip=skip.to(DEV) if with_skip else None, tensor_cores=True)
+    bn = (np.ones(cout, np.float32), shift.numpy(), np.zeros(cout, np.float32), np.full(cout, 1 - orc.BN_EPS, np.float32))
+    ref = orc.conv_transpose3d(x.numpy(), w.numpy(), bn, True, skip.numpy() if with_skip else None).astype(np.float64)
+    check(y, ref, "convT %d->%d %s" % (cin, cout, dims))
+
+
+@pytest.mark.parametrize("case", ["case_a", "case_b"])
+def test_tc_costreg_and_depth_golden(case, request, weights):
+    from test_gpu_parity import cu, load_model, maxabs
+    c = request.getfixturevalue(case)
+    m = load_model(weights, precision="bf16")
+    logits = m.cost_regularization.infer(cu(c["variance"]), "bf16")
+    assert maxabs(logits, c["logits"]) < 3e-2
+    with torch.no_grad():
+        out = m(cu(c["imgs"]), cu(c["proj"]), cu(c["dv"]))
+    rng = float(c["dv"].max() - c["dv"].min())
+    assert maxabs(out["depth"], c["depth"]) < 5e-3 * rng
