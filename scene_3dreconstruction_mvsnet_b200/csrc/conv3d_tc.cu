@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string.h>
+#include <vector>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -51,6 +52,10 @@ struct TcOp {
     uint16_t widx;      // index of the packed B block
     uint8_t plane_rel;  // which of the NEED planes of this step
     uint8_t acc;        // accumulator group
+    // UMMA descriptor low words minus the run-time bases (filled by finalize_ops): the issue loop reads them
+    // with uniform constant-bank loads, so no R2UR / shared-memory round trip sits between two tcgen05.mma
+    uint32_t a_lo;      // (a_off >> 4) | (lbo >> 4) << 16
+    uint32_t b_lo;      // (widx * NPAD * 32 >> 4) | (NPAD * 16 >> 4) << 16
 };
 
 struct TcLayer {
@@ -61,9 +66,14 @@ struct TcLayer {
     // ring
     int nsub, chunks, sub_bytes, sub_stride, slot_bytes, need, adv, nslot, pz0, zscale;
     int in_scale, sub_xoff[4], sub_yoff[4];
+    int merged_x;  // 1: tensor map is 4-D with the 8 channels and x merged into one contiguous inner dimension
     // gemm
     int nops, nacc, npad, wbytes_group;
     int acc_first[kMaxAcc + 1];  // op range of each accumulator group
+    // issue segments: maximal runs of ops with the same accumulator group and the same ring plane
+    int nseg;
+    uint16_t seg_first[2 * kMaxAcc + 4], seg_last[2 * kMaxAcc + 4];
+    uint8_t seg_plane[2 * kMaxAcc + 4], seg_acc[2 * kMaxAcc + 4], seg_new_acc[2 * kMaxAcc + 4];
     // epilogue
     int out_scale, acc_pz[kMaxAcc], acc_py[kMaxAcc], acc_px[kMaxAcc];
     int cout_group, cout_total, relu, out_f32;
@@ -80,6 +90,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// One elected lane issues every tcgen05.mma of one z-step.  Per op: one 8-byte shared-memory load of the two
+// precomputed descriptor low words, one add for the ring-slot base, MT back-to-back MMAs.
+template <int NPAD, int MT>
+__device__ __forceinline__ void issue_step(const TcLayer &L, const uint2 *__restrict__ optab, uint32_t tmem_buf,
+                                           uint32_t sb0, uint32_t sb1, uint32_t sb2, uint32_t idesc, uint64_t desc_hi) {
+    for (int sg = 0; sg < L.nseg; ++sg) {
+        const uint32_t pr = L.seg_plane[sg];
+        const uint32_t sb = pr == 0 ? sb0 : (pr == 1 ? sb1 : sb2);
+        const uint32_t d = tmem_buf + L.seg_acc[sg] * (MT * NPAD);
+        const int o0 = L.seg_first[sg], o1 = L.seg_last[sg];
+        uint32_t accum = L.seg_new_acc[sg] ? 0u : 1u;
+#pragma unroll 2
+        for (int o = o0; o < o1; ++o) {
+            const uint2 e = optab[o];
+            const uint32_t alo = e.x + sb;
+            const uint64_t bd = desc_hi | (uint64_t)e.y;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                ptx::mma_bf16_ss(d + mt * NPAD, desc_hi | (uint64_t)(alo + mt * 128), bd, idesc, accum);
+            accum = 1u;
+        }
+    }
+}
+
 template <int NPAD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
@@ -92,8 +126,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
-    uint8_t *w_smem = smem + 256;
-    const uint32_t w_base = bar_base + 256;
+    uint2 *optab = reinterpret_cast<uint2 *>(smem + 256);  // [kMaxOps] {A desc lo (no slot base), B desc lo}
+    constexpr uint32_t kHdr = 256 + kMaxOps * 8;
+    uint8_t *w_smem = smem + kHdr;
+    const uint32_t w_base = bar_base + kHdr;
+    // descriptor high word: SBO = 128 B (8 rows x 16 B), version 1 (Blackwell), no swizzle
+    constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
     const uint32_t ring_base = (w_base + L.wbytes_group + 127u) & ~127u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,6 +147,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
         for (int i = threadIdx.x; i < L.wbytes_group / 16; i += kTcThreads) dst[i] = __ldg(src + i);
     }
+    for (int o = threadIdx.x; o < L.nops; o += kTcThreads)
+        optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
     if (threadIdx.x == 0) {
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
@@ -126,7 +166,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     ptx::tcgen05_fence_before();
     __syncthreads();
     ptx::tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // warp-uniform copy of the TMEM base (shuffle from lane 0 lets the compiler keep it in a uniform register)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int items_per_group = L.n_items / L.ngroups;
     const int cta_in_group = blockIdx.x / L.ngroups;
@@ -158,50 +199,59 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     ptx::mbar_wait(empty_bar(slot), ((g / L.nslot) & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(full_bar(slot), tx_bytes);
                     const int pz = L.zscale * zs + L.pz0 + j;
-                    for (int s = 0; s < L.nsub; ++s)
-                        ptx::tma_load_5d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot), 0,
-                                         L.in_scale * x0 + L.sub_xoff[s], L.in_scale * y0 + L.sub_yoff[s], pz,
-                                         b * L.chunks);
+                    if (L.merged_x) {  // inner dimension = 16*P contiguous bytes per row (uint64 elements)
+                        ptx::tma_load_4d(ring_base + slot * L.slot_bytes, &tmap, full_bar(slot), 2 * (x0 + L.sub_xoff[0]),
+                                         y0 + L.sub_yoff[0], pz, b * L.chunks);
+                    } else {
+                        for (int s = 0; s < L.nsub; ++s)
+                            ptx::tma_load_5d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot), 0,
+                                             L.in_scale * x0 + L.sub_xoff[s], L.in_scale * y0 + L.sub_yoff[s], pz,
+                                             b * L.chunks);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::make_idesc_bf16_m128(NPAD);
-            uint32_t g = 0, st = 0;
-            for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
-                int b, x0, y0, zs, T;
-                decode(it, b, x0, y0, zs, T);
-                for (int t = 0; t < T; ++t, ++st) {
-                    const uint32_t g0 = g + (uint32_t)L.adv * t;
+        // The whole warp runs this loop with warp-uniform values (kernel parameters, loop counters) so that
+        // descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc = ptx::make_idesc_bf16_m128(NPAD);
+        uint32_t g = 0, st = 0;
+        for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
+            int b, x0, y0, zs, T;
+            decode(it, b, x0, y0, zs, T);
+            for (int t = 0; t < T; ++t, ++st) {
+                const uint32_t g0 = g + (uint32_t)L.adv * t;
+                const uint32_t buf = st & 1;
+                if (leader) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
                     for (int r = 0; r < L.need; ++r) {
                         const uint32_t gi = g0 + r;
                         ptx::mbar_wait(full_bar(gi % L.nslot), (gi / L.nslot) & 1);
                     }
-                    const uint32_t buf = st & 1;
                     ptx::mbar_wait(tempty_bar(buf), ((st >> 1) & 1) ^ 1);
-                    ptx::tcgen05_fence_after();
-                    for (int mt = 0; mt < L.MT; ++mt) {
-                        for (int a = 0; a < L.nacc; ++a) {
-                            const uint32_t d = tmem_base + buf * ncols_buf + (a * L.MT + mt) * NPAD;
-                            for (int o = L.acc_first[a]; o < L.acc_first[a + 1]; ++o) {
-                                const TcOp op = L.ops[o];
-                                const uint32_t slot = (g0 + op.plane_rel) % L.nslot;
-                                const uint32_t a_addr = ring_base + slot * L.slot_bytes + op.a_off + mt * 2048;
-                                const uint64_t ad = ptx::make_smem_desc(a_addr, op.lbo, 128);
-                                const uint64_t bd = ptx::make_smem_desc(w_base + op.widx * (NPAD * 32), NPAD * 16, 128);
-                                ptx::mma_bf16_ss(d, ad, bd, idesc, o != L.acc_first[a]);
-                            }
-                        }
-                    }
+                }
+                __syncwarp();
+                ptx::tcgen05_fence_after();
+                if (leader) {
+                    const uint32_t sb0 = (ring_base + ((g0 + 0) % L.nslot) * L.slot_bytes) >> 4;
+                    const uint32_t sb1 = (ring_base + ((g0 + 1) % L.nslot) * L.slot_bytes) >> 4;
+                    const uint32_t sb2 = (ring_base + ((g0 + 2) % L.nslot) * L.slot_bytes) >> 4;
+                    const uint32_t tbuf = tmem_base + buf * ncols_buf;
+                    if (L.MT == 4) issue_step<NPAD, 4>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
+                    else if (L.MT == 2) issue_step<NPAD, 2>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
+                    else if (L.MT == 1) issue_step<NPAD, 1>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
+                    else issue_step<NPAD, 3>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
+                }
+                if (leader) {
                     for (int r = 0; r < L.adv; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
                     if (t == T - 1)
                         for (int r = L.adv; r < L.need; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
                     ptx::tcgen05_commit(tfull_bar(buf));
                 }
-                g += (uint32_t)(L.adv * (T - 1) + L.need);
+                __syncwarp();
             }
+            g += (uint32_t)(L.adv * (T - 1) + L.need);
         }
     } else {
         // ================= epilogue (4 warps = 128 TMEM lanes) =================
@@ -405,7 +455,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int nsub = (kind == TC_CONV_S2) ? 4 : 1;
     const int halo = (kind == TC_CONV_S1) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
     // choose the tile: TXB columns, TY rows, MT M-tiles of 128 flattened positions
-    const int max_cols = (kind == TC_CONV_S2) ? 128 - halo : 254;  // boxDim <= 256 (x2 for elementStrides = 2)
+    const int max_cols = 128 - halo;  // boxDim[x] <= 256: 2 uint64 per voxel (merged inner dim) or elementStrides = 2
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
     double best_score = -1;
     const int tmem_budget = 256 / (nacc * npad);  // MT limit: 2 buffers x nacc x MT x npad <= 512 columns
@@ -419,14 +469,14 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const int rows = TY + halo;
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
-            for (int nslot = need + adv; nslot >= need; --nslot) {
-                const size_t total = 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+            for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
+                const size_t total = 256 + kMaxOps * 8 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
                 const double xeff = (double)Wt / (nx * TXB);
                 const double yeff = (double)Ht / (((Ht + TY - 1) / TY) * TY);
-                const double pipe = (nslot == need + adv) ? 1.0 : 0.8;
+                const double pipe = (nslot >= need + 2 * adv) ? 1.0 : (nslot >= need + adv ? 0.9 : 0.6);
                 const double score = useful * xeff * yeff * pipe * (0.9 + 0.1 * (double)TY / rows);
                 if (score > best_score) {
                     best_score = score; best_TXB = TXB; best_TY = TY; best_MT = MT; best_nslot = nslot;
@@ -551,9 +601,37 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     MVS_REQUIRE(nops == ntaps_ops, "tc conv: internal op count mismatch (%d vs %d)", nops, ntaps_ops);
     L.nops = nops;
     W.nblocks = nops;
+    {   // order ops by (accumulator group, ring plane); the packed weight block follows its op (widx = position)
+        std::vector<int> order(nops);
+        for (int i = 0; i < nops; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (L.ops[a].acc != L.ops[b].acc) return L.ops[a].acc < L.ops[b].acc;
+            return L.ops[a].plane_rel < L.ops[b].plane_rel;
+        });
+        std::vector<TcOp> ops2(nops);
+        std::vector<WSrc> src2(nops);
+        for (int i = 0; i < nops; ++i) { ops2[i] = L.ops[order[i]]; src2[i] = W.src[order[i]]; ops2[i].widx = (uint16_t)i; }
+        for (int i = 0; i < nops; ++i) { L.ops[i] = ops2[i]; W.src[i] = src2[i]; }
+        L.nseg = 0;
+        for (int i = 0; i < nops; ++i) {
+            const bool new_acc = (i == 0) || L.ops[i].acc != L.ops[i - 1].acc;
+            if (new_acc || L.ops[i].plane_rel != L.ops[i - 1].plane_rel) {
+                const int sg = L.nseg++;
+                L.seg_first[sg] = (uint16_t)i; L.seg_plane[sg] = L.ops[i].plane_rel; L.seg_acc[sg] = L.ops[i].acc;
+                L.seg_new_acc[sg] = new_acc;
+                if (sg > 0) L.seg_last[sg - 1] = (uint16_t)i;
+            }
+        }
+        L.seg_last[L.nseg - 1] = (uint16_t)nops;
+    }
+    for (int o = 0; o < nops; ++o) {
+        TcOp &op = L.ops[o];
+        op.a_lo = ((op.a_off >> 4) & 0x3FFFu) | ((op.lbo >> 4) << 16);
+        op.b_lo = (((uint32_t)op.widx * npad * 32) >> 4) | (((uint32_t)npad * 16 >> 4) << 16);
+    }
     pl.npad = npad;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
-    pl.smem_bytes = 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+    pl.smem_bytes = 256 + kMaxOps * 8 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
@@ -561,6 +639,20 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // ---- tensor map over the input: dims (8ch, x, y, z, B*chunks)
     tmap_encode_fn enc = get_tmap_encode();
     MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    L.merged_x = (kind != TC_CONV_S2);
+    if (L.merged_x) {
+        // A TMA request per 16-byte inner row is ~10 cycles; merging (8ch, x) into one contiguous inner
+        // dimension of uint64 elements makes every box row one 16*P-byte request.
+        cuuint64_t gdim4[4] = {(cuuint64_t)2 * Win, (cuuint64_t)Hin, (cuuint64_t)Din, (cuuint64_t)B * chunks};
+        cuuint64_t gstr4[3] = {(cuuint64_t)Win * 16, (cuuint64_t)Win * Hin * 16, (cuuint64_t)Win * Hin * Din * 16};
+        cuuint32_t box4[4] = {(cuuint32_t)(2 * P), (cuuint32_t)rows, 1, (cuuint32_t)chunks};
+        cuuint32_t estr4[4] = {1, 1, 1, 1};
+        CUresult cr4 = enc(&pl.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(in_ptr), gdim4, gstr4, box4,
+                           estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr4 != CUDA_SUCCESS) return set_error(MVS_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (%d)", (int)cr4);
+        return MVS_OK;
+    }
     const int es = (kind == TC_CONV_S2) ? 2 : 1;
     cuuint64_t gdim[5] = {8, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)Din, (cuuint64_t)B * chunks};
     cuuint64_t gstr[4] = {16, (cuuint64_t)Win * 16, (cuuint64_t)Win * Hin * 16, (cuuint64_t)Win * Hin * Din * 16};
