@@ -164,8 +164,6 @@ def run_ours(args):
 
     V, H, W, D, focal, itv = synth.CONFIGS[args.workload]
     h, w = H // 4, W // 4
-    torch.manual_seed(1)
-    model = MVSNet(refine=False, precision=args.precision).to(dev).eval()
     # each rank owns its own shard of reference views (weak scaling): different seed per rank
     imgs, proj, dv = synth.make_named(args.workload, B=1, seed=rank)
     d_imgs, d_proj, d_dv = imgs.to(dev), proj.to(dev), dv.to(dev)
@@ -175,35 +173,43 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput ----------------
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            model(d_imgs, d_proj, d_dv)
-        barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        model.stage_events = []
-        launches0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            out = model(d_imgs, d_proj, d_dv)
-        e1.record()
-        barrier()
-        launches = _lib.launch_count() - launches0
-        clocks = sampler.result()
-        elapsed_ms = e0.elapsed_time(e1)
-        stage_ms = {}
-        for marks in model.stage_events:
-            for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
-                stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
-        model.stage_events = None
-        stage_ms = {k: sum(v) / len(v) for k, v in stage_ms.items()}
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    value = world * args.steps / (max_ms * 1e-3)
+    def measure(precision, steps, warmup):
+        """Device-resident throughput of MVSNet.forward: CUDA events around `steps` forwards, max over ranks."""
+        torch.manual_seed(1)
+        model = MVSNet(refine=False, precision=precision).to(dev).eval()
+        with torch.no_grad():
+            for _ in range(warmup):
+                model(d_imgs, d_proj, d_dv)
+            barrier()
+            sampler = ClockSampler(local)
+            sampler.start()
+            model.stage_events = []
+            launches0 = _lib.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(d_imgs, d_proj, d_dv)
+            e1.record()
+            barrier()
+            launches = _lib.launch_count() - launches0
+            clocks = sampler.result()
+            elapsed_ms = e0.elapsed_time(e1)
+            stage_ms = {}
+            for marks in model.stage_events:
+                for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+                    stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
+            model.stage_events = None
+            stage_ms = {k: sum(v) / len(v) for k, v in stage_ms.items()}
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms = float(t.item())
+        return {"model": model, "value": world * steps / (max_ms * 1e-3), "max_ms": max_ms, "stage_ms": stage_ms,
+                "launches": int(launches), "clocks": clocks}
+
+    main = measure(args.precision, args.steps, args.warmup)
+    model, value, max_ms, stage_ms, launches, clocks = (main["model"], main["value"], main["max_ms"], main["stage_ms"],
+                                                        main["launches"], main["clocks"])
 
     # ---------------- end to end through the host-buffer API ----------------
     runner = DepthMapRunner(model, device=str(dev))
@@ -216,6 +222,7 @@ def run_ours(args):
     runner.run_views([(p_imgs, p_proj, p_dv)] * max(2, args.warmup), sink)
     barrier()
     t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     runner.run_views([(p_imgs, p_proj, p_dv)] * args.steps, sink)
     e1.record()
@@ -230,19 +237,24 @@ def run_ours(args):
     if rank == 0:
         hbm_peak, tf_peak, peak_kind = measured_peaks()
         wv_ms = stage_ms.get("warp_variance")
-        alg_bytes = 4 * 32 * D * h * w + 4 * V * 32 * h * w   # volume written + features read once
+        # volume written once + every feature map read once.  In the bf16 mode the fused
+        # kernel writes the volume as bf16 (the tensor-core CostRegNet's input), i.e. 2 bytes per element.
+        vol_elem = 2 if args.precision == "bf16" else 4
+        alg_bytes = vol_elem * 32 * D * h * w + 4 * V * 32 * h * w
         achieved = alg_bytes / (wv_ms * 1e-3) / 1e9 if wv_ms else None
         cr_ms = stage_ms.get("cost_regularization")
         flops = 20304.0 * D * h * w
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16(costreg)+f32",
+            "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16 operands/f32 accumulate (CostRegNet, tcgen05) + f32",
             "data": "synthetic",
             "config": {"workload": args.workload, "views": V, "image": [H, W], "depth_planes": D, "batch": 1,
                        "feature_map": [h, w], "weights": "random-init (seed 1), eval mode",
-                       "precision": args.precision, "featurenet": "cuDNN fp32 (TF32 off)",
-                       "l2": "per-step working set 2.8 GB cost volume >> 126 MB L2; no flush needed",
+                       "precision": args.precision,
+                       "featurenet": "cuDNN NHWC, " + ("TF32 allowed" if args.precision == "bf16" else "fp32 (TF32 off)"),
+                       "l2": "per-step working set (1.4-2.8 GB cost volume) >> 126 MB L2; no flush needed",
                        "sharding": "one reference view stream per rank, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_view,
@@ -250,7 +262,7 @@ def run_ours(args):
                     "inputs -> H2D -> MVSNet.forward -> D2H depth+confidence, double-buffered)"},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
-            "roofline": {"kernel": "warp_volume_fwd_kernel<MODE_VAR> (+compose, +nchw_to_nhwc32 pre-pass)",
+            "roofline": {"kernel": "warp_variance_fwd2_kernel (+compose, +nchw_to_nhwc32 pre-pass)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes": alg_bytes, "ms": wv_ms},
@@ -259,6 +271,14 @@ def run_ours(args):
                                  "bound": "fp32-fma" if args.precision == "fp32" else "tensor",
                                  "peak_bf16_tensor": tf_peak},
         }
+        if world == 1 and not args.no_other_mode:
+            other = "fp32" if args.precision == "bf16" else "bf16"
+            del model, runner
+            torch.cuda.empty_cache()
+            o = measure(other, max(3, args.steps // 4), 3)
+            line["other_precision_mode"] = {"precision": other, "value": o["value"], "unit": UNIT,
+                                            "ms_per_step": o["max_ms"] / max(3, args.steps // 4),
+                                            "stage_ms": o["stage_ms"], "gpu_launches": o["launches"]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_port_depth_maps_per_s(args.workload, steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -274,7 +294,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16: CostRegNet on tcgen05 tensor cores (north_star's conv3d path); fp32: strict CUDA-core path")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other precision mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -115,6 +115,16 @@ size_t mvs_costreg_workspace_bytes(int B, int D, int H, int W, int precision);
 int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *params, float *logits, void *workspace, int B,
                     int D, int H, int W, int precision, void *stream);
 
+/* bf16 precision mode, fused layout: the warp+variance kernel writes the cost volume directly as bf16
+ * "CP8" [B][32/8][D][H][W][8] (mvs_volume_cp8_bytes bytes), which mvs_costreg_fwd_cp8 consumes on the
+ * tensor cores -- the fp32 volume and its conversion pass never exist.  Workspaces as for the fp32 calls
+ * (mvs_warp_variance_workspace_bytes / mvs_costreg_workspace_bytes with MVS_PRECISION_BF16). */
+size_t mvs_volume_cp8_bytes(int B, int D, int H, int W);
+int mvs_warp_variance_fwd_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8,
+                              void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
+int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *params, float *logits, void *workspace, int B,
+                        int D, int H, int W, void *stream);
+
 /* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
  *                                                        models/mvsnet.py:192-193,204,214-218
  * logits [B,D,H,W], depth_values [B,D] -> depth [B,H,W], conf [B,H,W]; prob [B,D,H,W] optional. */

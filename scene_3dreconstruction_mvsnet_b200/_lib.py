@@ -45,6 +45,10 @@ SIGNATURES = {
     "mvs_costreg_workspace_bytes": (ctypes.c_size_t, [_i] * 5),
     "mvs_costreg_fwd": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 5 +
                         [ctypes.c_void_p]),
+    "mvs_volume_cp8_bytes": (ctypes.c_size_t, [_i] * 4),
+    "mvs_warp_variance_fwd_cp8": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
+    "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
+                            [ctypes.c_void_p]),
     "mvs_softmax_depth_conf": (_i, [_c_float_p] * 5 + [_i] * 4 + [ctypes.c_void_p]),
     "mvs_depth_regression": (_i, [_c_float_p, _c_float_p, _i, _c_float_p] + [_i] * 4 + [ctypes.c_void_p]),
     "mvs_depth_from_features_host": (_i, [_c_float_p] * 3 + [ctypes.POINTER(CostRegParams), _c_float_p, _c_float_p] +

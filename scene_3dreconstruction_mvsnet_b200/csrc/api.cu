@@ -25,8 +25,10 @@ int conv3d_fp32(const float *x, const float *w, const float *shift, int relu, fl
                 int H, int W, int stride, cudaStream_t st);
 int convT3d_fp32(const float *x, const float *w, const float *shift, int relu, const float *skip, float *y, int B,
                  int Cin, int Cout, int D, int H, int W, cudaStream_t st);
-int costreg_tc(const float *volume, const mvs_costreg_params *p, float *logits, void *workspace, int B, int D, int H,
-               int W, cudaStream_t st);
+int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_params *p, float *logits, void *workspace,
+               int B, int D, int H, int W, cudaStream_t st);
+int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
+                      int B, int V, int D, int H, int W, cudaStream_t st);
 size_t costreg_tc_workspace_bytes(int B, int D, int H, int W);
 
 // layer table of CostRegNet (mvsnet.py:36-62): {Cin, Cout}; order conv0..conv6, conv7, conv9, conv11, prob
@@ -69,7 +71,7 @@ extern "C" int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *p,
     for (int i = 0; i < MVS_COSTREG_LAYERS; ++i)
         MVS_REQUIRE(p->w[i] && p->shift[i], "costreg params: layer %d has a null pointer", i);
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == MVS_PRECISION_BF16) return costreg_tc(volume, p, logits, workspace, B, D, H, W, st);
+    if (precision == MVS_PRECISION_BF16) return costreg_tc(volume, nullptr, p, logits, workspace, B, D, H, W, st);
     MVS_REQUIRE(precision == MVS_PRECISION_FP32, "unknown precision %d", precision);
 
     const size_t n0 = (size_t)D * H * W * B;
@@ -99,6 +101,32 @@ extern "C" int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *p,
     RUN(conv3d_fp32(u11, p->w[10], p->shift[10], 0, logits, B, 8, 1, D, H, W, 1, st));
 #undef RUN
     return MVS_OK;
+}
+
+// bf16 chunk-planar ("CP8") variants: the fused warp+variance kernel writes the tensor-core CostRegNet's input
+// layout directly, so the fp32 volume never exists in the bf16 precision mode.
+extern "C" size_t mvs_volume_cp8_bytes(int B, int D, int H, int W) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)B * 32 * D * H * W * 2;
+}
+
+extern "C" int mvs_warp_variance_fwd_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8,
+                                         void *workspace, int B, int V, int C, int D, int H, int W, void *stream) {
+    MVS_REQUIRE(fea && proj && depth_values && vol_cp8 && workspace, "null pointer argument");
+    MVS_REQUIRE(C == 32, "warp_variance: C must be 32, got %d", C);
+    MVS_REQUIRE(B > 0 && V >= 1 && V <= 64 && D > 0 && H > 1 && W > 1, "bad shape");
+    MVS_REQUIRE((long long)B * D <= 65535LL * 16 && (long long)H * W < (1LL << 27), "shape too large");
+    return warp_variance_cp8(fea, proj, depth_values, vol_cp8, workspace, B, V, D, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *p, float *logits, void *workspace,
+                                   int B, int D, int H, int W, void *stream) {
+    MVS_REQUIRE(vol_cp8 && p && logits && workspace, "null pointer argument");
+    MVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && D % 8 == 0 && H % 8 == 0 && W % 8 == 0,
+                "CostRegNet needs D, H, W divisible by 8 (got D=%d H=%d W=%d)", D, H, W);
+    for (int i = 0; i < MVS_COSTREG_LAYERS; ++i)
+        MVS_REQUIRE(p->w[i] && p->shift[i], "costreg params: layer %d has a null pointer", i);
+    return costreg_tc(nullptr, vol_cp8, p, logits, workspace, B, D, H, W, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------

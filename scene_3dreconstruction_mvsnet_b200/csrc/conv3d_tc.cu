@@ -704,21 +704,25 @@ size_t costreg_tc_workspace_bytes(int B, int D, int H, int W) {
     return align_up(act, 1024) + 11 * kWScratch + 16 * 1024;
 }
 
-int costreg_tc(const float *volume, const mvs_costreg_params *p, float *logits, void *workspace, int B, int D, int H,
-               int W, cudaStream_t st) {
+int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_params *p, float *logits, void *workspace,
+               int B, int D, int H, int W, cudaStream_t st) {
     int dev = 0, num_sms = 148;
     MVS_CUDA(cudaGetDevice(&dev));
     MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t n0 = (size_t)B * D * H * W;
     uint8_t *ws = (uint8_t *)workspace;
     auto take = [&](size_t bytes) { uint8_t *r = ws; ws += align_up(bytes, 1024); return r; };
-    void *vol = take(n0 * 64), *c0 = take(n0 * 16), *c1 = take(n0 * 4), *c2 = take(n0 * 4), *c3 = take(n0),
+    void *vol = take(volume_cp8 ? 0 : n0 * 64), *c0 = take(n0 * 16), *c1 = take(n0 * 4), *c2 = take(n0 * 4), *c3 = take(n0),
          *c4 = take(n0), *c5 = take(n0 / 4), *c6 = take(n0 / 4), *u7 = take(n0), *u9 = take(n0 * 4),
          *u11 = take(n0 * 16);
     uint8_t *wsc = take(11 * kWScratch);
     const size_t N = (size_t)D * H * W;
-    ncdhw_to_cp8_kernel<<<dim3(cdiv(N, 256), B * 4), 256, 0, st>>>(volume, (uint4 *)vol, 32, N);
-    MVS_LAUNCH_CHECK(1);
+    if (volume_cp8) {
+        vol = const_cast<void *>(volume_cp8);
+    } else {
+        ncdhw_to_cp8_kernel<<<dim3(cdiv(N, 256), B * 4), 256, 0, st>>>(volume, (uint4 *)vol, 32, N);
+        MVS_LAUNCH_CHECK(1);
+    }
     int rc;
 #define RUN(expr) if ((rc = (expr)) != MVS_OK) return rc
     RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st));

@@ -19,6 +19,8 @@
 //     groups of a warp covering one full 128-byte line of the NCDHW volume;
 //   * per-view warped volumes never exist in memory: HBM traffic is the algorithmic
 //     4*B*32*D*H*W bytes written + the feature maps read once.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mvs {
@@ -310,6 +312,187 @@ warp_volume_fwd_kernel(const float *__restrict__ fea,       // [B,V,32,H,W]; vie
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward, second generation (variance only).  ncu on the first version showed the L1 data pipe
+// (l1tex__data_pipe_lsu_wavefronts) at 73 % of peak: every byte delivered to a register costs a
+// wavefront slot, so the per-step exchange of 4 offsets + 4 weights (2 x LDS.128 = 8 wavefronts
+// against 16 for the taps themselves) was a third of the traffic.  Here lane L publishes the four
+// zero-masked interpolation FACTORS (ax, bx, ay, by) and ONE packed base offset (clamped texel
+// index + the two clamp-aware increments in bits 30/31): LDS.128 + LDS.32 = 5 wavefronts; the four
+// weights are re-formed with 4 multiplies per step.  Masking the factors instead of the products
+// gives bit-identical weights (a product with a zeroed factor is the zero the mask would write).
+// OUT_CP8 writes the volume directly as bf16 [32/8][D][H][W][8] (the tensor-core CostRegNet's input
+// layout), pairing even/odd channel-group lanes with shuffles so that every store is a full 16-byte
+// voxel chunk: the fp32 volume and its conversion pass disappear and the HBM write halves.
+// ------------------------------------------------------------------------------------------------
+struct PackedTap {
+    float4 f;       // ax, bx, ay, by  (zeroed where the corresponding column / row is out of range)
+    uint32_t base;  // (cy0*W + cx0) | (cx1 != cx0) << 30 | (cy1 != cy0) << 31
+};
+
+__device__ __forceinline__ PackedTap sample_packed(const float *__restrict__ rt, float x, float y, float d, int H, int W) {
+    const float rx = __fadd_rn(__fadd_rn(__fmul_rn(rt[0], x), __fmul_rn(rt[1], y)), rt[2]);
+    const float ry = __fadd_rn(__fadd_rn(__fmul_rn(rt[3], x), __fmul_rn(rt[4], y)), rt[5]);
+    const float rz = __fadd_rn(__fadd_rn(__fmul_rn(rt[6], x), __fmul_rn(rt[7], y)), rt[8]);
+    const float qx = __fadd_rn(__fmul_rn(rx, d), rt[9]);
+    const float qy = __fadd_rn(__fmul_rn(ry, d), rt[10]);
+    const float qz = __fadd_rn(__fmul_rn(rz, d), rt[11]);
+    const float px = __fdiv_rn(qx, qz);
+    const float py = __fdiv_rn(qy, qz);
+    const float gx = __fsub_rn(__fdiv_rn(px, (float)(W - 1) * 0.5f), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(py, (float)(H - 1) * 0.5f), 1.0f);
+    const float ix = safe_coord(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 0.5f));
+    const float iy = safe_coord(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 0.5f));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+    PackedTap t;
+    t.f.x = vx0 ? __fsub_rn(__fadd_rn(fx0, 1.0f), ix) : 0.f;
+    t.f.y = vx1 ? __fsub_rn(ix, fx0) : 0.f;
+    t.f.z = vy0 ? __fsub_rn(__fadd_rn(fy0, 1.0f), iy) : 0.f;
+    t.f.w = vy1 ? __fsub_rn(iy, fy0) : 0.f;
+    t.base = (uint32_t)(cy0 * W + cx0) | ((uint32_t)(cx1 != cx0) << 30) | ((uint32_t)(cy1 != cy0) << 31);
+    return t;
+}
+
+enum { OUT_F32 = 0, OUT_CP8 = 1 };
+
+template <int OUT>
+__global__ void __launch_bounds__(kThreads, 2)
+warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W]; view 0 = reference view
+                          const float4 *__restrict__ src_cl,     // [B*nsrc][H*W][8] float4, channels-last
+                          const float *__restrict__ rt,          // [B*nsrc][12]
+                          const float *__restrict__ depth_values,  // [B,D]
+                          void *__restrict__ out_,               // OUT_F32: [B,32,D,H,W] fp32; OUT_CP8: bf16 [B,4,D,H,W,8]
+                          int V, int nsrc, int D, int H, int W, int dchunk) {
+    __shared__ float4 s_f[kWarps][32];
+    __shared__ uint32_t s_b[kWarps][32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = lane >> 3, g = lane & 7;
+    const int nchunks = (D + dchunk - 1) / dchunk;
+    const int b = blockIdx.z / nchunks;
+    const int d_begin = (blockIdx.z % nchunks) * dchunk;
+    const int d_end = min(D, d_begin + dchunk);
+    const int y = blockIdx.y * kWarps + warp;
+    if (y >= H) return;  // warp-uniform; only __syncwarp / full-mask shuffles below
+    const int x0 = blockIdx.x * 32;
+    const int xr = x0 + 8 * p;
+    const size_t HW = (size_t)H * W;
+    const bool vec_ok = ((W & 3) == 0);
+    const float invV = 1.0f / (float)V;
+    const float xl = (float)(x0 + lane), yf = (float)y;
+    const int W8 = W * 8;  // float4 units per texel row
+
+    for (int d = d_begin; d < d_end; ++d) {
+        const float dep = __ldg(depth_values + (size_t)b * D + d);
+        float S[8][4], Q[8][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *r = fea + (((size_t)b * V) * kC + 4 * g + j) * HW + (size_t)y * W + xr;
+            float v[8];
+            if (vec_ok && xr + 7 < W) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(r));
+                const float4 c = __ldg(reinterpret_cast<const float4 *>(r) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = (xr + i < W) ? __ldg(r + i) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                S[i][j] = v[i];
+                Q[i][j] = v[i] * v[i];
+            }
+        }
+
+        for (int v = 0; v < nsrc; ++v) {
+            const int n = b * nsrc + v;
+            const PackedTap t = sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+            __syncwarp();
+            s_f[warp][lane] = t.f;
+            s_b[warp][lane] = t.base;
+            __syncwarp();
+            const float4 *f = src_cl + (size_t)n * HW * 8 + g;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 fc = s_f[warp][8 * p + i];
+                const uint32_t bb = s_b[warp][8 * p + i];
+                const float4 *p00 = f + (size_t)(bb & 0x3FFFFFFFu) * 8;
+                const float4 *p01 = p00 + ((bb >> 30) & 1u) * 8;
+                const int dyo = (bb >> 31) ? W8 : 0;
+                const float4 a = __ldg(p00), bq = __ldg(p01), c = __ldg(p00 + dyo), dq = __ldg(p01 + dyo);
+                const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
+                const float vx = fmaf(dq.x, w11, fmaf(c.x, w10, fmaf(bq.x, w01, a.x * w00)));
+                const float vy = fmaf(dq.y, w11, fmaf(c.y, w10, fmaf(bq.y, w01, a.y * w00)));
+                const float vz = fmaf(dq.z, w11, fmaf(c.z, w10, fmaf(bq.z, w01, a.z * w00)));
+                const float vw = fmaf(dq.w, w11, fmaf(c.w, w10, fmaf(bq.w, w01, a.w * w00)));
+                S[i][0] += vx; Q[i][0] = fmaf(vx, vx, Q[i][0]);
+                S[i][1] += vy; Q[i][1] = fmaf(vy, vy, Q[i][1]);
+                S[i][2] += vz; Q[i][2] = fmaf(vz, vz, Q[i][2]);
+                S[i][3] += vw; Q[i][3] = fmaf(vw, vw, Q[i][3]);
+            }
+        }
+
+        if (OUT == OUT_F32) {
+            float *out = reinterpret_cast<float *>(out_);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float m = S[i][j] * invV;
+                    r[i] = fmaf(Q[i][j], invV, -m * m);  // Q/V - (S/V)^2   (mvsnet.py:177)
+                }
+                float *o = out + (((size_t)b * kC + 4 * g + j) * D + d) * HW + (size_t)y * W + xr;
+                if (vec_ok && xr + 7 < W) {
+                    __stcs(reinterpret_cast<float4 *>(o), make_float4(r[0], r[1], r[2], r[3]));
+                    __stcs(reinterpret_cast<float4 *>(o) + 1, make_float4(r[4], r[5], r[6], r[7]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (xr + i < W) o[i] = r[i];
+                }
+            }
+        } else {
+            // bf16 chunk-planar output.  This lane holds channels 4g..4g+3 of 8 pixels; its partner (g ^ 1) holds
+            // the other half of the same 8-channel chunk.  Even-g lanes keep even pixels, odd-g lanes odd pixels.
+            uint4 *out = reinterpret_cast<uint4 *>(out_);
+            const int odd = g & 1;
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+                uint32_t mine[2], give[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int ik = 2 * i2 + h;  // h == odd: the pixel this lane keeps
+                    float r[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float m = S[ik][j] * invV;
+                        r[j] = fmaf(Q[ik][j], invV, -m * m);
+                    }
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&lo), w1 = *reinterpret_cast<const uint32_t *>(&hi);
+                    if (h == 0) { mine[0] = w0; mine[1] = w1; } else { give[0] = w0; give[1] = w1; }
+                }
+                // even lane: keeps pixel 2*i2 (mine), gives pixel 2*i2+1 (give); odd lane: the opposite
+                const uint32_t k0 = odd ? give[0] : mine[0], k1 = odd ? give[1] : mine[1];
+                const uint32_t s0 = odd ? mine[0] : give[0], s1 = odd ? mine[1] : give[1];
+                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                const int x = xr + 2 * i2 + odd;
+                if (x < W) {
+                    const uint4 pk = odd ? make_uint4(r0, r1, k0, k1) : make_uint4(k0, k1, r0, r1);
+                    out[(((size_t)b * 4 + (g >> 1)) * D + d) * HW + (size_t)y * W + x] = pk;
+                }
+            }
+        }
+    }
+}
+
 // Generic-C fallback of the standalone homo_warping (any channel count, NCHW gathers).  Used only
 // when C != 32; one thread per (x, y, d), looping over channels.
 __global__ void homo_warp_generic_kernel(const float *__restrict__ src, const float *__restrict__ rt,
@@ -535,11 +718,33 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
     }
     const int dchunk = pick_dchunk(B, D, H, W);
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-    warp_volume_fwd_kernel<MODE_VAR><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, var, V,
-                                                                nsrc, D, H, W, dchunk);
+    warp_variance_fwd2_kernel<OUT_F32><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, var, V,
+                                                                  nsrc, D, H, W, dchunk);
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }
+
+// Internal: same op, output written as bf16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
+namespace mvs {
+int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
+                      int B, int V, int D, int H, int W, cudaStream_t st) {
+    const int nsrc = V - 1;
+    float *rt = (float *)workspace;
+    float *src_cl = (float *)((char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float)));
+    const int HW = H * W;
+    if (nsrc > 0) {
+        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+        nchw_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src_cl, HW, nsrc, V);
+        MVS_LAUNCH_CHECK(1);
+    }
+    const int dchunk = pick_dchunk(B, D, H, W);
+    dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
+    warp_variance_fwd2_kernel<OUT_CP8><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, vol_cp8,
+                                                                  V, nsrc, D, H, W, dchunk);
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+}  // namespace mvs
 
 extern "C" int mvs_homo_warping(const float *src_fea, const float *src_proj, const float *ref_proj,
                                 const float *depth_values, float *out, int B, int C, int D, int H, int W,

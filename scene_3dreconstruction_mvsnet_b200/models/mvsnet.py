@@ -131,7 +131,16 @@ class MVSNet(nn.Module):
         B, V = imgs.shape[:2]
         if self.training:
             return torch.stack([self.feature(img) for img in torch.unbind(imgs, 1)], 1)
-        f = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        # channels_last suits cuDNN better for these tiny channel counts (measured on B200 at 5 x 1152x1600:
+        # NCHW fp32 11.7 ms, NHWC fp32 9.8 ms, NHWC with TF32 allowed 3.0 ms)
+        x = imgs.reshape(B * V, *imgs.shape[2:]).contiguous(memory_format=torch.channels_last)
+        if self.precision == "bf16":
+            # reduced-precision mode: let cuDNN use its TF32 tensor-core kernels for FeatureNet (PyTorch's own
+            # default for convolutions, i.e. what the reference does on a GPU); fp32 mode keeps the ambient setting
+            with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=True):
+                f = self.feature(x).contiguous()
+        else:
+            f = self.feature(x).contiguous()
         return f.view(B, V, *f.shape[1:])
 
     def forward(self, imgs, proj_matrices, depth_values):
@@ -152,6 +161,17 @@ class MVSNet(nn.Module):
         mark("features")
         proj_matrices = proj_matrices.float()
         depth_values = depth_values.float()
+        if not torch.is_grad_enabled() and not self.training and self.precision == "bf16":
+            # tensor-core mode: the cost volume goes from the fused warp+variance kernel to the tcgen05 CostRegNet
+            # as bf16 chunk-planar data; no fp32 volume is written
+            logits = ops.warp_variance_costreg_bf16(fea, proj_matrices, depth_values,
+                                                    self.cost_regularization.folded_params(), marks=mark)
+            mark("cost_regularization")
+            depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
+            mark("depth_tail")
+            if marks is not None:
+                self.stage_events.append(marks)
+            return {"depth": depth, "photometric_confidence": photometric_confidence}
         volume_variance = ops.warp_variance(fea, proj_matrices, depth_values)
         mark("warp_variance")
 

@@ -32,8 +32,25 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _ws(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+_WS_CACHE = {}
+
+
+def _ws(nbytes, device, tag=None):
+    """Scratch device memory.  With a tag the buffer is kept and reused by later calls on the same device and
+    stream (stream-ordered reuse is safe; it spares the caching allocator multi-GB alloc/free churn per step)."""
+    nbytes = max(int(nbytes), 16)
+    if tag is None:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (tag, torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WS_CACHE[key] = buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+def release_workspaces():
+    """Drop every cached scratch buffer (they are re-created on demand)."""
+    _WS_CACHE.clear()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -107,7 +124,7 @@ def warp_variance_fwd(fea, proj, depth_values):
         raise RuntimeError("depth_values batch %d != %d" % (depth_values.shape[0], B))
     lib = _lib.load()
     var = torch.empty((B, C, D, H, W), dtype=torch.float32, device=fea.device)
-    ws = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
+    ws = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device, "warp")
     with torch.cuda.device(fea.device):
         rc = lib.mvs_warp_variance_fwd(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(var), _ptr(ws), B, V, C, D, H, W,
                                        _stream(fea))
@@ -212,12 +229,75 @@ def cost_regularization(volume, folded, precision="fp32"):
     nbytes = lib.mvs_costreg_workspace_bytes(B, D, H, W, prec)
     if nbytes == 0:
         raise RuntimeError("CostRegNet needs D, H, W divisible by 8 (got D=%d H=%d W=%d)" % (D, H, W))
-    ws = _ws(nbytes, volume.device)
+    ws = _ws(nbytes, volume.device, "costreg")
     logits = torch.empty((B, D, H, W), dtype=torch.float32, device=volume.device)
     with torch.cuda.device(volume.device):
         rc = lib.mvs_costreg_fwd(_ptr(volume), ctypes.byref(params), _ptr(logits), _ptr(ws), B, D, H, W, prec,
                                  _stream(volume))
     _lib.check(rc, "mvs_costreg_fwd")
+    return logits
+
+
+def _costreg_params(folded):
+    if len(folded) != _lib.COSTREG_LAYERS:
+        raise RuntimeError("cost_regularization expects %d folded layers" % _lib.COSTREG_LAYERS)
+    params = _lib.CostRegParams()
+    keep = []
+    for i, (w, s) in enumerate(folded):
+        w, s = _prep(w, "weight%d" % i), _prep(s, "shift%d" % i)
+        keep += [w, s]
+        params.w[i] = w.data_ptr()
+        params.shift[i] = s.data_ptr()
+    return params, keep
+
+
+def warp_variance_cp8(fea, proj, depth_values):
+    """Fused warp+variance with the bf16 chunk-planar output: returns a bf16 tensor [B, 4, D, h, w, 8]
+    (channel = chunk*8 + last index).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
+    fea = _prep(fea, "features", 5)
+    proj = _prep(proj, "proj_matrices", 4)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    B, V, C, H, W = fea.shape
+    D = depth_values.shape[1]
+    lib = _lib.load()
+    vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.bfloat16, device=fea.device)
+    ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
+    with torch.cuda.device(fea.device):
+        rc = lib.mvs_warp_variance_fwd_cp8(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H,
+                                           W, _stream(fea))
+    _lib.check(rc, "mvs_warp_variance_fwd_cp8")
+    return vol
+
+
+def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
+    """bf16 precision mode: fused warp+variance writing the bf16 CP8 volume, then the tcgen05 CostRegNet.
+    fea [B,V,32,h,w] -> logits [B,D,h,w] (fp32).  `marks`, if a callable, is invoked between the two kernels
+    families (stage timing)."""
+    fea = _prep(fea, "features", 5)
+    proj = _prep(proj, "proj_matrices", 4)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    B, V, C, H, W = fea.shape
+    D = depth_values.shape[1]
+    if proj.shape != (B, V, 4, 4):
+        raise RuntimeError("Different number of images and projection matrices: features %s proj %s"
+                           % (tuple(fea.shape), tuple(proj.shape)))
+    lib = _lib.load()
+    params, keep = _costreg_params(folded)
+    nbytes = lib.mvs_costreg_workspace_bytes(B, D, H, W, _lib.PRECISION_BF16)
+    if nbytes == 0:
+        raise RuntimeError("CostRegNet needs D, H, W divisible by 8 (got D=%d H=%d W=%d)" % (D, H, W))
+    vol = _ws(lib.mvs_volume_cp8_bytes(B, D, H, W), fea.device, "vol_cp8")
+    ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device, "warp")
+    ws2 = _ws(nbytes, fea.device, "costreg")
+    logits = torch.empty((B, D, H, W), dtype=torch.float32, device=fea.device)
+    with torch.cuda.device(fea.device):
+        rc = lib.mvs_warp_variance_fwd_cp8(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H,
+                                           W, _stream(fea))
+        _lib.check(rc, "mvs_warp_variance_fwd_cp8")
+        if marks is not None:
+            marks("warp_variance")
+        rc = lib.mvs_costreg_fwd_cp8(_ptr(vol), ctypes.byref(params), _ptr(logits), _ptr(ws2), B, D, H, W, _stream(fea))
+        _lib.check(rc, "mvs_costreg_fwd_cp8")
     return logits
 
 
