@@ -41,6 +41,7 @@ SIGNATURES = {
     "mvs_conv3d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
     "mvs_conv_transpose3d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p, _c_float_p] + [_i] * 6 +
                                         [ctypes.c_void_p]),
+    "mvs_tc_set_debug_buffer": (_i, [ctypes.c_void_p]),
     "mvs_tc_plan_describe": (_i, [_i] * 8 + [ctypes.c_char_p, _i]),
     "mvs_costreg_workspace_bytes": (ctypes.c_size_t, [_i] * 5),
     "mvs_costreg_fwd": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 5 +

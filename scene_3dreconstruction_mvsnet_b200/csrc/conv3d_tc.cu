@@ -18,7 +18,7 @@
 //
 // A CTA (persistent, one per SM) walks a column of the volume along z: each new input plane is
 // loaded exactly once into a ring of NSLOT planes and reused by the 3 (or 2) z-steps that need it.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue.
 #include <algorithm>
 #include <mutex>
 #include <string.h>
@@ -44,7 +44,7 @@ tmap_encode_fn get_tmap_encode() {
 
 constexpr int kMaxOps = 112;
 constexpr int kMaxAcc = 8;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 
 struct TcOp {
     uint32_t a_off;     // byte offset of the A operand inside its ring plane (sub-plane + tap + chunk pair)
@@ -76,12 +76,14 @@ struct TcLayer {
     uint8_t seg_plane[2 * kMaxAcc + 4], seg_acc[2 * kMaxAcc + 4], seg_new_acc[2 * kMaxAcc + 4];
     // epilogue
     int out_scale, acc_pz[kMaxAcc], acc_py[kMaxAcc], acc_px[kMaxAcc];
+    int acc_voff[kMaxAcc];  // (pz*Hout + py)*Wout + px
     int cout_group, cout_total, relu, out_f32;
     int Dout, Hout, Wout;
     void *out;
     const uint4 *skip;
     const float *shift;
     const uint4 *wpacked;
+    long long *dbg;  // optional [gridDim.x][8] cycle counters (tools/tc_profile.py); nullptr in production
     TcOp ops[kMaxOps];
 };
 
@@ -127,7 +129,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 256);  // [kMaxOps] {A desc lo (no slot base), B desc lo}
-    constexpr uint32_t kHdr = 256 + kMaxOps * 8;
+    float *s_shift = reinterpret_cast<float *>(smem + 256 + kMaxOps * 8);  // [64] folded shifts of this channel group
+    constexpr uint32_t kHdr = 256 + kMaxOps * 8 + 256;
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     // descriptor high word: SBO = 128 B (8 rows x 16 B), version 1 (Blackwell), no swizzle
@@ -149,6 +152,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     }
     for (int o = threadIdx.x; o < L.nops; o += kTcThreads)
         optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
+    if (threadIdx.x < 64)
+        s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + group * L.cout_group + threadIdx.x) : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
@@ -156,7 +161,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(tfull_bar(b), 1);
-            ptx::mbar_init(tempty_bar(b), 4);
+            ptx::mbar_init(tempty_bar(b), 8);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmap);
@@ -189,6 +194,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t g = 0;
+            long long prod_wait = 0;
             const uint32_t tx_bytes = (uint32_t)L.nsub * L.sub_bytes;
             for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
                 int b, x0, y0, zs, T;
@@ -196,7 +202,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 const int nplanes = L.adv * (T - 1) + L.need;
                 for (int j = 0; j < nplanes; ++j, ++g) {
                     const int slot = g % L.nslot;
+                    const long long c0 = clock64();
                     ptx::mbar_wait(empty_bar(slot), ((g / L.nslot) & 1) ^ 1);
+                    prod_wait += clock64() - c0;
                     ptx::mbar_arrive_expect_tx(full_bar(slot), tx_bytes);
                     const int pz = L.zscale * zs + L.pz0 + j;
                     if (L.merged_x) {  // inner dimension = 16*P contiguous bytes per row (uint64 elements)
@@ -210,6 +218,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     }
                 }
             }
+            if (L.dbg) L.dbg[blockIdx.x * 8 + 0] = prod_wait;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -217,89 +226,153 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
         const bool leader = ptx::elect_one();
         const uint32_t idesc = ptx::make_idesc_bf16_m128(NPAD);
-        uint32_t g = 0, st = 0;
+        uint32_t st = 0;
+        uint32_t s0 = 0;    // ring slot of the oldest plane of the current step
+        uint32_t par = 0;   // bit s: parity of the fill of slot s that is current (toggles when the slot is released)
+        long long w_full = 0, w_tempty = 0, t_issue = 0;
+        const long long t_start = clock64();
+        const uint32_t nslot = L.nslot, need = L.need, adv = L.adv;
+        auto wrap = [&](uint32_t s) { return s >= nslot ? s - nslot : s; };
         for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
             for (int t = 0; t < T; ++t, ++st) {
-                const uint32_t g0 = g + (uint32_t)L.adv * t;
                 const uint32_t buf = st & 1;
+                const uint32_t sl0 = s0, sl1 = wrap(s0 + 1), sl2 = wrap(s0 + 2);
                 if (leader) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
-                    for (int r = 0; r < L.need; ++r) {
-                        const uint32_t gi = g0 + r;
-                        ptx::mbar_wait(full_bar(gi % L.nslot), (gi / L.nslot) & 1);
+                    const long long c0 = clock64();
+                    // planes already waited for in earlier steps of this item need no second look
+                    for (uint32_t r = (t == 0) ? 0 : need - adv; r < need; ++r) {
+                        const uint32_t sl = wrap(s0 + r);
+                        ptx::mbar_wait(full_bar(sl), (par >> sl) & 1u);
                     }
+                    const long long c1 = clock64();
                     ptx::mbar_wait(tempty_bar(buf), ((st >> 1) & 1) ^ 1);
+                    w_full += c1 - c0;
+                    w_tempty += clock64() - c1;
                 }
                 __syncwarp();
                 ptx::tcgen05_fence_after();
                 if (leader) {
-                    const uint32_t sb0 = (ring_base + ((g0 + 0) % L.nslot) * L.slot_bytes) >> 4;
-                    const uint32_t sb1 = (ring_base + ((g0 + 1) % L.nslot) * L.slot_bytes) >> 4;
-                    const uint32_t sb2 = (ring_base + ((g0 + 2) % L.nslot) * L.slot_bytes) >> 4;
+                    const long long ci = clock64();
+                    const uint32_t sb0 = (ring_base + sl0 * L.slot_bytes) >> 4;
+                    const uint32_t sb1 = (ring_base + sl1 * L.slot_bytes) >> 4;
+                    const uint32_t sb2 = (ring_base + sl2 * L.slot_bytes) >> 4;
                     const uint32_t tbuf = tmem_base + buf * ncols_buf;
                     if (L.MT == 4) issue_step<NPAD, 4>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
                     else if (L.MT == 2) issue_step<NPAD, 2>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
                     else if (L.MT == 1) issue_step<NPAD, 1>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
                     else issue_step<NPAD, 3>(L, optab, tbuf, sb0, sb1, sb2, idesc, kDescHi);
+                    t_issue += clock64() - ci;
                 }
-                if (leader) {
-                    for (int r = 0; r < L.adv; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
-                    if (t == T - 1)
-                        for (int r = L.adv; r < L.need; ++r) ptx::tcgen05_commit(empty_bar((g0 + r) % L.nslot));
-                    ptx::tcgen05_commit(tfull_bar(buf));
+                // release the planes this step was the last user of (all of them at the end of an item)
+                const uint32_t nrel = (t == T - 1) ? need : adv;
+                for (uint32_t r = 0; r < nrel; ++r) {
+                    const uint32_t sl = wrap(s0 + r);
+                    if (leader) ptx::tcgen05_commit(empty_bar(sl));
+                    par ^= 1u << sl;
                 }
+                if (leader) ptx::tcgen05_commit(tfull_bar(buf));
+                s0 = wrap(s0 + nrel);
                 __syncwarp();
             }
-            g += (uint32_t)(L.adv * (T - 1) + L.need);
+        }
+        if (leader && L.dbg) {
+            L.dbg[blockIdx.x * 8 + 1] = w_full;
+            L.dbg[blockIdx.x * 8 + 2] = w_tempty;
+            L.dbg[blockIdx.x * 8 + 3] = t_issue;
+            L.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+            L.dbg[blockIdx.x * 8 + 5] = st;
         }
     } else {
         // ================= epilogue (4 warps = 128 TMEM lanes) =================
+        // Per item the (row, col) of each of this thread's <= 4 M-tile rows and its output voxel offset are fixed;
+        // only z advances.  Per z-step the (M-tile, accumulator) pairs are drained in batches of G = 64/NPAD:
+        // all tcgen05.ld of a batch are issued back to back, the skip-connection loads of the batch are issued
+        // while they fly, then one tcgen05.wait::ld -- so TMEM and global latencies overlap instead of adding up.
+        constexpr int G = 64 / NPAD;
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int eset = (warp - 2) >> 2;  // the two warps of a quadrant alternate over the batches of a step
         const uint4 *skip = L.skip;
+        const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
+        const size_t zstride = (size_t)L.out_scale * L.Hout * L.Wout;
+        const int nacc_shift = (L.nacc == 8) ? 3 : 0;
+        const int npairs = L.MT << nacc_shift;
+        const int nchunk = (L.cout_group + 7) >> 3;
+        const int chunk0 = (group * L.cout_group) >> 3;  // first output chunk of this CTA's channel group
         uint32_t st = 0;
+        long long epi_wait = 0, epi_work = 0;
         for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
-            for (int t = 0; t < T; ++t, ++st) {
-                const uint32_t buf = st & 1;
-                ptx::mbar_wait(tfull_bar(buf), (st >> 1) & 1);
-                ptx::tcgen05_fence_after();
-                const int z = zs + t;
-                for (int mt = 0; mt < L.MT; ++mt) {
+            size_t base0 = 0, base1 = 0, base2 = 0, base3 = 0;
+            uint32_t vmask = 0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                if (mt < L.MT) {
                     const int pos = mt * 128 + q * 32 + lane;
                     const int y = pos / L.P, x = pos - y * L.P;
                     const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
-                    for (int a = 0; a < L.nacc; ++a) {
-                        const uint32_t taddr =
-                            tmem_base + ((uint32_t)(q * 32) << 16) + buf * ncols_buf + (a * L.MT + mt) * NPAD;
-                        const int oz = L.out_scale * z + L.acc_pz[a];
-                        const int oy = L.out_scale * (y0 + y) + L.acc_py[a];
-                        const int ox = L.out_scale * (x0 + x) + L.acc_px[a];
-                        const size_t vox = ((size_t)oz * L.Hout + oy) * L.Wout + ox;
-                        const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
+                    const size_t bs = (size_t)(L.out_scale * (y0 + y)) * L.Wout + (size_t)L.out_scale * (x0 + x);
+                    vmask |= (valid ? 1u : 0u) << mt;
+                    if (mt == 0) base0 = bs; else if (mt == 1) base1 = bs; else if (mt == 2) base2 = bs; else base3 = bs;
+                }
+            }
+            for (int t = 0; t < T; ++t, ++st) {
+                const uint32_t buf = st & 1;
+                const long long c0 = clock64();
+                ptx::mbar_wait(tfull_bar(buf), (st >> 1) & 1);
+                const long long c1 = clock64();
+                epi_wait += c1 - c0;
+                ptx::tcgen05_fence_after();
+                const size_t zoff = (size_t)(zs + t) * zstride;
+                const uint32_t tbuf = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ncols_buf;
+                for (int p0 = eset * G; p0 < npairs; p0 += 2 * G) {
+                    uint32_t r[G][NPAD];
+                    uint4 sk[G][NPAD / 8];
+                    size_t vox[G];
+                    bool ok[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        const int pr = p0 + j;
+                        ok[j] = false;
+                        vox[j] = 0;
+                        if (pr < npairs) {  // warp-uniform
+                            const int mt = pr >> nacc_shift, a = pr & (L.nacc - 1);
+#pragma unroll
+                            for (int c8 = 0; c8 < NPAD / 8; ++c8)
+                                if (c8 < nchunk) ptx::tmem_ld_x8(tbuf + (a * L.MT + mt) * NPAD + c8 * 8, &r[j][c8 * 8]);
+                            const size_t bs = mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3));
+                            ok[j] = (vmask >> mt) & 1u;
+                            vox[j] = bs + zoff + (size_t)L.acc_voff[a];
+                        }
+                    }
+                    if (skip != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < G; ++j)
+#pragma unroll
+                            for (int c8 = 0; c8 < NPAD / 8; ++c8)
+                                if (ok[j] && c8 < nchunk)
+                                    sk[j][c8] = __ldg(skip + ((size_t)b * (L.cout_total / 8) + chunk0 + c8) * plane + vox[j]);
+                    }
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        if (!ok[j]) continue;
 #pragma unroll
                         for (int c8 = 0; c8 < NPAD / 8; ++c8) {
-                            if (c8 * 8 >= L.cout_group) break;   // padded accumulator columns (warp-uniform)
-                            uint32_t r[8];
-                            ptx::tmem_ld_x8(taddr + c8 * 8, r);  // warp-collective: outside the validity branch
-                            ptx::tmem_ld_wait();
-                            const int co = group * L.cout_group + c8 * 8;  // first real output channel of this chunk
-                            if (!valid) continue;
+                            if (c8 >= nchunk) break;
                             float v[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const int ch = min(co + e, L.cout_total - 1);
-                                v[e] = __uint_as_float(r[e]) + __ldg(L.shift + ch);
+                                v[e] = __uint_as_float(r[j][c8 * 8 + e]) + s_shift[c8 * 8 + e];
                                 if (L.relu) v[e] = fmaxf(v[e], 0.f);
                             }
                             if (L.out_f32) {  // single-channel fp32 output (the prob layer): [B][D][H][W]
-                                reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
+                                reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox[j]] = v[0];
                             } else {
-                                const size_t o16 = ((size_t)b * (L.cout_total / 8) + co / 8) * plane + vox;
                                 if (skip != nullptr) {  // skip + relu(bn(convT))  (mvsnet.py:69-71)
-                                    const uint4 s = __ldg(skip + o16);
-                                    const __nv_bfloat162 *sp = reinterpret_cast<const __nv_bfloat162 *>(&s);
+                                    const __nv_bfloat162 *sp = reinterpret_cast<const __nv_bfloat162 *>(&sk[j][c8]);
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
                                         const float2 f = __bfloat1622float2(sp[e]);
@@ -312,7 +385,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                 pk.y = pack_bf16x2(v[2], v[3]);
                                 pk.z = pack_bf16x2(v[4], v[5]);
                                 pk.w = pack_bf16x2(v[6], v[7]);
-                                reinterpret_cast<uint4 *>(L.out)[o16] = pk;
+                                reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + chunk0 + c8) * plane + vox[j]] = pk;
                             }
                         }
                     }
@@ -320,7 +393,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 ptx::tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+                epi_work += clock64() - c1;
             }
+        }
+        if (warp == 2 && lane == 0 && L.dbg) {
+            L.dbg[blockIdx.x * 8 + 6] = epi_wait;
+            L.dbg[blockIdx.x * 8 + 7] = epi_work;
         }
     }
 
@@ -470,7 +548,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
-                const size_t total = 256 + kMaxOps * 8 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -599,6 +677,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         L.acc_first[8] = nops;
     }
     MVS_REQUIRE(nops == ntaps_ops, "tc conv: internal op count mismatch (%d vs %d)", nops, ntaps_ops);
+    for (int a = 0; a < nacc; ++a) L.acc_voff[a] = (L.acc_pz[a] * L.Hout + L.acc_py[a]) * L.Wout + L.acc_px[a];
+    MVS_REQUIRE((long long)L.Dout * L.Hout * L.Wout < (1LL << 31), "tc conv: volume too large for 32-bit class offsets");
     L.nops = nops;
     W.nblocks = nops;
     {   // order ops by (accumulator group, ring plane); the packed weight block follows its op (widx = position)
@@ -631,7 +711,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     }
     pl.npad = npad;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
-    pl.smem_bytes = 256 + kMaxOps * 8 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
@@ -665,6 +745,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     return MVS_OK;
 }
 
+static long long *g_tc_dbg = nullptr;  // set by mvs_tc_set_debug_buffer (diagnostics only)
+
 static int run_layer(TcKind kind, const void *in, const float *w_fp32, const float *shift, int relu, const void *skip,
                      void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
                      int num_sms, cudaStream_t st) {
@@ -676,6 +758,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     pl.L.relu = relu;
     pl.L.out_f32 = out_f32;
     pl.L.wpacked = (const uint4 *)wpacked_scratch;
+    pl.L.dbg = g_tc_dbg;
     const int nw = (int)(pl.wpacked_bytes / 2);
     pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)wpacked_scratch, pl.W);
     MVS_LAUNCH_CHECK(1);
@@ -794,6 +877,13 @@ extern "C" int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, c
     MVS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "bad shape");
     MVS_REQUIRE(Cin % 16 == 0 && Cout % 8 == 0, "tensor-core conv_transpose3d needs Cin %% 16 == 0 and Cout %% 8 == 0");
     return tc_layer_ncdhw(TC_CONVT, x, w, shift, relu, skip, y, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
+}
+
+// Diagnostics: device buffer of [grid][8] int64 cycle counters filled by the next tensor-core layer launches
+// (producer wait, MMA wait-full / wait-tmem / issue / total / steps, epilogue wait / work).  nullptr disables.
+extern "C" int mvs_tc_set_debug_buffer(void *buf) {
+    g_tc_dbg = (long long *)buf;
+    return MVS_OK;
 }
 
 // Diagnostics: the tile / ring / grid configuration the planner picks for one layer (no GPU needed).

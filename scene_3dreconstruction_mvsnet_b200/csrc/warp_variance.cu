@@ -19,7 +19,9 @@
 //     groups of a warp covering one full 128-byte line of the NCDHW volume;
 //   * per-view warped volumes never exist in memory: HBM traffic is the algorithmic
 //     4*B*32*D*H*W bytes written + the feature maps read once.
+#include <algorithm>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -358,6 +360,41 @@ __device__ __forceinline__ PackedTap sample_packed(const float *__restrict__ rt,
     return t;
 }
 
+// Same arithmetic, split in two: R*(x,y,1) depends only on (pixel, view) and is hoisted out of the depth walk.
+__device__ __forceinline__ void rot_pixel(const float *__restrict__ rt, float x, float y, float &rx, float &ry, float &rz) {
+    rx = __fadd_rn(__fadd_rn(__fmul_rn(rt[0], x), __fmul_rn(rt[1], y)), rt[2]);
+    ry = __fadd_rn(__fadd_rn(__fmul_rn(rt[3], x), __fmul_rn(rt[4], y)), rt[5]);
+    rz = __fadd_rn(__fadd_rn(__fmul_rn(rt[6], x), __fmul_rn(rt[7], y)), rt[8]);
+}
+
+__device__ __forceinline__ PackedTap sample_packed_r(float rx, float ry, float rz, float tx, float ty, float tz, float d,
+                                                     int H, int W) {
+    const float qx = __fadd_rn(__fmul_rn(rx, d), tx);
+    const float qy = __fadd_rn(__fmul_rn(ry, d), ty);
+    const float qz = __fadd_rn(__fmul_rn(rz, d), tz);
+    const float px = __fdiv_rn(qx, qz);
+    const float py = __fdiv_rn(qy, qz);
+    const float gx = __fsub_rn(__fdiv_rn(px, (float)(W - 1) * 0.5f), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(py, (float)(H - 1) * 0.5f), 1.0f);
+    const float ix = safe_coord(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 0.5f));
+    const float iy = safe_coord(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 0.5f));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+    PackedTap t;
+    t.f.x = vx0 ? __fsub_rn(__fadd_rn(fx0, 1.0f), ix) : 0.f;
+    t.f.y = vx1 ? __fsub_rn(ix, fx0) : 0.f;
+    t.f.z = vy0 ? __fsub_rn(__fadd_rn(fy0, 1.0f), iy) : 0.f;
+    t.f.w = vy1 ? __fsub_rn(iy, fy0) : 0.f;
+    t.base = (uint32_t)(cy0 * W + cx0) | ((uint32_t)(cx1 != cx0) << 30) | ((uint32_t)(cy1 != cy0) << 31);
+    return t;
+}
+
+constexpr int kMaxSrcSmem = 8;  // source views whose per-pixel rotation terms are kept in shared memory
+
 enum { OUT_F32 = 0, OUT_CP8 = 1 };
 
 template <int OUT>
@@ -368,8 +405,14 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
                           const float *__restrict__ depth_values,  // [B,D]
                           void *__restrict__ out_,               // OUT_F32: [B,32,D,H,W] fp32; OUT_CP8: bf16 [B,4,D,H,W,8]
                           int V, int nsrc, int D, int H, int W, int dchunk) {
+    // Work mapping: a warp owns one 32-pixel row segment and walks `dchunk` consecutive depth planes (measured
+    // best among row-/plane-major variants, tools/warp_tune.py).  Everything that does not depend on the plane is
+    // hoisted out of the walk: R*(x,y,1) per (pixel, view) and the translation live in shared memory, so the
+    // per-(plane, view) coordinate pass issues 6 conflict-free LDS instead of 12 uniform global loads.
     __shared__ float4 s_f[kWarps][32];
     __shared__ uint32_t s_b[kWarps][32];
+    __shared__ float s_r[kWarps][kMaxSrcSmem][3][32];
+    __shared__ float s_t[kMaxSrcSmem][4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = lane >> 3, g = lane & 7;
@@ -378,7 +421,6 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
     const int d_begin = (blockIdx.z % nchunks) * dchunk;
     const int d_end = min(D, d_begin + dchunk);
     const int y = blockIdx.y * kWarps + warp;
-    if (y >= H) return;  // warp-uniform; only __syncwarp / full-mask shuffles below
     const int x0 = blockIdx.x * 32;
     const int xr = x0 + 8 * p;
     const size_t HW = (size_t)H * W;
@@ -386,6 +428,17 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
     const float invV = 1.0f / (float)V;
     const float xl = (float)(x0 + lane), yf = (float)y;
     const int W8 = W * 8;  // float4 units per texel row
+    const int nsm = min(nsrc, kMaxSrcSmem);
+    if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
+    for (int v = 0; v < nsm; ++v) {
+        float rx, ry, rz;
+        rot_pixel(rt + (size_t)(b * nsrc + v) * 12, xl, yf, rx, ry, rz);
+        s_r[warp][v][0][lane] = rx;
+        s_r[warp][v][1][lane] = ry;
+        s_r[warp][v][2][lane] = rz;
+    }
+    __syncthreads();
+    if (y >= H) return;  // warp-uniform; only __syncwarp / full-mask shuffles below
 
     for (int d = d_begin; d < d_end; ++d) {
         const float dep = __ldg(depth_values + (size_t)b * D + d);
@@ -412,7 +465,10 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
 
         for (int v = 0; v < nsrc; ++v) {
             const int n = b * nsrc + v;
-            const PackedTap t = sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+            const PackedTap t = (v < kMaxSrcSmem)
+                                    ? sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane],
+                                                      s_t[v][0], s_t[v][1], s_t[v][2], dep, H, W)
+                                    : sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
             __syncwarp();
             s_f[warp][lane] = t.f;
             s_b[warp][lane] = t.base;
@@ -672,6 +728,7 @@ static int pick_dchunk(int B, int D, int H, int W) {
     const long long tiles = (long long)cdiv(W, 32) * cdiv(H, kWarps) * B;
     int dchunk = 16;
     while (dchunk > 2 && tiles * cdiv(D, dchunk) < 148LL * 2 * 4) dchunk >>= 1;
+    if (const char *e = getenv("MVS_WARP_DCHUNK")) dchunk = std::max(1, atoi(e));  // tuning knob (tools/warp_tune.py)
     while ((long long)B * cdiv(D, dchunk) > 65535) dchunk <<= 1;  // gridDim.z limit
     return dchunk;
 }
