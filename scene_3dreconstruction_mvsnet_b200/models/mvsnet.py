@@ -42,6 +42,31 @@ class FeatureNet(nn.Module):
         x = self.conv4(self.conv3(self.conv2(x)))
         return self.feature(self.conv6(self.conv5(x)))
 
+    _ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6")
+
+    def folded_params(self):
+        """[(weight NHWC, bias, stride, padding)] x 7 with eval-mode BN folded in; cached like CostRegNet's."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if getattr(self, "_folded", None) is None or key != self._folded_key:
+            with torch.no_grad():
+                out = []
+                for n in self._ORDER:
+                    layer = getattr(self, n)
+                    w, b = fold_bn(layer.conv.weight, layer.bn, out_dim=0)
+                    out.append((w.contiguous(memory_format=torch.channels_last), b, layer.conv.stride,
+                                layer.conv.padding))
+            self._folded, self._folded_key = out, key
+        return self._folded
+
+    def infer(self, x):
+        """Inference path (still cuDNN -- FeatureNet is outside this build's scope): BN folded into the weights and
+        cuDNN's fused conv+bias+ReLU, i.e. one kernel per layer instead of conv, BN and ReLU passes
+        (measured at 5 x 1152x1600 on B200: 3.0 -> 1.6 ms with TF32, 9.6 -> 8.7 ms in strict fp32)."""
+        for w, b, stride, padding in self.folded_params():
+            x = torch.cudnn_convolution_relu(x, w, b, stride, padding, (1, 1), 1)
+        return F.conv2d(x, self.feature.weight, self.feature.bias, 1, 1)
+
 
 def _up(cin, cout):
     return nn.Sequential(
@@ -138,10 +163,15 @@ class MVSNet(nn.Module):
             # reduced-precision mode: let cuDNN use its TF32 tensor-core kernels for FeatureNet (PyTorch's own
             # default for convolutions, i.e. what the reference does on a GPU); fp32 mode keeps the ambient setting
             with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=True):
-                f = self.feature(x).contiguous()
+                f = self._features_eval(x)
         else:
-            f = self.feature(x).contiguous()
+            f = self._features_eval(x)
         return f.view(B, V, *f.shape[1:])
+
+    def _features_eval(self, x):
+        if torch.is_grad_enabled():
+            return self.feature(x).contiguous()
+        return self.feature.infer(x).contiguous()
 
     def forward(self, imgs, proj_matrices, depth_values):
         if imgs.shape[1] != proj_matrices.shape[1]:

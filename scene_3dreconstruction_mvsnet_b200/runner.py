@@ -11,10 +11,13 @@ import torch
 
 
 class DepthMapRunner:
-    def __init__(self, model, device="cuda:0", depth=2):
+    def __init__(self, model, device="cuda:0", depth=3):
         self.model = model.to(device).eval()
         self.device = torch.device(device)
+        # separate streams (and copy engines) for uploads and downloads: a download waits for its forward pass, and
+        # on a shared stream it would hold back the next view's upload until that forward pass is over
         self.copy_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
         self.depth = depth
         self._slots = None
         self.h2d_bytes_per_view = 0
@@ -86,11 +89,11 @@ class DepthMapRunner:
             out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
             d_out = torch.stack((out["depth"], out["photometric_confidence"]))
             s["done"].record(compute)
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(s["done"])
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(s["done"])
                 s["h_out"].copy_(d_out, non_blocking=True)
-                d_out.record_stream(self.copy_stream)
-                s["copied"].record(self.copy_stream)
+                d_out.record_stream(self.d2h_stream)
+                s["copied"].record(self.d2h_stream)
             pending.append((idx, s))
         for e in pending:
             drain(e)
