@@ -549,6 +549,164 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16-texel variant of the forward kernel (tensor-core precision mode only).  Source-view features are stored
+// channels-last in bf16 (64-byte texels), so one 16-byte load carries 8 channels: per (pixel, view) the taps cost
+// 4 x 16 B instead of 4 x 2 x 16 B in registers -- the L1 data pipe (the measured limiter) moves half the bytes,
+// and the coordinate exchange is amortised over 8 channels per lane instead of 4.  Lanes are (q = L/4, g = L%4):
+// the 8 q-groups take 8 CONSECUTIVE pixels per step, so a tap load of the warp touches ~8 adjacent texels
+// (4 x 128-byte lines), and thread (q, g) owns channel chunk g of pixels q, q+8, q+16, q+24 -- exactly one
+// 16-byte voxel chunk of the CP8 output per pixel, stored without any shuffle.  Interpolation and the Sum/Sum^2
+// accumulation stay in fp32; the reference view is read in fp32.
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc32_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, int HW, int nsrc,
+                                           int V) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.y;
+    const int b = n / nsrc, v = n % nsrc + (V - nsrc);
+    const float *src = in + ((size_t)b * V + v) * kC * HW;
+    __nv_bfloat16 *dst = out + (size_t)n * HW * kC;
+    const int p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int c = ty; c < 32; c += 8) tile[c][tx] = (p0 + tx < HW) ? src[(size_t)c * HW + p0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (p0 + r < HW) dst[(size_t)(p0 + r) * kC + tx] = __float2bfloat16_rn(tile[tx][r]);
+}
+
+// reference view only: [B,V,32,HW] view 0 -> [B][HW][32] fp32
+__global__ void ref_to_nhwc32_kernel(const float *__restrict__ in, float *__restrict__ out, int HW, int V) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.y;
+    const float *src = in + (size_t)b * V * kC * HW;
+    float *dst = out + (size_t)b * HW * kC;
+    const int p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int c = ty; c < 32; c += 8) tile[c][tx] = (p0 + tx < HW) ? src[(size_t)c * HW + p0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (p0 + r < HW) dst[(size_t)(p0 + r) * kC + tx] = tile[tx][r];
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 v, float *f) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8] float4 (fp32 channels-last reference view)
+                             const uint4 *__restrict__ src_cl,     // [B*nsrc][H*W][4] uint4 (bf16 channels-last)
+                             const float *__restrict__ rt, const float *__restrict__ depth_values,
+                             uint4 *__restrict__ out,              // bf16 CP8 [B,4,D,H,W,8]
+                             int V, int nsrc, int D, int H, int W, int dchunk) {
+    __shared__ float4 s_f[kWarps][32];
+    __shared__ uint32_t s_b[kWarps][32];
+    __shared__ float s_r[kWarps][kMaxSrcSmem][3][32];
+    __shared__ float s_t[kMaxSrcSmem][4];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane >> 2, g = lane & 3;
+    const int nchunks = (D + dchunk - 1) / dchunk;
+    const int b = blockIdx.z / nchunks;
+    const int d_begin = (blockIdx.z % nchunks) * dchunk;
+    const int d_end = min(D, d_begin + dchunk);
+    const int y = blockIdx.y * kWarps + warp;
+    const int x0 = blockIdx.x * 32;
+    const size_t HW = (size_t)H * W;
+    const float invV = 1.0f / (float)V;
+    const float xl = (float)(x0 + lane), yf = (float)y;
+    const int W4 = W * 4;  // uint4 units per bf16 texel row
+    const int nsm = min(nsrc, kMaxSrcSmem);
+    if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
+    for (int v = 0; v < nsm; ++v) {
+        float rx, ry, rz;
+        rot_pixel(rt + (size_t)(b * nsrc + v) * 12, xl, yf, rx, ry, rz);
+        s_r[warp][v][0][lane] = rx;
+        s_r[warp][v][1][lane] = ry;
+        s_r[warp][v][2][lane] = rz;
+    }
+    __syncthreads();
+    if (y >= H) return;  // warp-uniform
+
+    // reference-view values of this thread's 4 pixels x 8 channels do not depend on the plane
+    float R[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x0 + q + 8 * i;
+        if (x < W) {
+            const float4 *r = ref_cl + ((size_t)b * HW + (size_t)y * W + x) * 8 + 2 * g;
+            const float4 a = __ldg(r), c = __ldg(r + 1);
+            R[i][0] = a.x; R[i][1] = a.y; R[i][2] = a.z; R[i][3] = a.w;
+            R[i][4] = c.x; R[i][5] = c.y; R[i][6] = c.z; R[i][7] = c.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) R[i][j] = 0.f;
+        }
+    }
+
+    for (int d = d_begin; d < d_end; ++d) {
+        const float dep = __ldg(depth_values + (size_t)b * D + d);
+        float S[4][8], Q[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                S[i][j] = R[i][j];
+                Q[i][j] = R[i][j] * R[i][j];
+            }
+        for (int v = 0; v < nsrc; ++v) {
+            const int n = b * nsrc + v;
+            const PackedTap t = (v < kMaxSrcSmem)
+                                    ? sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane],
+                                                      s_t[v][0], s_t[v][1], s_t[v][2], dep, H, W)
+                                    : sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+            __syncwarp();
+            s_f[warp][lane] = t.f;
+            s_b[warp][lane] = t.base;
+            __syncwarp();
+            const uint4 *f = src_cl + (size_t)n * HW * 4 + g;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 fc = s_f[warp][q + 8 * i];
+                const uint32_t bb = s_b[warp][q + 8 * i];
+                const uint4 *p00 = f + (size_t)(bb & 0x3FFFFFFFu) * 4;
+                const uint4 *p01 = p00 + ((bb >> 30) & 1u) * 4;
+                const int dyo = (bb >> 31) ? W4 : 0;
+                const uint4 ta = __ldg(p00), tb = __ldg(p01), tc = __ldg(p00 + dyo), td = __ldg(p01 + dyo);
+                const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
+                float fa[8], fb[8], fcc[8], fd[8];
+                unpack_bf16x8(ta, fa); unpack_bf16x8(tb, fb); unpack_bf16x8(tc, fcc); unpack_bf16x8(td, fd);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float val = fmaf(fd[j], w11, fmaf(fcc[j], w10, fmaf(fb[j], w01, fa[j] * w00)));
+                    S[i][j] += val;
+                    Q[i][j] = fmaf(val, val, Q[i][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = x0 + q + 8 * i;
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float m = S[i][j] * invV;
+                r[j] = fmaf(Q[i][j], invV, -m * m);
+            }
+            if (x < W) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(r[0], r[1]), t1 = __floats2bfloat162_rn(r[2], r[3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(r[4], r[5]), t3 = __floats2bfloat162_rn(r[6], r[7]);
+                pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                __stcs(out + (((size_t)b * 4 + g) * D + d) * HW + (size_t)y * W + x, pk);
+            }
+        }
+    }
+}
+
 // Generic-C fallback of the standalone homo_warping (any channel count, NCHW gathers).  Used only
 // when C != 32; one thread per (x, y, d), looping over channels.
 __global__ void homo_warp_generic_kernel(const float *__restrict__ src, const float *__restrict__ rt,
@@ -739,8 +897,10 @@ using namespace mvs;
 
 extern "C" size_t mvs_warp_variance_workspace_bytes(int B, int V, int C, int H, int W) {
     if (B <= 0 || V < 1 || C <= 0 || H <= 0 || W <= 0) return 0;
+    // homographies | channels-last sources (fp32, or bf16 + an fp32 channels-last reference view in the bf16-texel path)
     return align256((size_t)B * (V > 1 ? V - 1 : 1) * 12 * sizeof(float)) +
-           align256((size_t)B * (V > 1 ? V - 1 : 1) * H * W * C * sizeof(float));
+           align256((size_t)B * (V > 1 ? V - 1 : 1) * H * W * C * sizeof(float)) +
+           align256((size_t)B * H * W * C * sizeof(float)) + 512;
 }
 
 extern "C" size_t mvs_warp_variance_bwd_workspace_bytes(int B, int V, int C, int H, int W) {
@@ -786,6 +946,25 @@ namespace mvs {
 int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                       int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
+    static const bool bf16_texels = !(getenv("MVS_BF16_TEXELS") && atoi(getenv("MVS_BF16_TEXELS")) == 0);
+    if (bf16_texels && nsrc > 0) {
+        // workspace (sized for fp32 texels): rt | bf16 sources (half of the fp32 area) | fp32 reference view NHWC
+        float *rt = (float *)workspace;
+        char *base = (char *)workspace + align256((size_t)B * nsrc * 12 * sizeof(float));
+        __nv_bfloat16 *src16 = (__nv_bfloat16 *)base;
+        float *ref_cl = (float *)(base + align256((size_t)B * nsrc * H * W * kC * 2));
+        const int HW = H * W;
+        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+        nchw_to_nhwc32_bf16_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
+        ref_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B), dim3(32, 8), 0, st>>>(fea, ref_cl, HW, V);
+        MVS_LAUNCH_CHECK(2);
+        const int dchunk = pick_dchunk(B, D, H, W);
+        dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
+        warp_variance_bf16tex_kernel<<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt, depth_values,
+                                                                (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
+        MVS_LAUNCH_CHECK(1);
+        return MVS_OK;
+    }
     float *rt = (float *)workspace;
     float *src_cl = (float *)((char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float)));
     const int HW = H * W;
