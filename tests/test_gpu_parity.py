@@ -295,3 +295,61 @@ def test_full_size_c1_properties(weights):
     assert float(a["depth"].min()) >= float(dv.min()) - 1e-2 and float(a["depth"].max()) <= float(dv.max()) + 1e-2
     c = a["photometric_confidence"]
     assert float(c.min()) >= 0 and float(c.max()) <= 1 + 1e-5
+
+
+def test_host_buffer_c_abi_entry(case_a, weights):
+    """mvs_depth_from_features_host: host pointers in, host pointers out, through the C ABI only (no torch tensors
+    on the device side) -- must agree with the tensor path and with the reference goldens."""
+    import ctypes
+    from scene_3dreconstruction_mvsnet_b200 import _lib
+    m = load_model(weights)
+    folded = [(w.cpu().contiguous(), s.cpu().contiguous()) for w, s in m.cost_regularization.folded_params()]
+    params = _lib.CostRegParams()
+    for i, (w, s) in enumerate(folded):
+        params.w[i] = w.data_ptr()
+        params.shift[i] = s.data_ptr()
+    fea = np.ascontiguousarray(case_a["features"])
+    proj = np.ascontiguousarray(case_a["proj"])
+    dv = np.ascontiguousarray(case_a["dv"])
+    B, V, C, h, w = fea.shape
+    D = dv.shape[1]
+    depth = np.empty((B, h, w), np.float32)
+    conf = np.empty((B, h, w), np.float32)
+    rc = _lib.load().mvs_depth_from_features_host(
+        fea.ctypes.data_as(ctypes.c_void_p), proj.ctypes.data_as(ctypes.c_void_p), dv.ctypes.data_as(ctypes.c_void_p),
+        ctypes.byref(params), depth.ctypes.data_as(ctypes.c_void_p), conf.ctypes.data_as(ctypes.c_void_p),
+        B, V, D, h, w, _lib.PRECISION_FP32, 0)
+    _lib.check(rc, "mvs_depth_from_features_host")
+    rng = float(dv.max() - dv.min())
+    assert maxabs(depth, case_a["depth"]) < DEPTH_TOL_FRAC * rng
+    safe = np.abs(case_a["index_f"] - np.round(case_a["index_f"])) > 2e-3
+    assert float((np.abs(conf - case_a["conf"]) / case_a["conf"])[safe].max()) < 5e-4
+
+
+def test_runner_host_api_matches_forward(case_b, weights):
+    from scene_3dreconstruction_mvsnet_b200.runner import DepthMapRunner
+    m = load_model(weights)
+    with torch.no_grad():
+        direct = m(cu(case_b["imgs"]), cu(case_b["proj"]), cu(case_b["dv"]))
+    runner = DepthMapRunner(m, device=DEV)
+    views = [(case_b["imgs"], case_b["proj"], case_b["dv"])] * 4 + [(case_b["imgs"][:1], case_b["proj"][:1], case_b["dv"][:1])]
+    res = runner.run_views(views)
+    assert len(res) == 5
+    for d, c in res[:4]:
+        assert maxabs(d, direct["depth"]) == 0.0 and maxabs(c, direct["photometric_confidence"]) == 0.0
+    assert res[4][0].shape == (1,) + tuple(direct["depth"].shape[1:])   # shape change mid-stream re-allocates
+    assert maxabs(res[4][0], direct["depth"][:1]) < 1e-4
+
+
+def test_c3_four_view_grayscale_full_size(weights):
+    """BASELINE config 3 shape: 4 views 512x640 grayscale, interval scale 1.33; both precision modes agree within
+    the stated bf16 tolerance."""
+    imgs, proj, dv = synth.make_named("c3_bin_4view_512x640")
+    imgs, proj, dv = imgs.to(DEV), proj.to(DEV), dv.to(DEV)
+    with torch.no_grad():
+        a = load_model(weights, "fp32")(imgs, proj, dv)
+        b = load_model(weights, "bf16")(imgs, proj, dv)
+    rng = float(dv.max() - dv.min())
+    assert a["depth"].shape == (1, 128, 160)
+    assert maxabs(a["depth"], b["depth"]) < 2e-2 * rng
+    assert float((a["depth"] - b["depth"]).abs().mean()) < 2e-3 * rng
