@@ -676,13 +676,24 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
                 const int dyo = (bb >> 31) ? W4 : 0;
                 const uint4 ta = __ldg(p00), tb = __ldg(p01), tc = __ldg(p00 + dyo), td = __ldg(p01 + dyo);
                 const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
-                float fa[8], fb[8], fcc[8], fd[8];
-                unpack_bf16x8(ta, fa); unpack_bf16x8(tb, fb); unpack_bf16x8(tc, fcc); unpack_bf16x8(td, fd);
+                // packed fp32x2 arithmetic (sm_100 FFMA2/FADD2): each 32-bit word of a texel holds two bf16 channels, which
+                // unpack into an (even, odd) fp32 pair with one shift and one mask; two FMAs per issue slot, IEEE-identical
+                const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01);
+                const float2 w10p = make_float2(w10, w10), w11p = make_float2(w11, w11);
+                const uint32_t wa[4] = {ta.x, ta.y, ta.z, ta.w}, wb[4] = {tb.x, tb.y, tb.z, tb.w};
+                const uint32_t wc[4] = {tc.x, tc.y, tc.z, tc.w}, wd[4] = {td.x, td.y, td.z, td.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float val = fmaf(fd[j], w11, fmaf(fcc[j], w10, fmaf(fb[j], w01, fa[j] * w00)));
-                    S[i][j] += val;
-                    Q[i][j] = fmaf(val, val, Q[i][j]);
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a2 = make_float2(__uint_as_float(wa[j] << 16), __uint_as_float(wa[j] & 0xffff0000u));
+                    const float2 b2 = make_float2(__uint_as_float(wb[j] << 16), __uint_as_float(wb[j] & 0xffff0000u));
+                    const float2 c2 = make_float2(__uint_as_float(wc[j] << 16), __uint_as_float(wc[j] & 0xffff0000u));
+                    const float2 d2 = make_float2(__uint_as_float(wd[j] << 16), __uint_as_float(wd[j] & 0xffff0000u));
+                    const float2 zero2 = make_float2(0.f, 0.f), one2 = make_float2(1.f, 1.f);
+                    const float2 val = __ffma2_rn(d2, w11p, __ffma2_rn(c2, w10p, __ffma2_rn(b2, w01p, __ffma2_rn(a2, w00p, zero2))));
+                    const float2 s2 = __ffma2_rn(val, one2, make_float2(S[i][2 * j], S[i][2 * j + 1]));
+                    const float2 q2 = __ffma2_rn(val, val, make_float2(Q[i][2 * j], Q[i][2 * j + 1]));
+                    S[i][2 * j] = s2.x; S[i][2 * j + 1] = s2.y;
+                    Q[i][2 * j] = q2.x; Q[i][2 * j + 1] = q2.y;
                 }
             }
         }
