@@ -21,6 +21,8 @@
 //     4*B*32*D*H*W bytes written + the feature maps read once.
 #include <algorithm>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -559,19 +561,23 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
 // 16-byte voxel chunk of the CP8 output per pixel, stored without any shuffle.  Interpolation and the Sum/Sum^2
 // accumulation stay in fp32; the reference view is read in fp32.
 // ------------------------------------------------------------------------------------------------
-__global__ void nchw_to_nhwc32_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, int HW, int nsrc,
-                                           int V) {
+template <bool FP16>
+__global__ void nchw_to_nhwc32_lp_kernel(const float *__restrict__ in, uint16_t *__restrict__ out, int HW, int nsrc, int V) {
     __shared__ float tile[32][33];
     const int n = blockIdx.y;
     const int b = n / nsrc, v = n % nsrc + (V - nsrc);
     const float *src = in + ((size_t)b * V + v) * kC * HW;
-    __nv_bfloat16 *dst = out + (size_t)n * HW * kC;
+    uint16_t *dst = out + (size_t)n * HW * kC;
     const int p0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
     for (int c = ty; c < 32; c += 8) tile[c][tx] = (p0 + tx < HW) ? src[(size_t)c * HW + p0 + tx] : 0.f;
     __syncthreads();
     for (int r = ty; r < 32; r += 8)
-        if (p0 + r < HW) dst[(size_t)(p0 + r) * kC + tx] = __float2bfloat16_rn(tile[tx][r]);
+        if (p0 + r < HW) {
+            const float v = tile[tx][r];
+            if (FP16) dst[(size_t)(p0 + r) * kC + tx] = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+            else dst[(size_t)(p0 + r) * kC + tx] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+        }
 }
 
 // reference view only: [B,V,32,HW] view 0 -> [B][HW][32] fp32
@@ -595,6 +601,7 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 v, float *f) {
     f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 
+template <bool FP16>
 __global__ void __launch_bounds__(kThreads, 2)
 warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8] float4 (fp32 channels-last reference view)
                              const uint4 *__restrict__ src_cl,     // [B*nsrc][H*W][4] uint4 (bf16 channels-last)
@@ -631,30 +638,30 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
     if (y >= H) return;  // warp-uniform
 
     // reference-view values of this thread's 4 pixels x 8 channels do not depend on the plane
-    float R[4][8];
+    float2 R[4][4];  // channel pairs: the accumulators below are packed fp32x2 registers
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int x = x0 + q + 8 * i;
         if (x < W) {
             const float4 *r = ref_cl + ((size_t)b * HW + (size_t)y * W + x) * 8 + 2 * g;
             const float4 a = __ldg(r), c = __ldg(r + 1);
-            R[i][0] = a.x; R[i][1] = a.y; R[i][2] = a.z; R[i][3] = a.w;
-            R[i][4] = c.x; R[i][5] = c.y; R[i][6] = c.z; R[i][7] = c.w;
+            R[i][0] = make_float2(a.x, a.y); R[i][1] = make_float2(a.z, a.w);
+            R[i][2] = make_float2(c.x, c.y); R[i][3] = make_float2(c.z, c.w);
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) R[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) R[i][j] = make_float2(0.f, 0.f);
         }
     }
 
     for (int d = d_begin; d < d_end; ++d) {
         const float dep = __ldg(depth_values + (size_t)b * D + d);
-        float S[4][8], Q[4][8];
+        float2 S[4][4], Q[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 S[i][j] = R[i][j];
-                Q[i][j] = R[i][j] * R[i][j];
+                Q[i][j] = make_float2(R[i][j].x * R[i][j].x, R[i][j].y * R[i][j].y);
             }
         for (int v = 0; v < nsrc; ++v) {
             const int n = b * nsrc + v;
@@ -676,24 +683,39 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
                 const int dyo = (bb >> 31) ? W4 : 0;
                 const uint4 ta = __ldg(p00), tb = __ldg(p01), tc = __ldg(p00 + dyo), td = __ldg(p01 + dyo);
                 const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
-                // packed fp32x2 arithmetic (sm_100 FFMA2/FADD2): each 32-bit word of a texel holds two bf16 channels, which
-                // unpack into an (even, odd) fp32 pair with one shift and one mask; two FMAs per issue slot, IEEE-identical
-                const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01);
-                const float2 w10p = make_float2(w10, w10), w11p = make_float2(w11, w11);
                 const uint32_t wa[4] = {ta.x, ta.y, ta.z, ta.w}, wb[4] = {tb.x, tb.y, tb.z, tb.w};
                 const uint32_t wc[4] = {tc.x, tc.y, tc.z, tc.w}, wd[4] = {td.x, td.y, td.z, td.w};
+                const float2 one2 = make_float2(1.f, 1.f);
+                if (FP16) {
+                    // fp16 texels: the 4-tap interpolation runs as packed half2 FMAs (11-bit mantissa: storage + 4 roundings
+                    // ~1e-3 relative, tighter than bf16 storage alone); Sum / Sum^2 are accumulated in fp32 (packed FFMA2)
+                    const __half2 h00 = __float2half2_rn(w00), h01 = __float2half2_rn(w01);
+                    const __half2 h10 = __float2half2_rn(w10), h11 = __float2half2_rn(w11);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 a2 = make_float2(__uint_as_float(wa[j] << 16), __uint_as_float(wa[j] & 0xffff0000u));
-                    const float2 b2 = make_float2(__uint_as_float(wb[j] << 16), __uint_as_float(wb[j] & 0xffff0000u));
-                    const float2 c2 = make_float2(__uint_as_float(wc[j] << 16), __uint_as_float(wc[j] & 0xffff0000u));
-                    const float2 d2 = make_float2(__uint_as_float(wd[j] << 16), __uint_as_float(wd[j] & 0xffff0000u));
-                    const float2 zero2 = make_float2(0.f, 0.f), one2 = make_float2(1.f, 1.f);
-                    const float2 val = __ffma2_rn(d2, w11p, __ffma2_rn(c2, w10p, __ffma2_rn(b2, w01p, __ffma2_rn(a2, w00p, zero2))));
-                    const float2 s2 = __ffma2_rn(val, one2, make_float2(S[i][2 * j], S[i][2 * j + 1]));
-                    const float2 q2 = __ffma2_rn(val, val, make_float2(Q[i][2 * j], Q[i][2 * j + 1]));
-                    S[i][2 * j] = s2.x; S[i][2 * j + 1] = s2.y;
-                    Q[i][2 * j] = q2.x; Q[i][2 * j + 1] = q2.y;
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2 a2 = *reinterpret_cast<const __half2 *>(&wa[j]), b2 = *reinterpret_cast<const __half2 *>(&wb[j]);
+                        const __half2 c2 = *reinterpret_cast<const __half2 *>(&wc[j]), d2 = *reinterpret_cast<const __half2 *>(&wd[j]);
+                        const __half2 vh = __hfma2(d2, h11, __hfma2(c2, h10, __hfma2(b2, h01, __hmul2(a2, h00))));
+                        const float2 val = __half22float2(vh);
+                        S[i][j] = __ffma2_rn(val, one2, S[i][j]);
+                        Q[i][j] = __ffma2_rn(val, val, Q[i][j]);
+                    }
+                } else {
+                    // bf16 texels: each 32-bit word unpacks into an (even, odd) fp32 pair with one shift and one mask;
+                    // packed fp32x2 arithmetic (sm_100 FFMA2): two IEEE FMAs per issue slot
+                    const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01);
+                    const float2 w10p = make_float2(w10, w10), w11p = make_float2(w11, w11);
+                    const float2 zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a2 = make_float2(__uint_as_float(wa[j] << 16), __uint_as_float(wa[j] & 0xffff0000u));
+                        const float2 b2 = make_float2(__uint_as_float(wb[j] << 16), __uint_as_float(wb[j] & 0xffff0000u));
+                        const float2 c2 = make_float2(__uint_as_float(wc[j] << 16), __uint_as_float(wc[j] & 0xffff0000u));
+                        const float2 d2 = make_float2(__uint_as_float(wd[j] << 16), __uint_as_float(wd[j] & 0xffff0000u));
+                        const float2 val = __ffma2_rn(d2, w11p, __ffma2_rn(c2, w10p, __ffma2_rn(b2, w01p, __ffma2_rn(a2, w00p, zero2))));
+                        S[i][j] = __ffma2_rn(val, one2, S[i][j]);
+                        Q[i][j] = __ffma2_rn(val, val, Q[i][j]);
+                    }
                 }
             }
         }
@@ -702,9 +724,10 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
             const int x = x0 + q + 8 * i;
             float r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float m = S[i][j] * invV;
-                r[j] = fmaf(Q[i][j], invV, -m * m);
+            for (int j = 0; j < 4; ++j) {
+                const float mx = S[i][j].x * invV, my = S[i][j].y * invV;
+                r[2 * j] = fmaf(Q[i][j].x, invV, -mx * mx);
+                r[2 * j + 1] = fmaf(Q[i][j].y, invV, -my * my);
             }
             if (x < W) {
                 uint4 pk;
@@ -957,22 +980,32 @@ namespace mvs {
 int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                       int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
-    static const bool bf16_texels = !(getenv("MVS_BF16_TEXELS") && atoi(getenv("MVS_BF16_TEXELS")) == 0);
-    if (bf16_texels && nsrc > 0) {
+    // texel format of the source views in the tensor-core mode: fp16 (default), bf16, or fp32 (MVS_TEXEL_FMT, tuning knob)
+    static const int texel_fmt = [] {
+        const char *e = getenv("MVS_TEXEL_FMT");
+        if (!e) return 16;
+        return !strcmp(e, "fp32") ? 32 : (!strcmp(e, "bf16") ? 17 : 16);
+    }();
+    if (texel_fmt != 32 && nsrc > 0) {
         // workspace (sized for fp32 texels): rt | bf16 sources (half of the fp32 area) | fp32 reference view NHWC
         float *rt = (float *)workspace;
         char *base = (char *)workspace + align256((size_t)B * nsrc * 12 * sizeof(float));
-        __nv_bfloat16 *src16 = (__nv_bfloat16 *)base;
+        uint16_t *src16 = (uint16_t *)base;
         float *ref_cl = (float *)(base + align256((size_t)B * nsrc * H * W * kC * 2));
         const int HW = H * W;
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-        nchw_to_nhwc32_bf16_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
+        if (texel_fmt == 16) nchw_to_nhwc32_lp_kernel<true><<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
+        else nchw_to_nhwc32_lp_kernel<false><<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
         ref_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B), dim3(32, 8), 0, st>>>(fea, ref_cl, HW, V);
         MVS_LAUNCH_CHECK(2);
         const int dchunk = pick_dchunk(B, D, H, W);
         dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-        warp_variance_bf16tex_kernel<<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt, depth_values,
-                                                                (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
+        if (texel_fmt == 16)
+            warp_variance_bf16tex_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
+                                                                          depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
+        else
+            warp_variance_bf16tex_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
+                                                                           depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     }

@@ -74,18 +74,22 @@ def test_tc_conv_transpose3d(cin, cout, dims, with_skip):
 
 @pytest.mark.parametrize("B,V,h,w,D", [(1, 5, 24, 40, 16), (2, 3, 9, 33, 5), (1, 4, 16, 104, 8), (1, 2, 8, 31, 3)])
 def test_warp_variance_cp8(B, V, h, w, D):
-    """bf16-mode fused kernel: source-view features are sampled from bf16 texels (reference view fp32), arithmetic
-    in fp32, result stored as bf16 CP8.  Oracle: the C restatement run on features whose source views were rounded
-    to bf16; remaining difference = fp32 ordering + the bf16 rounding of the stored variance."""
+    """Tensor-core-mode fused kernel: source views are sampled from fp16 texels with packed-half interpolation
+    (reference view and the Sum / Sum^2 accumulation in fp32), result stored as bf16 CP8.  Oracle: the C restatement
+    on features whose source views were rounded to fp16.  Tolerance (stated for this mode): interpolation in fp16 adds
+    ~1e-3 relative per warped value on top of the bf16 rounding of the stored variance: 2^-7 |ref| + 8e-3 on N(0,1)
+    features."""
     from scene_3dreconstruction_mvsnet_b200 import synth
     fea = synth.make_features(B, V, 32, h, w, seed=V)
     _, proj, dv = synth.make_inputs(B=B, V=V, H=4 * h, W=4 * w, D=D, focal=0.9 * w, interval_scale=8.0, yaw=0.04, seed=D)
     fea_q = fea.clone()
-    fea_q[:, 1:] = bf16_round(fea[:, 1:])
+    fea_q[:, 1:] = fea[:, 1:].half().float()
     ref = orc.warp_variance(fea_q.numpy(), proj.numpy(), dv.numpy()).astype(np.float64)
     cp8 = ops.warp_variance_cp8(fea.to(DEV), proj.to(DEV), dv.to(DEV))          # [B,4,D,h,w,8] bf16
-    back = cp8.permute(0, 1, 5, 2, 3, 4).reshape(B, 32, D, h, w).float()
-    check(back, ref, "warp_variance_cp8 %s" % ((B, V, h, w, D),))
+    back = cp8.permute(0, 1, 5, 2, 3, 4).reshape(B, 32, D, h, w).float().cpu().numpy().astype(np.float64)
+    err = np.abs(back - ref)
+    assert (err <= np.abs(ref) * 2.0 ** -7 + 8e-3).all(), "max err %.4g" % err.max()
+    assert err.mean() < 1.5e-3
 
 
 @pytest.mark.parametrize("case", ["case_a", "case_b"])
