@@ -395,6 +395,32 @@ __device__ __forceinline__ PackedTap sample_packed_r(float rx, float ry, float r
     return t;
 }
 
+// Reduced-precision-mode variant of the position arithmetic: the same map with the two normalisations folded into
+// one FMA (ix = px * W/(W-1) - 0.5, the reference's align_corners mismatch in closed form) and approximate
+// reciprocal division.  Differs from the exact chain by ~1e-7 relative (1e-4 texel), far below the fp16 texel
+// quantisation of the mode that uses it; the coordinate pass drops from ~150 to ~55 instructions.
+__device__ __forceinline__ PackedTap sample_packed_fast(float rx, float ry, float rz, float tx, float ty, float tz, float d,
+                                                        float sx, float sy, int H, int W) {
+    const float qx = fmaf(rx, d, tx), qy = fmaf(ry, d, ty), qz = fmaf(rz, d, tz);
+    const float iz = __frcp_rn(qz);
+    const float ix = safe_coord(fmaf(qx * iz, sx, -0.5f));
+    const float iy = safe_coord(fmaf(qy * iz, sy, -0.5f));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+    const float bx = ix - fx0, by = iy - fy0;
+    PackedTap t;
+    t.f.x = vx0 ? 1.0f - bx : 0.f;
+    t.f.y = vx1 ? bx : 0.f;
+    t.f.z = vy0 ? 1.0f - by : 0.f;
+    t.f.w = vy1 ? by : 0.f;
+    t.base = (uint32_t)(cy0 * W + cx0) | ((uint32_t)(cx1 != cx0) << 30) | ((uint32_t)(cy1 != cy0) << 31);
+    return t;
+}
+
 constexpr int kMaxSrcSmem = 8;  // source views whose per-pixel rotation terms are kept in shared memory
 
 enum { OUT_F32 = 0, OUT_CP8 = 1 };
@@ -624,7 +650,8 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
     const size_t HW = (size_t)H * W;
     const float invV = 1.0f / (float)V;
     const float xl = (float)(x0 + lane), yf = (float)y;
-    const int W4 = W * 4;  // uint4 units per bf16 texel row
+    const int W4 = W * 4;  // uint4 units per 16-bit texel row
+    const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
     const int nsm = min(nsrc, kMaxSrcSmem);
     if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
     for (int v = 0; v < nsm; ++v) {
@@ -665,12 +692,29 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
             }
         for (int v = 0; v < nsrc; ++v) {
             const int n = b * nsrc + v;
-            const PackedTap t = (v < kMaxSrcSmem)
-                                    ? sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane],
-                                                      s_t[v][0], s_t[v][1], s_t[v][2], dep, H, W)
-                                    : sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+            PackedTap t;
+            if (v < kMaxSrcSmem) {
+                t = sample_packed_fast(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0],
+                                       s_t[v][1], s_t[v][2], dep, sx, sy, H, W);
+            } else {
+                float rx, ry, rz;
+                const float *rtv = rt + (size_t)n * 12;
+                rot_pixel(rtv, xl, yf, rx, ry, rz);
+                t = sample_packed_fast(rx, ry, rz, rtv[9], rtv[10], rtv[11], dep, sx, sy, H, W);
+            }
             __syncwarp();
-            s_f[warp][lane] = t.f;
+            if (FP16) {  // publish the four tap weights ready-made as duplicated half2 (formed once per pixel, not per lane)
+                const __half2 h00 = __float2half2_rn(t.f.x * t.f.z), h01 = __float2half2_rn(t.f.y * t.f.z);
+                const __half2 h10 = __float2half2_rn(t.f.x * t.f.w), h11 = __float2half2_rn(t.f.y * t.f.w);
+                float4 pk;
+                pk.x = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h00));
+                pk.y = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h01));
+                pk.z = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h10));
+                pk.w = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h11));
+                s_f[warp][lane] = pk;
+            } else {
+                s_f[warp][lane] = t.f;
+            }
             s_b[warp][lane] = t.base;
             __syncwarp();
             const uint4 *f = src_cl + (size_t)n * HW * 4 + g;
@@ -682,15 +726,16 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
                 const uint4 *p01 = p00 + ((bb >> 30) & 1u) * 4;
                 const int dyo = (bb >> 31) ? W4 : 0;
                 const uint4 ta = __ldg(p00), tb = __ldg(p01), tc = __ldg(p00 + dyo), td = __ldg(p01 + dyo);
-                const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
                 const uint32_t wa[4] = {ta.x, ta.y, ta.z, ta.w}, wb[4] = {tb.x, tb.y, tb.z, tb.w};
                 const uint32_t wc[4] = {tc.x, tc.y, tc.z, tc.w}, wd[4] = {td.x, td.y, td.z, td.w};
                 const float2 one2 = make_float2(1.f, 1.f);
                 if (FP16) {
                     // fp16 texels: the 4-tap interpolation runs as packed half2 FMAs (11-bit mantissa: storage + 4 roundings
                     // ~1e-3 relative, tighter than bf16 storage alone); Sum / Sum^2 are accumulated in fp32 (packed FFMA2)
-                    const __half2 h00 = __float2half2_rn(w00), h01 = __float2half2_rn(w01);
-                    const __half2 h10 = __float2half2_rn(w10), h11 = __float2half2_rn(w11);
+                    const uint32_t u00 = __float_as_uint(fc.x), u01 = __float_as_uint(fc.y);
+                    const uint32_t u10 = __float_as_uint(fc.z), u11 = __float_as_uint(fc.w);
+                    const __half2 h00 = *reinterpret_cast<const __half2 *>(&u00), h01 = *reinterpret_cast<const __half2 *>(&u01);
+                    const __half2 h10 = *reinterpret_cast<const __half2 *>(&u10), h11 = *reinterpret_cast<const __half2 *>(&u11);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const __half2 a2 = *reinterpret_cast<const __half2 *>(&wa[j]), b2 = *reinterpret_cast<const __half2 *>(&wb[j]);
@@ -703,6 +748,7 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
                 } else {
                     // bf16 texels: each 32-bit word unpacks into an (even, odd) fp32 pair with one shift and one mask;
                     // packed fp32x2 arithmetic (sm_100 FFMA2): two IEEE FMAs per issue slot
+                    const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
                     const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01);
                     const float2 w10p = make_float2(w10, w10), w11p = make_float2(w11, w11);
                     const float2 zero2 = make_float2(0.f, 0.f);
