@@ -248,12 +248,12 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16 operands/f32 accumulate (CostRegNet, tcgen05) + f32",
+            "dtype": "f32" if args.precision == "fp32" else "bf16 operands/f32 accumulate (CostRegNet, tcgen05); fp16 features; f32 sums",
             "data": "synthetic",
             "config": {"workload": args.workload, "views": V, "image": [H, W], "depth_planes": D, "batch": 1,
                        "feature_map": [h, w], "weights": "random-init (seed 1), eval mode",
                        "precision": args.precision,
-                       "featurenet": "cuDNN NHWC, " + ("TF32 allowed" if args.precision == "bf16" else "fp32 (TF32 off)"),
+                       "featurenet": "cuDNN NHWC fused conv+bias+relu, " + ("fp16" if args.precision == "bf16" else "fp32 (TF32 off)"),
                        "l2": "per-step working set (1.4-2.8 GB cost volume) >> 126 MB L2; no flush needed",
                        "sharding": "one reference view stream per rank, no collective"},
             "clocks": clocks,

@@ -123,6 +123,10 @@ int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *params, float
 size_t mvs_volume_cp8_bytes(int B, int D, int H, int W);
 int mvs_warp_variance_fwd_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8,
                               void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
+/* Same, but the features arrive as ONE fp16 channels-last tensor [B][V][H][W][32] (what a half-precision FeatureNet
+ * emits): no layout pre-pass; view 0 is the reference view. */
+int mvs_warp_variance_fwd_cp8_f16(const void *fea16_nhwc, const float *proj, const float *depth_values, void *vol_cp8,
+                                  void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
 int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *params, float *logits, void *workspace, int B,
                         int D, int H, int W, void *stream);
 

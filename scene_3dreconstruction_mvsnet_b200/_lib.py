@@ -48,6 +48,7 @@ SIGNATURES = {
                         [ctypes.c_void_p]),
     "mvs_volume_cp8_bytes": (ctypes.c_size_t, [_i] * 4),
     "mvs_warp_variance_fwd_cp8": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
+    "mvs_warp_variance_fwd_cp8_f16": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
                             [ctypes.c_void_p]),
     "mvs_softmax_depth_conf": (_i, [_c_float_p] * 5 + [_i] * 4 + [ctypes.c_void_p]),

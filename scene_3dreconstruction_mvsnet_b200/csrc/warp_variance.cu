@@ -627,10 +627,12 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 v, float *f) {
     f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 
-template <bool FP16>
+// ALLV16: `src_cl` is one fp16 channels-last tensor holding ALL V views, [B][V][H*W][32] (what the fp16 FeatureNet
+// emits); view 0 doubles as the reference view and `ref_cl` is unused.
+template <bool FP16, bool ALLV16>
 __global__ void __launch_bounds__(kThreads, 2)
 warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8] float4 (fp32 channels-last reference view)
-                             const uint4 *__restrict__ src_cl,     // [B*nsrc][H*W][4] uint4 (bf16 channels-last)
+                             const uint4 *__restrict__ src_cl,     // [B*nsrc][H*W][4] uint4 (16-bit channels-last)
                              const float *__restrict__ rt, const float *__restrict__ depth_values,
                              uint4 *__restrict__ out,              // bf16 CP8 [B,4,D,H,W,8]
                              int V, int nsrc, int D, int H, int W, int dchunk) {
@@ -669,7 +671,12 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int x = x0 + q + 8 * i;
-        if (x < W) {
+        if (x < W && ALLV16) {
+            const uint4 rv = __ldg(src_cl + ((size_t)b * V * HW + (size_t)y * W + x) * 4 + g);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) R[i][j] = __half22float2(*reinterpret_cast<const __half2 *>(&rw[j]));
+        } else if (x < W) {
             const float4 *r = ref_cl + ((size_t)b * HW + (size_t)y * W + x) * 8 + 2 * g;
             const float4 a = __ldg(r), c = __ldg(r + 1);
             R[i][0] = make_float2(a.x, a.y); R[i][1] = make_float2(a.z, a.w);
@@ -717,7 +724,7 @@ warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8]
             }
             s_b[warp][lane] = t.base;
             __syncwarp();
-            const uint4 *f = src_cl + (size_t)n * HW * 4 + g;
+            const uint4 *f = src_cl + (size_t)(ALLV16 ? b * V + v + 1 : n) * HW * 4 + g;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 fc = s_f[warp][q + 8 * i];
@@ -1047,11 +1054,11 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
         const int dchunk = pick_dchunk(B, D, H, W);
         dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
         if (texel_fmt == 16)
-            warp_variance_bf16tex_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
-                                                                          depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
+            warp_variance_bf16tex_kernel<true, false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
+                                                                                 depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
         else
-            warp_variance_bf16tex_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
-                                                                           depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
+            warp_variance_bf16tex_kernel<false, false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
+                                                                                  depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     }
@@ -1067,6 +1074,21 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
     warp_variance_fwd2_kernel<OUT_CP8><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, vol_cp8,
                                                                   V, nsrc, D, H, W, dchunk);
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+
+// fp16 channels-last features of all V views in ([B][V][H*W][32]), bf16 CP8 volume out: no layout pre-pass at all.
+int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
+                          int B, int V, int D, int H, int W, cudaStream_t st) {
+    const int nsrc = V - 1;
+    float *rt = (float *)workspace;
+    if (nsrc > 0)
+        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+    const int dchunk = pick_dchunk(B, D, H, W);
+    dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
+    warp_variance_bf16tex_kernel<true, true><<<grid, kThreads, 0, st>>>(nullptr, (const uint4 *)fea16, rt, depth_values,
+                                                                        (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }

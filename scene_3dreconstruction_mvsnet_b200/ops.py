@@ -271,12 +271,19 @@ def warp_variance_cp8(fea, proj, depth_values):
 
 def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
     """bf16 precision mode: fused warp+variance writing the bf16 CP8 volume, then the tcgen05 CostRegNet.
-    fea [B,V,32,h,w] -> logits [B,D,h,w] (fp32).  `marks`, if a callable, is invoked between the two kernels
-    families (stage timing)."""
-    fea = _prep(fea, "features", 5)
+    fea: fp32 [B,V,32,h,w], or fp16 channels-last [B,V,h,w,32] (then no layout pre-pass runs) -> logits
+    [B,D,h,w] (fp32).  `marks`, if a callable, is invoked between the two kernel families (stage timing)."""
+    half_nhwc = isinstance(fea, torch.Tensor) and fea.dtype == torch.float16
+    if half_nhwc:
+        if not fea.is_cuda or fea.dim() != 5 or fea.shape[-1] != 32 or not fea.is_contiguous():
+            raise RuntimeError("fp16 features must be a contiguous CUDA tensor [B,V,h,w,32], got %s" % (tuple(fea.shape),))
+        fea = fea.detach()
+        B, V, H, W, C = fea.shape
+    else:
+        fea = _prep(fea, "features", 5)
+        B, V, C, H, W = fea.shape
     proj = _prep(proj, "proj_matrices", 4)
     depth_values = _prep(depth_values, "depth_values", 2)
-    B, V, C, H, W = fea.shape
     D = depth_values.shape[1]
     if proj.shape != (B, V, 4, 4):
         raise RuntimeError("Different number of images and projection matrices: features %s proj %s"
@@ -291,8 +298,8 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
     ws2 = _ws(nbytes, fea.device, "costreg")
     logits = torch.empty((B, D, H, W), dtype=torch.float32, device=fea.device)
     with torch.cuda.device(fea.device):
-        rc = lib.mvs_warp_variance_fwd_cp8(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H,
-                                           W, _stream(fea))
+        fn = lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8
+        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
         _lib.check(rc, "mvs_warp_variance_fwd_cp8")
         if marks is not None:
             marks("warp_variance")

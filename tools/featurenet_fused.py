@@ -29,7 +29,24 @@ def fused(x):
     for w, b, s, p in layers:
         x = torch.cudnn_convolution_relu(x, w, b, s, p, (1, 1), 1)
     return torch.nn.functional.conv2d(x, net.feature.weight, net.feature.bias, 1, 1)
+def fused_lp(x, dt):
+    x = x.to(dt)
+    for w, b, s_, p in layers:
+        x = torch.cudnn_convolution_relu(x, w.to(dt), b.to(dt), s_, p, (1, 1), 1)
+    return torch.nn.functional.conv2d(x, net.feature.weight.to(dt), net.feature.bias.to(dt), 1, 1)
 with torch.no_grad():
+    netc = net.to(memory_format=torch.channels_last)
+    ref = netc(x)
+    for dt in (torch.float16, torch.bfloat16):
+        ws = [(w.to(dt), b.to(dt), s_, p) for w, b, s_, p in layers]
+        fw, fb = net.feature.weight.to(dt).contiguous(memory_format=torch.channels_last), net.feature.bias.to(dt)
+        def run():
+            y = x.to(dt)
+            for w, b, s_, p in ws:
+                y = torch.cudnn_convolution_relu(y, w, b, s_, p, (1, 1), 1)
+            return torch.nn.functional.conv2d(y, fw, fb, 1, 1)
+        y = run()
+        print(dt, "%.3f ms" % timeit(run), "maxdiff %.3g (absmax %.3g)" % ((y.float() - ref).abs().max().item(), ref.abs().max().item()))
     for tf32 in (False, True):
         torch.backends.cudnn.allow_tf32 = tf32
         netc = net.to(memory_format=torch.channels_last)
