@@ -239,7 +239,7 @@ def run_ours(args):
         wv_ms = stage_ms.get("warp_variance")
         # volume written once + every feature map read once.  In the bf16 mode the fused
         # kernel writes the volume as bf16 (the tensor-core CostRegNet's input), i.e. 2 bytes per element.
-        vol_elem = 2 if args.precision == "bf16" else 4
+        vol_elem = 4 if args.precision == "fp32" else 2
         alg_bytes = vol_elem * 32 * D * h * w + 4 * V * 32 * h * w
         achieved = alg_bytes / (wv_ms * 1e-3) / 1e9 if wv_ms else None
         cr_ms = stage_ms.get("cost_regularization")
@@ -248,12 +248,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16 operands/f32 accumulate (CostRegNet, tcgen05); fp16 features; f32 sums",
+            "dtype": {"fp32": "f32",
+                      "bf16": "bf16 operands / f32 accumulate in CostRegNet (tcgen05); f32 elsewhere (FeatureNet: cuDNN, TF32 allowed)",
+                      "fast": "bf16 CostRegNet (tcgen05) + fp16 features / fp16 tap interpolation, f32 sums"}[args.precision],
             "data": "synthetic",
             "config": {"workload": args.workload, "views": V, "image": [H, W], "depth_planes": D, "batch": 1,
                        "feature_map": [h, w], "weights": "random-init (seed 1), eval mode",
                        "precision": args.precision,
-                       "featurenet": "cuDNN NHWC fused conv+bias+relu, " + ("fp16" if args.precision == "bf16" else "fp32 (TF32 off)"),
+                       "featurenet": "cuDNN NHWC fused conv+bias+relu, " + {"fp32": "fp32 (TF32 off)", "bf16": "TF32 allowed (PyTorch default)",
+                                                                           "fast": "fp16"}[args.precision],
                        "l2": "per-step working set (1.4-2.8 GB cost volume) >> 126 MB L2; no flush needed",
                        "sharding": "one reference view stream per rank, no collective"},
             "clocks": clocks,
@@ -272,13 +275,18 @@ def run_ours(args):
                                  "peak_bf16_tensor": tf_peak},
         }
         if world == 1 and not args.no_other_mode:
-            other = "fp32" if args.precision == "bf16" else "bf16"
             del model, runner
-            torch.cuda.empty_cache()
-            o = measure(other, max(3, args.steps // 4), 3)
-            line["other_precision_mode"] = {"precision": other, "value": o["value"], "unit": UNIT,
-                                            "ms_per_step": o["max_ms"] / max(3, args.steps // 4),
-                                            "stage_ms": o["stage_ms"], "gpu_launches": o["launches"]}
+            line["other_precision_modes"] = []
+            for other in ("fp32", "bf16", "fast"):
+                if other == args.precision:
+                    continue
+                torch.cuda.empty_cache()
+                n = max(3, args.steps // 4)
+                o = measure(other, n, 3)
+                line["other_precision_modes"].append({"precision": other, "value": o["value"], "unit": UNIT,
+                                                      "ms_per_step": o["max_ms"] / n, "stage_ms": o["stage_ms"],
+                                                      "gpu_launches": o["launches"]})
+                del o
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_port_depth_maps_per_s(args.workload, steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -294,8 +302,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="bf16: CostRegNet on tcgen05 tensor cores (north_star's conv3d path); fp32: strict CUDA-core path")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16", "fast"],
+                    help="bf16 (default): CostRegNet on tcgen05 tensor cores, the bf16 conv3d path north_star allows, fp32 "
+                         "arithmetic elsewhere; fp32: strict CUDA-core path; fast: bf16 + fp16 features")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other precision mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

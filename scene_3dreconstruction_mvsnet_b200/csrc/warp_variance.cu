@@ -1033,11 +1033,13 @@ namespace mvs {
 int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                       int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
-    // texel format of the source views in the tensor-core mode: fp16 (default), bf16, or fp32 (MVS_TEXEL_FMT, tuning knob)
+    // fp32 features in: fp32 texels and the reference's exact fp32 arithmetic by default (only the stored volume is
+    // bf16).  MVS_TEXEL_FMT=fp16|bf16 converts the source views to 16-bit texels first (tuning knob; the production
+    // 16-bit path is mvs_warp_variance_fwd_cp8_f16, fed directly by a half-precision FeatureNet).
     static const int texel_fmt = [] {
         const char *e = getenv("MVS_TEXEL_FMT");
-        if (!e) return 16;
-        return !strcmp(e, "fp32") ? 32 : (!strcmp(e, "bf16") ? 17 : 16);
+        if (!e) return 32;
+        return !strcmp(e, "fp16") ? 16 : (!strcmp(e, "bf16") ? 17 : 32);
     }();
     if (texel_fmt != 32 && nsrc > 0) {
         // workspace (sized for fp32 texels): rt | bf16 sources (half of the fp32 area) | fp32 reference view NHWC

@@ -149,11 +149,18 @@ class MVSNet(nn.Module):
     refine: kept for constructor compatibility.  The reference's RefineNet is dead code (F.cat does
             not exist, mvsnet.py:85; eval hard-codes refine=False, eval.py:308); refine=True raises.
     debug:  the reference's cv2.imshow bitmask; accepted and ignored (needs a display).
-    precision: "fp32" (default, matches the reference to fp32 rounding) or "bf16" (tensor cores).
+    precision: "fp32" (default) - everything in fp32 FMA arithmetic, matches the reference to fp32 rounding;
+               "bf16" - CostRegNet on the tcgen05 tensor cores (bf16 operands, fp32 accumulate), cost volume stored
+                        as bf16; warp/variance arithmetic in fp32 on fp32 features; FeatureNet on cuDNN with TF32
+                        allowed (PyTorch's default, i.e. what the reference itself does on a GPU);
+               "fast" - "bf16" plus fp16 features: FeatureNet in fp16, fp16 texels and packed-half interpolation
+                        in the fused warp kernel (sums still fp32).
     """
 
     def __init__(self, refine=True, debug=0, precision="fp32"):
         super().__init__()
+        if precision not in ("fp32", "bf16", "fast"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fast', got %r" % (precision,))
         self.refine = refine
         self.debug = debug
         self.precision = precision
@@ -176,8 +183,8 @@ class MVSNet(nn.Module):
         # channels_last suits cuDNN better for these tiny channel counts (measured on B200 at 5 x 1152x1600:
         # NCHW fp32 11.7 ms, NHWC fp32 9.8 ms, NHWC with TF32 allowed 3.0 ms)
         x = imgs.reshape(B * V, *imgs.shape[2:]).contiguous(memory_format=torch.channels_last)
-        if self.precision == "bf16":
-            # reduced-precision mode: let cuDNN use its TF32 tensor-core kernels for FeatureNet (PyTorch's own
+        if self.precision in ("bf16", "fast"):
+            # tensor-core modes: let cuDNN use its TF32 tensor-core kernels for FeatureNet (PyTorch's own
             # default for convolutions, i.e. what the reference does on a GPU); fp32 mode keeps the ambient setting
             with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=True):
                 f = self._features_eval(x)
@@ -214,13 +221,13 @@ class MVSNet(nn.Module):
                 marks.append((name, e))
 
         mark("start")
-        tc_mode = (not torch.is_grad_enabled()) and (not self.training) and self.precision == "bf16"
-        fea = self.extract_features_half(imgs) if tc_mode else self.extract_features(imgs)
+        fast = (not torch.is_grad_enabled()) and (not self.training) and self.precision == "fast"
+        fea = self.extract_features_half(imgs) if fast else self.extract_features(imgs)
         mark("features")
         proj_matrices = proj_matrices.float()
         depth_values = depth_values.float()
-        if not torch.is_grad_enabled() and not self.training and self.precision == "bf16":
-            # tensor-core mode: the cost volume goes from the fused warp+variance kernel to the tcgen05 CostRegNet
+        if not torch.is_grad_enabled() and not self.training and self.precision in ("bf16", "fast"):
+            # tensor-core modes: the cost volume goes from the fused warp+variance kernel to the tcgen05 CostRegNet
             # as bf16 chunk-planar data; no fp32 volume is written
             logits = ops.warp_variance_costreg_bf16(fea, proj_matrices.float(), depth_values.float(),
                                                     self.cost_regularization.folded_params(), marks=mark)
@@ -237,7 +244,7 @@ class MVSNet(nn.Module):
             if self.training:  # train-mode BN under no_grad (e.g. BN re-calibration): keep nn.Module semantics
                 logits = self.cost_regularization(volume_variance).squeeze(1)
             else:
-                logits = self.cost_regularization.infer(volume_variance, self.precision)
+                logits = self.cost_regularization.infer(volume_variance, "fp32" if self.precision == "fp32" else "bf16")
             mark("cost_regularization")
             depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
             mark("depth_tail")

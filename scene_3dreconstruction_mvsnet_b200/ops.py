@@ -253,18 +253,24 @@ def _costreg_params(folded):
 
 def warp_variance_cp8(fea, proj, depth_values):
     """Fused warp+variance with the bf16 chunk-planar output: returns a bf16 tensor [B, 4, D, h, w, 8]
-    (channel = chunk*8 + last index).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
-    fea = _prep(fea, "features", 5)
+    (channel = chunk*8 + last index).  fea: fp32 [B,V,32,h,w] (exact fp32 arithmetic) or fp16 channels-last
+    [B,V,h,w,32] (fp16 texels).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
+    half_nhwc = fea.dtype == torch.float16
+    if half_nhwc:
+        fea = fea.detach().contiguous()
+        B, V, H, W, C = fea.shape
+    else:
+        fea = _prep(fea, "features", 5)
+        B, V, C, H, W = fea.shape
     proj = _prep(proj, "proj_matrices", 4)
     depth_values = _prep(depth_values, "depth_values", 2)
-    B, V, C, H, W = fea.shape
     D = depth_values.shape[1]
     lib = _lib.load()
     vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.bfloat16, device=fea.device)
     ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
     with torch.cuda.device(fea.device):
-        rc = lib.mvs_warp_variance_fwd_cp8(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H,
-                                           W, _stream(fea))
+        fn = lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8
+        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
     _lib.check(rc, "mvs_warp_variance_fwd_cp8")
     return vol
 

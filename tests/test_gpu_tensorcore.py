@@ -85,18 +85,26 @@ def test_warp_variance_cp8(B, V, h, w, D):
     fea_q = fea.clone()
     fea_q[:, 1:] = fea[:, 1:].half().float()
     ref = orc.warp_variance(fea_q.numpy(), proj.numpy(), dv.numpy()).astype(np.float64)
-    cp8 = ops.warp_variance_cp8(fea.to(DEV), proj.to(DEV), dv.to(DEV))          # [B,4,D,h,w,8] bf16
+    fea16 = fea.to(DEV).half().permute(0, 1, 3, 4, 2).contiguous()             # [B,V,h,w,32] fp16 channels-last
+    cp8 = ops.warp_variance_cp8(fea16, proj.to(DEV), dv.to(DEV))                # [B,4,D,h,w,8] bf16
     back = cp8.permute(0, 1, 5, 2, 3, 4).reshape(B, 32, D, h, w).float().cpu().numpy().astype(np.float64)
+    fea_q[:, 0] = fea[:, 0].half().float()                                       # this entry also takes the ref view in fp16
+    ref = orc.warp_variance(fea_q.numpy(), proj.numpy(), dv.numpy()).astype(np.float64)
     err = np.abs(back - ref)
     assert (err <= np.abs(ref) * 2.0 ** -7 + 8e-3).all(), "max err %.4g" % err.max()
     assert err.mean() < 1.5e-3
+    # fp32 features in: exact fp32 arithmetic, only the stored volume is rounded to bf16
+    cp8s = ops.warp_variance_cp8(fea.to(DEV), proj.to(DEV), dv.to(DEV))
+    var = ops.warp_variance(fea.to(DEV), proj.to(DEV), dv.to(DEV))
+    assert torch.equal(cp8s.permute(0, 1, 5, 2, 3, 4).reshape(B, 32, D, h, w).float(), var.to(torch.bfloat16).float())
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fast"])
 @pytest.mark.parametrize("case", ["case_a", "case_b"])
-def test_tc_costreg_and_depth_golden(case, request, weights):
+def test_tc_costreg_and_depth_golden(case, precision, request, weights):
     from test_gpu_parity import cu, load_model, maxabs
     c = request.getfixturevalue(case)
-    m = load_model(weights, precision="bf16")
+    m = load_model(weights, precision=precision)
     logits = m.cost_regularization.infer(cu(c["variance"]), "bf16")
     assert maxabs(logits, c["logits"]) < 3e-2
     with torch.no_grad():
