@@ -456,6 +456,7 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
     const float invV = 1.0f / (float)V;
     const float xl = (float)(x0 + lane), yf = (float)y;
     const int W8 = W * 8;  // float4 units per texel row
+    const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
     const int nsm = min(nsrc, kMaxSrcSmem);
     if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
     for (int v = 0; v < nsm; ++v) {
@@ -493,10 +494,20 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
 
         for (int v = 0; v < nsrc; ++v) {
             const int n = b * nsrc + v;
-            const PackedTap t = (v < kMaxSrcSmem)
-                                    ? sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane],
-                                                      s_t[v][0], s_t[v][1], s_t[v][2], dep, H, W)
-                                    : sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+            PackedTap t;
+            if (OUT == OUT_CP8 && v < kMaxSrcSmem) {
+                // bf16-volume mode: closed-form coordinates (1e-7 relative from the reference's chain, invisible after the
+                // bf16 rounding of the stored variance) and the four tap weights formed once per pixel
+                t = sample_packed_fast(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0],
+                                       s_t[v][1], s_t[v][2], dep, sx, sy, H, W);
+                t.f = make_float4(t.f.x * t.f.z, t.f.y * t.f.z, t.f.x * t.f.w, t.f.y * t.f.w);
+            } else if (v < kMaxSrcSmem) {
+                t = sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0], s_t[v][1],
+                                    s_t[v][2], dep, H, W);
+            } else {
+                t = sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
+                if (OUT == OUT_CP8) t.f = make_float4(t.f.x * t.f.z, t.f.y * t.f.z, t.f.x * t.f.w, t.f.y * t.f.w);
+            }
             __syncwarp();
             s_f[warp][lane] = t.f;
             s_b[warp][lane] = t.base;
@@ -510,7 +521,8 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
                 const float4 *p01 = p00 + ((bb >> 30) & 1u) * 8;
                 const int dyo = (bb >> 31) ? W8 : 0;
                 const float4 a = __ldg(p00), bq = __ldg(p01), c = __ldg(p00 + dyo), dq = __ldg(p01 + dyo);
-                const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
+                const float w00 = (OUT == OUT_CP8) ? fc.x : fc.x * fc.z, w01 = (OUT == OUT_CP8) ? fc.y : fc.y * fc.z;
+                const float w10 = (OUT == OUT_CP8) ? fc.z : fc.x * fc.w, w11 = (OUT == OUT_CP8) ? fc.w : fc.y * fc.w;
                 const float vx = fmaf(dq.x, w11, fmaf(c.x, w10, fmaf(bq.x, w01, a.x * w00)));
                 const float vy = fmaf(dq.y, w11, fmaf(c.y, w10, fmaf(bq.y, w01, a.y * w00)));
                 const float vz = fmaf(dq.z, w11, fmaf(c.z, w10, fmaf(bq.z, w01, a.z * w00)));
@@ -1030,9 +1042,30 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
 
 // Internal: same op, output written as bf16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
 namespace mvs {
+int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
+                          int H, int W, cudaStream_t st);
+int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st);
+int features_nhwc16_to_rcp8(const void *fea16, void *tex16, int N, int H, int W, cudaStream_t st);
+static int warp_generation() {
+    static const int gen = [] {
+        const char *e = getenv("MVS_WARP_GEN");
+        return (e && atoi(e) == 2) ? 2 : 3;
+    }();
+    return gen;
+}
 int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                       int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
+    // Default: 16-bit texels through the TMA-window kernel (warp_variance_win.cu).  workspace (sized for fp32 texels):
+    // rt | fp16 RCP8 features of all V views.  MVS_WARP_GEN=2 keeps the previous-generation kernels selectable for A/B runs.
+    if (warp_generation() == 3) {
+        float *rt = (float *)workspace;
+        void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
+        if (nsrc > 0)
+            if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+        if (int rc = features_nchw_to_rcp8(fea, tex16, B * V, H, W, st)) return rc;
+        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+    }
     // fp32 features in: fp32 texels and the reference's exact fp32 arithmetic by default (only the stored volume is
     // bf16).  MVS_TEXEL_FMT=fp16|bf16 converts the source views to 16-bit texels first (tuning knob; the production
     // 16-bit path is mvs_warp_variance_fwd_cp8_f16, fed directly by a half-precision FeatureNet).
@@ -1087,6 +1120,11 @@ int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *dep
     float *rt = (float *)workspace;
     if (nsrc > 0)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+    if (warp_generation() == 3) {
+        void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
+        if (int rc = features_nhwc16_to_rcp8(fea16, tex16, B * V, H, W, st)) return rc;
+        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+    }
     const int dchunk = pick_dchunk(B, D, H, W);
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
     warp_variance_bf16tex_kernel<true, true><<<grid, kThreads, 0, st>>>(nullptr, (const uint4 *)fea16, rt, depth_values,
