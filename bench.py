@@ -249,8 +249,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": {"fp32": "f32",
-                      "bf16": "bf16 operands / f32 accumulate in CostRegNet (tcgen05); f32 elsewhere (FeatureNet: cuDNN, TF32 allowed)",
-                      "fast": "bf16 CostRegNet (tcgen05) + fp16 features / fp16 tap interpolation, f32 sums"}[args.precision],
+                      "bf16": "bf16 operands / f32 accumulate in CostRegNet (tcgen05); fp16 texels + packed-half tap interpolation, f32 sums in the fused warp kernel; FeatureNet cuDNN TF32",
+                      "fast": "as bf16, FeatureNet in fp16 as well"}[args.precision],
             "data": "synthetic",
             "config": {"workload": args.workload, "views": V, "image": [H, W], "depth_planes": D, "batch": 1,
                        "feature_map": [h, w], "weights": "random-init (seed 1), eval mode",
@@ -265,7 +265,8 @@ def run_ours(args):
                     "inputs -> H2D -> MVSNet.forward -> D2H depth+confidence, double-buffered)"},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
-            "roofline": {"kernel": "warp_variance_fwd2_kernel (+compose, +nchw_to_nhwc32 pre-pass)",
+            "roofline": {"kernel": ("warp_variance_fwd2_kernel" if args.precision == "fp32" else "warp_variance_win_kernel") +
+                                   " (+ homography compose and feature layout pre-passes, ~2% of the stage)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
                          "algorithmic_bytes": alg_bytes, "ms": wv_ms},

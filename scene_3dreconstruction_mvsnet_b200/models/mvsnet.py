@@ -151,10 +151,12 @@ class MVSNet(nn.Module):
     debug:  the reference's cv2.imshow bitmask; accepted and ignored (needs a display).
     precision: "fp32" (default) - everything in fp32 FMA arithmetic, matches the reference to fp32 rounding;
                "bf16" - CostRegNet on the tcgen05 tensor cores (bf16 operands, fp32 accumulate), cost volume stored
-                        as bf16; warp/variance arithmetic in fp32 on fp32 features; FeatureNet on cuDNN with TF32
-                        allowed (PyTorch's default, i.e. what the reference itself does on a GPU);
-               "fast" - "bf16" plus fp16 features: FeatureNet in fp16, fp16 texels and packed-half interpolation
-                        in the fused warp kernel (sums still fp32).
+                        as bf16; the fused warp+variance kernel samples fp16 texels with packed-half interpolation
+                        and accumulates Sum / Sum^2 in fp32 (TMA-window kernel, csrc/warp_variance_win.cu);
+                        FeatureNet on cuDNN with TF32 allowed (PyTorch's default, i.e. what the reference itself
+                        does on a GPU);
+               "fast" - "bf16" with FeatureNet in fp16 as well (its channels-last output feeds the warp kernel's
+                        layout pass directly).
     """
 
     def __init__(self, refine=True, debug=0, precision="fp32"):
