@@ -84,6 +84,8 @@ struct TcLayer {
     const float *shift;
     const uint4 *wpacked;
     long long *dbg;  // optional [gridDim.x][8] cycle counters (tools/tc_profile.py); nullptr in production
+    int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
+    int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     TcOp ops[kMaxOps];
 };
 
@@ -413,6 +415,296 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Depth-folded variant for stride-1 layers with Cout <= 16 (conv0 32->8, conv2 16->16, prob 8->1).
+//
+// With N = 16 every K=16 tcgen05.mma streams 4 KB of activations from shared memory for 16 output columns and
+// costs ~39 cycles regardless (tools/mma_microbench2.cu: 32 + N/4 cycles up to N = 128): conv0 spent 54 of them
+// per 128-voxel tile and was bound by that operand path (profiles/r01e).  Here the CTA walks INPUT planes instead
+// of output planes: input plane p contributes to output planes p-1, p, p+1 through the taps kd = 2, 1, 0, so one
+// MMA per (kh, kw, K-chunk) with N = 3*CW computes all three contributions at once (44 cycles at N = 48) --
+// 18 MMAs per plane for conv0 instead of 54.  The accumulators of consecutive output planes are consecutive
+// CW-column blocks of a ring of R blocks in TMEM (per M-tile), so the three contributions land in the right
+// accumulators by construction: same TMEM lane (= voxel), adjacent column blocks.  Every instruction accumulates:
+// the epilogue zeroes a block (tcgen05.st) right after draining it, so the issue loop stays as lean as the
+// output-stationary one (one descriptor add per MMA, everything else loop-invariant).  A window that wraps around
+// the ring is issued as two passes over the op table; partial windows at the ends of a z-segment are a B-row
+// offset plus a smaller N.  An output plane is complete -- and handed to the epilogue through its own mbarrier --
+// one step after its centre plane.  Each input plane is used by exactly one step, so the plane ring is pure TMA
+// prefetch depth.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFoldMaxR = 16;
+
+template <int MT>
+__device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab, int nops, uint32_t d, uint32_t cols_mt,
+                                                uint32_t sb, uint32_t brow, uint32_t idesc, uint64_t desc_hi) {
+#pragma unroll 2
+    for (int o = 0; o < nops; ++o) {
+        const uint2 e = optab[o];
+        const uint32_t alo = e.x + sb;
+        const uint64_t bd = desc_hi | (uint64_t)(e.y + brow);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            ptx::mma_bf16_ss(d + mt * cols_mt, desc_hi | (uint64_t)(alo + mt * 128), bd, idesc, 1u);
+    }
+}
+
+template <int CW>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t bar_base = ptx::smem_u32(smem);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (32 + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
+    uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
+    float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
+    constexpr uint32_t kHdr = 1664;
+    static_assert(400 + kMaxOps * 8 + 256 <= kHdr, "fold kernel header overflow");
+    uint8_t *w_smem = smem + kHdr;
+    const uint32_t w_base = bar_base + kHdr;
+    constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
+    const uint32_t ring_base = (w_base + L.wbytes_group + 127u) & ~127u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MT = L.MT;
+    const int R = L.fold_R;                 // accumulator blocks per M-tile
+    const uint32_t cols_mt = R * CW;        // TMEM columns per M-tile
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)MT * cols_mt) tmem_cols <<= 1;
+
+    {
+        const uint4 *src = L.wpacked;
+        uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
+        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+    }
+    for (int o = threadIdx.x; o < L.nops; o += kTcThreads)
+        optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
+    if (threadIdx.x < 64) s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + threadIdx.x) : 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < L.nslot; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < R; ++b) {
+            ptx::mbar_init(tfull_bar(b), 1);
+            ptx::mbar_init(tempty_bar(b), 8);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmap);
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
+    ptx::fence_proxy_async_smem();
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // all accumulator blocks start from zero (afterwards the epilogue re-zeroes each block as it drains it)
+    if (warp >= 2 && warp < 6) {
+        const uint32_t tb = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (uint32_t c = 0; c < (uint32_t)MT * cols_mt; c += 16) ptx::tmem_st_zero_x16(tb + c);
+        ptx::tmem_st_wait();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+
+    auto decode = [&](int it, int &b, int &x0, int &y0, int &zs, int &T) {
+        int r = it;
+        const int zseg = r % L.zsegs; r /= L.zsegs;
+        const int tx = r % L.tiles_x; r /= L.tiles_x;
+        const int ty = r % L.tiles_y; r /= L.tiles_y;
+        b = r;
+        x0 = tx * L.TXB;
+        y0 = ty * L.TY;
+        zs = zseg * L.zseg_len;
+        T = min(L.zseg_len, L.Dt - zs);
+    };
+
+    if (warp == 0) {
+        // ================= TMA producer: input planes zs-1 .. zs+T of every item =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            long long prod_wait = 0;
+            const uint32_t tx_bytes = (uint32_t)L.sub_bytes;
+            for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
+                int b, x0, y0, zs, T;
+                decode(it, b, x0, y0, zs, T);
+                for (int j = 0; j < T + 2; ++j, ++g) {
+                    const int slot = g % L.nslot;
+                    const long long c0 = clock64();
+                    ptx::mbar_wait(empty_bar(slot), ((g / L.nslot) & 1) ^ 1);
+                    prod_wait += clock64() - c0;
+                    ptx::mbar_arrive_expect_tx(full_bar(slot), tx_bytes);
+                    ptx::tma_load_4d(ring_base + slot * L.slot_bytes, &tmap, full_bar(slot), 2 * (x0 - 1), y0 - 1, zs - 1 + j,
+                                     b * L.chunks);
+                }
+            }
+            if (L.dbg) L.dbg[blockIdx.x * 8 + 0] = prod_wait;
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const bool leader = ptx::elect_one();
+        uint32_t g = 0;      // input planes consumed so far
+        uint32_t slot = 0;   // ring slot of plane g, and the parity of its current fill (all tracked incrementally:
+        uint32_t fpar = 0;   // no division or modulo in the per-plane path)
+        uint32_t pj = 0;     // TMEM ring position of accumulator block j of the current item
+        uint32_t epar = 0;   // bit b: parity of tempty_bar(b) to wait for next
+        long long w_full = 0, w_tempty = 0, t_issue = 0;
+        const long long t_start = clock64();
+        const int nops = L.nops;
+        const uint32_t nslot = L.nslot, uR = (uint32_t)R;
+        auto wrapR = [&](uint32_t v) { return v >= uR ? v - uR : v; };
+        for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
+            int b_, x0, y0, zs, T;
+            decode(it, b_, x0, y0, zs, T);
+            for (int j = 0; j < T + 2; ++j, ++g) {
+                // B row block k (kd = 2 - k) of input plane j feeds accumulator block j + k; valid outputs are 2 .. T+1
+                const int k0 = max(0, 2 - j), k1 = min(2, T + 1 - j);
+                const bool first_touch = (k1 == 2);
+                const uint32_t ft_blk = wrapR(pj + 2);
+                if (leader) {
+                    const long long c0 = clock64();
+                    ptx::mbar_wait(full_bar(slot), fpar);
+                    const long long c1 = clock64();
+                    // the block this plane touches first must have been drained and re-zeroed by the epilogue
+                    if (first_touch) ptx::mbar_wait(tempty_bar(ft_blk), ((epar >> ft_blk) & 1u) ^ 1u);
+                    w_full += c1 - c0;
+                    w_tempty += clock64() - c1;
+                }
+                if (first_touch) epar ^= 1u << ft_blk;
+                __syncwarp();
+                ptx::tcgen05_fence_after();
+                const uint32_t p0 = wrapR(pj + k0);
+                const int cnt = k1 - k0 + 1;
+                const int len0 = min(cnt, (int)(uR - p0));
+                if (leader) {
+                    const long long ci = clock64();
+                    const uint32_t sb = (ring_base + slot * L.slot_bytes) >> 4;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (pass == 1 && len0 == cnt) break;  // no wrap: one pass
+                        const uint32_t d = tmem_base + (pass == 0 ? p0 * CW : 0);
+                        const uint32_t brow = (pass == 0 ? k0 : k0 + len0) * CW;
+                        const uint32_t idesc = ptx::make_idesc_bf16_m128((pass == 0 ? len0 : cnt - len0) * CW);
+                        if (MT == 4) issue_fold_pass<4>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                        else if (MT == 3) issue_fold_pass<3>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                        else if (MT == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                        else issue_fold_pass<1>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                    }
+                    t_issue += clock64() - ci;
+                    ptx::tcgen05_commit(empty_bar(slot));
+                    if (j >= 2) ptx::tcgen05_commit(tfull_bar(pj));  // output plane zs + j - 2 is complete
+                }
+                __syncwarp();
+                if (++slot == nslot) { slot = 0; fpar ^= 1u; }
+                pj = wrapR(pj + 1);
+            }
+        }
+        if (leader && L.dbg) {
+            L.dbg[blockIdx.x * 8 + 1] = w_full;
+            L.dbg[blockIdx.x * 8 + 2] = w_tempty;
+            L.dbg[blockIdx.x * 8 + 3] = t_issue;
+            L.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+            L.dbg[blockIdx.x * 8 + 5] = g;
+        }
+    } else {
+        // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating over the M-tiles =================
+        const int q = warp & 3;
+        const int eset = (warp - 2) >> 2;
+        const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
+        const size_t zstride = (size_t)L.Hout * L.Wout;
+        const int nchunk = (L.cout_group + 7) >> 3;
+        uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
+        long long epi_wait = 0, epi_work = 0;
+        for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
+            int b, x0, y0, zs, T;
+            decode(it, b, x0, y0, zs, T);
+            size_t base[2] = {0, 0};
+            bool valid[2] = {false, false};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int mt = eset + 2 * i;
+                if (mt < MT) {
+                    const int pos = mt * 128 + q * 32 + lane;
+                    const int y = pos / L.P, x = pos - y * L.P;
+                    valid[i] = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
+                    base[i] = (size_t)(y0 + y) * L.Wout + (size_t)(x0 + x);
+                }
+            }
+            for (int e = 0; e < T; ++e) {
+                const long long c0 = clock64();
+                ptx::mbar_wait(tfull_bar(blk), (fpar >> blk) & 1u);
+                fpar ^= 1u << blk;
+                const long long c1 = clock64();
+                epi_wait += c1 - c0;
+                ptx::tcgen05_fence_after();
+                const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + blk * CW;
+                uint32_t r[2][CW];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int mt = eset + 2 * i;
+                    if (mt < MT) {
+#pragma unroll
+                        for (int c8 = 0; c8 < CW / 8; ++c8)
+                            if (c8 < nchunk) ptx::tmem_ld_x8(tb + mt * cols_mt + c8 * 8, &r[i][c8 * 8]);
+                    }
+                }
+                ptx::tmem_ld_wait();
+                // values are in registers: zero the block for its next use and hand it back
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    if (eset + 2 * i < MT) ptx::tmem_st_zero_x16(tb + (eset + 2 * i) * cols_mt);
+                ptx::tmem_st_wait();
+                ptx::tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(blk));
+                const size_t zoff = (size_t)(zs + e) * zstride;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (eset + 2 * i >= MT || !valid[i]) continue;
+                    const size_t vox = base[i] + zoff;
+#pragma unroll
+                    for (int c8 = 0; c8 < CW / 8; ++c8) {
+                        if (c8 >= nchunk) break;
+                        float v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            v[k] = __uint_as_float(r[i][c8 * 8 + k]) + s_shift[c8 * 8 + k];
+                            if (L.relu) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        if (L.out_f32) {
+                            reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
+                        } else {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[0], v[1]);
+                            pk.y = pack_bf16x2(v[2], v[3]);
+                            pk.z = pack_bf16x2(v[4], v[5]);
+                            pk.w = pack_bf16x2(v[6], v[7]);
+                            reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + c8) * plane + vox] = pk;
+                        }
+                    }
+                }
+                epi_work += clock64() - c1;
+                if (++blk == (uint32_t)R) blk = 0;
+            }
+            blk = (blk + 2) % R;  // the two lead-in blocks of the next item are never drained
+        }
+        if (warp == 2 && lane == 0 && L.dbg) {
+            L.dbg[blockIdx.x * 8 + 6] = epi_wait;
+            L.dbg[blockIdx.x * 8 + 7] = epi_work;
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout conversion and weight packing kernels
 // ------------------------------------------------------------------------------------------------
 // fp32 NCDHW [B][C][N] -> bf16 CP8 [B][C/8][N][8]     (N = D*H*W voxels)
@@ -457,6 +749,7 @@ struct WSrc {
 };
 struct WPackParams {
     int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
+    int fold_cw;  // > 0: depth-folded layout, B row n = (kd = 2 - n / fold_cw, cout = n % fold_cw); src taps are kh*3+kw
     WSrc src[kMaxOps];
 };
 
@@ -471,11 +764,17 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     const int n = r % p.npad; r /= p.npad;
     const int c = r % 2;
     const int blk = r / 2;
-    const int tap = p.src[blk].tap[c];
+    int tap = p.src[blk].tap[c];
     const int cin = p.src[blk].cin0[c] + e;
-    const int co = g * p.cout_group + n;
+    int co = g * p.cout_group + n;
+    int nn = n;
+    if (p.fold_cw > 0) {
+        nn = n % p.fold_cw;
+        co = nn;
+        if (tap >= 0) tap += (2 - n / p.fold_cw) * 9;
+    }
     float v = 0.f;
-    if (tap >= 0 && n < p.cout_group && co < p.cout_total && cin < p.cin_total)
+    if (tap >= 0 && nn < p.cout_group && co < p.cout_total && cin < p.cin_total)
         v = p.transposed ? w[((size_t)cin * p.cout_total + co) * 27 + tap] : w[((size_t)co * p.cin_total + cin) * 27 + tap];
     out[idx] = __float2bfloat16_rn(v);
 }
@@ -510,25 +809,29 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     else { Dt = Din; Ht = Hin; Wt = Win; }
     // N (padded cout) per CTA: keep resident weights <= ~112 KB
     const int kpairs_tap = (cin >= 16) ? cin / 16 : 1;
+    // depth-folded variant (conv3d_tc_fold_kernel): stride-1 layers whose Cout fits one 16-column block
+    static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
+    const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
     int ntaps_ops;  // MMA instructions per step
-    if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
+    if (fold) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
+    else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
     else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
     MVS_REQUIRE(!(kind == TC_CONVT && cin < 16), "tc convT needs Cin >= 16");
     MVS_REQUIRE(ntaps_ops <= kMaxOps, "tc conv: too many ops");
     int ngroups = 1;
     int cout_group = cout;
     while (true) {
-        const int npad_try = cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64);
+        const int npad_try = fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
         if ((size_t)ntaps_ops * npad_try * 32 <= 112 * 1024 && cout_group <= 64) break;
         ngroups *= 2;
         cout_group = cout / ngroups;
         MVS_REQUIRE(cout_group >= 8 && cout % ngroups == 0, "tc conv: cannot split Cout=%d", cout);
     }
-    const int npad = cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64);
+    const int npad = fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
     const int nacc = (kind == TC_CONVT) ? 8 : 1;
     const int wbytes = ntaps_ops * npad * 32;
     // ring geometry
-    const int need = (kind == TC_CONVT) ? 2 : 3;
+    const int need = fold ? 1 : ((kind == TC_CONVT) ? 2 : 3);
     const int adv = (kind == TC_CONV_S2) ? 2 : 1;
     const int nsub = (kind == TC_CONV_S2) ? 4 : 1;
     const int halo = (kind == TC_CONV_S1) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
@@ -536,7 +839,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int max_cols = 128 - halo;  // boxDim[x] <= 256: 2 uint64 per voxel (merged inner dim) or elementStrides = 2
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
     double best_score = -1;
-    const int tmem_budget = 256 / (nacc * npad);  // MT limit: 2 buffers x nacc x MT x npad <= 512 columns
+    // MT limit: 2 buffers x nacc x MT x npad <= 512 columns; folded: MT regions of R blocks x 16 columns, R >= 8
+    const int tmem_budget = fold ? 4 : 256 / (nacc * npad);
     for (int nx = 1; nx <= 64; ++nx) {
         const int TXB = (Wt + nx - 1) / nx;
         if (TXB > max_cols) continue;
@@ -597,7 +901,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const int len = (Dt + zs - 1) / zs, nseg = (Dt + len - 1) / len;
             const long long items = (long long)cols * nseg;
             const double wave = (double)items / ((double)((items + num_sms - 1) / num_sms) * num_sms);
-            const double haloeff = (double)(adv * len) / (adv * (len - 1) + need);
+            const double haloeff = fold ? (double)len / (len + 2) : (double)(adv * len) / (adv * (len - 1) + need);
             const double sc = wave * haloeff;
             if (sc > best + 1e-9) { best = sc; zsegs = zs; }
         }
@@ -614,6 +918,9 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     WPackParams &W = pl.W;
     W.npad = npad; W.cout_group = cout_group; W.cout_total = cout; W.cin_total = cin; W.ngroups = ngroups;
     W.transposed = (kind == TC_CONVT);
+    W.fold_cw = fold ? 16 : 0;
+    L.fold = fold ? 1 : 0;
+    L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * 16)) : 0;
     const int chunk_stride = rows * P * 16;
     int nops = 0;
     auto tap_off = [&](int kh, int kw) -> int {  // byte offset of a conv tap inside its plane (chunk 0)
@@ -623,7 +930,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     };
     if (kind != TC_CONVT) {
         L.acc_first[0] = 0;
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = 0; kd < (fold ? 1 : 3); ++kd) {  // folded: kd lives in the rows of the packed B block
             if (cin >= 16) {
                 for (int kh = 0; kh < 3; ++kh)
                     for (int kw = 0; kw < 3; ++kw)
@@ -768,6 +1075,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };
+    if (pl.L.fold) return launch(conv3d_tc_fold_kernel<16>);
     if (pl.npad == 16) return launch(conv3d_tc_kernel<16>);
     if (pl.npad == 32) return launch(conv3d_tc_kernel<32>);
     return launch(conv3d_tc_kernel<64>);

@@ -49,7 +49,7 @@ int main() {
     const int iters = 4096;
     for (int layout : {0, 2})
         for (int M : {128, 64})
-            for (int N : {8, 16, 32, 64, 128, 256}) {
+            for (int N : {8, 16, 32, 48, 64, 80, 96, 112, 128, 192, 256}) {
                 if (M == 128 && N < 16) continue;
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
                 const uint32_t sbo = layout ? 1024 : 128, lbo = layout ? 16 : 12288;
