@@ -130,6 +130,31 @@ int mvs_warp_variance_fwd_cp8_f16(const void *fea16_nhwc, const float *proj, con
 int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *params, float *logits, void *workspace, int B,
                         int D, int H, int W, void *stream);
 
+/* ---- FeatureNet.forward (models/mvsnet.py:10-30), eval mode, on the tensor cores (fp16 operands, fp32 accumulate).
+ * the stage next to the hot path.  imgs [N,3,H,W] fp32 (N = B*V images) ->
+ * fea_rcp8_f16: fp16 row-chunk-planar [N][H/4][32/8][W/4][8], the layout mvs_warp_variance_fwd_cp8_feat samples
+ * through its TMA windows (no conversion pass in between).
+ * params: the 8 layers conv0, conv1, conv2, conv3, conv4, conv5, conv6, feature in their NATIVE shapes
+ * ([Cout][Cin][k][k], k = 5 for conv2 / conv5), eval-mode BN already folded: w scaled, shift = folded bias
+ * (the last layer's shift is its conv bias).  H, W divisible by 4. */
+#define MVS_FEATURENET_LAYERS 8
+typedef struct {
+    const float *w[MVS_FEATURENET_LAYERS];
+    const float *shift[MVS_FEATURENET_LAYERS];
+} mvs_featurenet_params;
+size_t mvs_featurenet_tc_workspace_bytes(int N, int H, int W);
+int mvs_featurenet_tc_fwd(const float *imgs, const mvs_featurenet_params *params, void *fea_rcp8_f16, void *workspace,
+                          int N, int H, int W, void *stream);
+/* One ConvBnReLU (models/module.py:8-15) on the same kernel, fp32 NCHW in/out (tests, diagnostics):
+ * ksize 3 / stride 1 / pad 1, or ksize 5 / stride 2 / pad 2.  s2d_out = 1 returns the space-to-depth form
+ * [N, 4*Cout, H'/2, W'/2] (channel = (y&1)*2+(x&1) major) that a following stride-2 layer consumes. */
+int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin, int Cout,
+                          int H, int W, int ksize, int stride, int s2d_out, void *stream);
+/* Fused warp+variance on features in the layout mvs_featurenet_tc_fwd produces: fea [B*V][H][4][W][8] fp16 with
+ * image index n = b*V + v (view 0 = reference view).  workspace: mvs_warp_variance_workspace_bytes(). */
+int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const float *proj, const float *depth_values, void *vol_cp8,
+                                   void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
+
 /* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
  *                                                        models/mvsnet.py:192-193,204,214-218
  * logits [B,D,H,W], depth_values [B,D] -> depth [B,H,W], conf [B,H,W]; prob [B,D,H,W] optional. */

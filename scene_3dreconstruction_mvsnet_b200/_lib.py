@@ -15,6 +15,7 @@ MVS_OK = 0
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 COSTREG_LAYERS = 11
+FEATURENET_LAYERS = 8
 
 _c_float_p = ctypes.c_void_p  # device or host pointers are passed as raw addresses
 _i = ctypes.c_int
@@ -22,6 +23,10 @@ _i = ctypes.c_int
 
 class CostRegParams(ctypes.Structure):
     _fields_ = [("w", ctypes.c_void_p * COSTREG_LAYERS), ("shift", ctypes.c_void_p * COSTREG_LAYERS)]
+
+
+class FeatureNetParams(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p * FEATURENET_LAYERS), ("shift", ctypes.c_void_p * FEATURENET_LAYERS)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/mvsnet_b200.h
@@ -49,6 +54,11 @@ SIGNATURES = {
     "mvs_volume_cp8_bytes": (ctypes.c_size_t, [_i] * 4),
     "mvs_warp_variance_fwd_cp8": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_warp_variance_fwd_cp8_f16": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
+    "mvs_warp_variance_fwd_cp8_feat": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
+    "mvs_featurenet_tc_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
+    "mvs_featurenet_tc_fwd": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
+                              [ctypes.c_void_p]),
+    "mvs_conv2d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 8 + [ctypes.c_void_p]),
     "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
                             [ctypes.c_void_p]),
     "mvs_softmax_depth_conf": (_i, [_c_float_p] * 5 + [_i] * 4 + [ctypes.c_void_p]),

@@ -4,6 +4,9 @@
 //   * Conv3d k3 s1 p1 (+BN+ReLU)                      conv0, conv2, conv4, conv6, prob
 //   * Conv3d k3 s2 p1 (+BN+ReLU)                      conv1, conv3, conv5
 //   * ConvTranspose3d k3 s2 p1 op1 (+BN+ReLU, +skip)  conv7, conv9, conv11  (8 output-parity classes)
+//   * Conv2d k3 s1 p1 (+BN+ReLU), fp16 operands       FeatureNet (mvsnet.py:10-30): the N images are the planes, no z
+//     taps; its two 5x5 stride-2 layers run as 3x3 stride-1 layers on a space-to-depth layout that the previous
+//     layer's epilogue writes directly (featurenet_tc below)
 //
 // Activations live in HBM as bf16 "CP8":  [B][C/8][D][H][W][8]  -- channel chunks of 8 (16 bytes)
 // are the innermost unit, so (a) a TMA box {8ch, P cols, R rows, 1 plane, C/8 chunks} lands in shared
@@ -84,6 +87,9 @@ struct TcLayer {
     const float *shift;
     const uint4 *wpacked;
     long long *dbg;  // optional [gridDim.x][8] cycle counters (tools/tc_profile.py); nullptr in production
+    int f16;         // 1: fp16 operands / fp16 outputs (FeatureNet); 0: bf16
+    int out_mode;    // 0: CP8 [C/8][D][H][W][8]; 1: space-to-depth [4 parities x C/8][D][H/2][W/2][8];
+                     // 2: row-chunk-planar "RCP8" [D][H][C/8][W][8] (what the fused warp kernel's TMA windows read)
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     TcOp ops[kMaxOps];
@@ -92,6 +98,14 @@ struct TcLayer {
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+    return F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
 }
 
 // One elected lane issues every tcgen05.mma of one z-step.  Per op: one 8-byte shared-memory load of the two
@@ -118,7 +132,7 @@ __device__ __forceinline__ void issue_step(const TcLayer &L, const uint2 *__rest
     }
 }
 
-template <int NPAD>
+template <int NPAD, bool F16 = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -227,7 +241,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // The whole warp runs this loop with warp-uniform values (kernel parameters, loop counters) so that
         // descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
         const bool leader = ptx::elect_one();
-        const uint32_t idesc = ptx::make_idesc_bf16_m128(NPAD);
+        const uint32_t idesc = F16 ? ptx::make_idesc_f16_m128(NPAD) : ptx::make_idesc_bf16_m128(NPAD);
         uint32_t st = 0;
         uint32_t s0 = 0;    // ring slot of the oldest plane of the current step
         uint32_t par = 0;   // bit s: parity of the fill of slot s that is current (toggles when the slot is released)
@@ -296,8 +310,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int eset = (warp - 2) >> 2;  // the two warps of a quadrant alternate over the batches of a step
         const uint4 *skip = L.skip;
-        const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
-        const size_t zstride = (size_t)L.out_scale * L.Hout * L.Wout;
+        // space-to-depth output (out_s2d): voxel (z, y, x), chunk c -> chunk ((y&1)*2 + (x&1)) * C/8 + c of a volume
+        // with half the rows and columns; the parity term is folded into the per-thread base offset below
+        // and RCP8 (out_mode 2) only change the chunk stride ("plane"), the z stride and the per-thread base
+        const bool s2d = L.out_mode == 1, rcp8 = L.out_mode == 2;
+        const size_t plane = s2d ? (size_t)L.Dout * (L.Hout / 2) * (L.Wout / 2)
+                                 : (rcp8 ? (size_t)L.Wout : (size_t)L.Dout * L.Hout * L.Wout);
+        const size_t zstride = s2d ? (size_t)(L.Hout / 2) * (L.Wout / 2)
+                                   : (rcp8 ? (size_t)L.Hout * (L.cout_total >> 3) * L.Wout : (size_t)L.out_scale * L.Hout * L.Wout);
         const int nacc_shift = (L.nacc == 8) ? 3 : 0;
         const int npairs = L.MT << nacc_shift;
         const int nchunk = (L.cout_group + 7) >> 3;
@@ -315,7 +335,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     const int pos = mt * 128 + q * 32 + lane;
                     const int y = pos / L.P, x = pos - y * L.P;
                     const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
-                    const size_t bs = (size_t)(L.out_scale * (y0 + y)) * L.Wout + (size_t)L.out_scale * (x0 + x);
+                    size_t bs = (size_t)(L.out_scale * (y0 + y)) * L.Wout + (size_t)L.out_scale * (x0 + x);
+                    if (s2d)
+                        bs = (size_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * plane +
+                             (size_t)((y0 + y) >> 1) * (L.Wout / 2) + (size_t)((x0 + x) >> 1);
+                    if (rcp8) bs = (size_t)(y0 + y) * (L.cout_total >> 3) * L.Wout + (size_t)(x0 + x);
                     vmask |= (valid ? 1u : 0u) << mt;
                     if (mt == 0) base0 = bs; else if (mt == 1) base1 = bs; else if (mt == 2) base2 = bs; else base3 = bs;
                 }
@@ -383,10 +407,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                     }
                                 }
                                 uint4 pk;
-                                pk.x = pack_bf16x2(v[0], v[1]);
-                                pk.y = pack_bf16x2(v[2], v[3]);
-                                pk.z = pack_bf16x2(v[4], v[5]);
-                                pk.w = pack_bf16x2(v[6], v[7]);
+                                pk.x = pack16x2<F16>(v[0], v[1]);
+                                pk.y = pack16x2<F16>(v[2], v[3]);
+                                pk.z = pack16x2<F16>(v[4], v[5]);
+                                pk.w = pack16x2<F16>(v[6], v[7]);
                                 reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + chunk0 + c8) * plane + vox[j]] = pk;
                             }
                         }
@@ -750,6 +774,8 @@ struct WSrc {
 struct WPackParams {
     int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
     int fold_cw;  // > 0: depth-folded layout, B row n = (kd = 2 - n / fold_cw, cout = n % fold_cw); src taps are kh*3+kw
+    int ntaps;    // taps per (cout, cin) pair in the source weights: 27 (3-D) or 9 (2-D, [Cout][Cin][3][3])
+    int f16;      // 1: fp16 output, 0: bf16
     WSrc src[kMaxOps];
 };
 
@@ -775,14 +801,15 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     }
     float v = 0.f;
     if (tap >= 0 && nn < p.cout_group && co < p.cout_total && cin < p.cin_total)
-        v = p.transposed ? w[((size_t)cin * p.cout_total + co) * 27 + tap] : w[((size_t)co * p.cin_total + cin) * 27 + tap];
-    out[idx] = __float2bfloat16_rn(v);
+        v = p.transposed ? w[((size_t)cin * p.cout_total + co) * 27 + tap] : w[((size_t)co * p.cin_total + cin) * p.ntaps + tap];
+    if (p.f16) reinterpret_cast<__half *>(out)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    else out[idx] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host side: per-layer configuration
 // ------------------------------------------------------------------------------------------------
-enum TcKind { TC_CONV_S1 = 0, TC_CONV_S2 = 1, TC_CONVT = 2 };
+enum TcKind { TC_CONV_S1 = 0, TC_CONV_S2 = 1, TC_CONVT = 2, TC_CONV2D = 3 };
 
 struct TcPlan {
     TcLayer L;
@@ -812,8 +839,9 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // depth-folded variant (conv3d_tc_fold_kernel): stride-1 layers whose Cout fits one 16-column block
     static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
     const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
+    const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
     int ntaps_ops;  // MMA instructions per step
-    if (fold) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
+    if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
     else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
     else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
     MVS_REQUIRE(!(kind == TC_CONVT && cin < 16), "tc convT needs Cin >= 16");
@@ -831,10 +859,10 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int nacc = (kind == TC_CONVT) ? 8 : 1;
     const int wbytes = ntaps_ops * npad * 32;
     // ring geometry
-    const int need = fold ? 1 : ((kind == TC_CONVT) ? 2 : 3);
+    const int need = (fold || is2d) ? 1 : ((kind == TC_CONVT) ? 2 : 3);
     const int adv = (kind == TC_CONV_S2) ? 2 : 1;
     const int nsub = (kind == TC_CONV_S2) ? 4 : 1;
-    const int halo = (kind == TC_CONV_S1) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
+    const int halo = (kind == TC_CONV_S1 || is2d) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
     // choose the tile: TXB columns, TY rows, MT M-tiles of 128 flattened positions
     const int max_cols = 128 - halo;  // boxDim[x] <= 256: 2 uint64 per voxel (merged inner dim) or elementStrides = 2
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
@@ -881,10 +909,10 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     L.sub_stride = (L.sub_bytes + 127) & ~127;
     L.slot_bytes = nsub * L.sub_stride;
     L.need = need; L.adv = adv; L.nslot = best_nslot;
-    L.pz0 = (kind == TC_CONVT) ? 0 : -1;
+    L.pz0 = (kind == TC_CONVT || is2d) ? 0 : -1;
     L.zscale = (kind == TC_CONV_S2) ? 2 : 1;
     L.in_scale = (kind == TC_CONV_S2) ? 2 : 1;
-    if (kind == TC_CONV_S1) { L.sub_xoff[0] = -1; L.sub_yoff[0] = -1; }
+    if (kind == TC_CONV_S1 || is2d) { L.sub_xoff[0] = -1; L.sub_yoff[0] = -1; }
     else if (kind == TC_CONVT) { L.sub_xoff[0] = 0; L.sub_yoff[0] = 0; }
     else {
         for (int s = 0; s < 4; ++s) {  // s = ypar*2 + xpar; parity 1 = odd input index, starts one element earlier
@@ -897,7 +925,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     int zsegs = 1;
     {
         double best = -1;
-        for (int zs = 1; zs <= std::max(1, Dt / 4); ++zs) {
+        for (int zs = 1; zs <= (is2d ? Dt : std::max(1, Dt / 4)); ++zs) {
             const int len = (Dt + zs - 1) / zs, nseg = (Dt + len - 1) / len;
             const long long items = (long long)cols * nseg;
             const double wave = (double)items / ((double)((items + num_sms - 1) / num_sms) * num_sms);
@@ -919,18 +947,19 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.npad = npad; W.cout_group = cout_group; W.cout_total = cout; W.cin_total = cin; W.ngroups = ngroups;
     W.transposed = (kind == TC_CONVT);
     W.fold_cw = fold ? 16 : 0;
+    W.ntaps = is2d ? 9 : 27;
     L.fold = fold ? 1 : 0;
     L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * 16)) : 0;
     const int chunk_stride = rows * P * 16;
     int nops = 0;
     auto tap_off = [&](int kh, int kw) -> int {  // byte offset of a conv tap inside its plane (chunk 0)
-        if (kind == TC_CONV_S1) return (kh * P + kw) * 16;
+        if (kind == TC_CONV_S1 || is2d) return (kh * P + kw) * 16;
         const int ypar = (kh != 1), xpar = (kw != 1);
         return (ypar * 2 + xpar) * L.sub_stride + ((kh == 2 ? 1 : 0) * P + (kw == 2 ? 1 : 0)) * 16;
     };
     if (kind != TC_CONVT) {
         L.acc_first[0] = 0;
-        for (int kd = 0; kd < (fold ? 1 : 3); ++kd) {  // folded: kd lives in the rows of the packed B block
+        for (int kd = 0; kd < ((fold || is2d) ? 1 : 3); ++kd) {  // folded: kd lives in the rows of the packed B block; 2-D: no kd
             if (cin >= 16) {
                 for (int kh = 0; kh < 3; ++kh)
                     for (int kw = 0; kw < 3; ++kw)
@@ -1056,9 +1085,15 @@ static long long *g_tc_dbg = nullptr;  // set by mvs_tc_set_debug_buffer (diagno
 
 static int run_layer(TcKind kind, const void *in, const float *w_fp32, const float *shift, int relu, const void *skip,
                      void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
-                     int num_sms, cudaStream_t st) {
+                     int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0) {
     static thread_local TcPlan pl;  // ~3 KB; not kept across calls
     if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms)) return rc;
+    MVS_REQUIRE(!f16 || (kind == TC_CONV2D && pl.npad <= 32 && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
+    MVS_REQUIRE(out_mode == 0 || (kind == TC_CONV2D && B == 1), "alternative output layouts: 2-D layers only");
+    MVS_REQUIRE(out_mode != 1 || (Hin % 2 == 0 && Win % 2 == 0), "space-to-depth output needs even H, W");
+    pl.L.f16 = f16;
+    pl.L.out_mode = out_mode;
+    pl.W.f16 = f16;
     pl.L.out = out;
     pl.L.skip = (const uint4 *)skip;
     pl.L.shift = shift;
@@ -1076,6 +1111,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         return MVS_OK;
     };
     if (pl.L.fold) return launch(conv3d_tc_fold_kernel<16>);
+    if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true>) : launch(conv3d_tc_kernel<32, true>);
     if (pl.npad == 16) return launch(conv3d_tc_kernel<16>);
     if (pl.npad == 32) return launch(conv3d_tc_kernel<32>);
     return launch(conv3d_tc_kernel<64>);
@@ -1163,6 +1199,161 @@ int tc_layer_ncdhw(int kind, const float *x, const float *w, const float *shift,
     return MVS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// FeatureNet.forward (mvsnet.py:10-30) on the tensor cores, eval mode (BN folded by the caller), fp16 operands.
+// Activations are fp16 "CP8 over images": [C/8][N][H][W][8] -- the N images play the role of the depth planes of
+// the 3-D layers (no taps across them).  The two 5x5 stride-2 layers (conv2, conv5) are evaluated as 3x3
+// stride-1 layers over the space-to-depth form of their input: out(yo,xo) = sum_{kh,kw} in(2yo+kh-2, 2xo+kw-2)
+// w(kh,kw) with kh = 2 KH + py: the 3x3 window KH over half-resolution rows Y = yo-1..yo+1 of the four
+// parity sub-images (py, px), i.e. a 3x3 conv with 4 Cin channels and the 5x5 weights scattered into 6x6
+// (row/column 5 zero).  The layer before each of them writes that layout straight from its epilogue.
+// ------------------------------------------------------------------------------------------------
+// fp32 NCHW [N][C][H][W] -> fp16 [ceil(C/8) (x4 if s2d)][N][Ho][Wo][8]; channels beyond C are zero
+__global__ void nchw_to_cp8n_f16_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int N, int C, int H, int W,
+                                        int s2d, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Ho = s2d ? H / 2 : H, Wo = s2d ? W / 2 : W, cpc = (C + 7) / 8;
+    const int x = (int)(i % Wo);
+    long long r = i / Wo;
+    const int y = (int)(r % Ho); r /= Ho;
+    const int n = (int)(r % N);
+    const int chunk = (int)(r / N);
+    const int par = s2d ? chunk / cpc : 0, cc = s2d ? chunk % cpc : chunk;
+    const int ys = s2d ? 2 * y + (par >> 1) : y, xs = s2d ? 2 * x + (par & 1) : x;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float f[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = cc * 8 + 2 * j + h;
+            f[h] = (c < C) ? __ldg(in + (((size_t)n * C + c) * H + ys) * W + xs) : 0.f;
+        }
+        w[j] = pack_f16x2(f[0], f[1]);
+    }
+    out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// fp16 [C/8][N][H][W][8] -> fp32 NCHW (tests)
+__global__ void cp8n_f16_to_nchw_kernel(const uint4 *__restrict__ in, float *__restrict__ out, int N, int C, int H, int W,
+                                        long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int n = (int)(r % N);
+    const int cc = (int)(r / N);
+    const uint4 v = __ldg(in + i);
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        out[(((size_t)n * C + cc * 8 + 2 * j) * H + y) * W + x] = f.x;
+        out[(((size_t)n * C + cc * 8 + 2 * j + 1) * H + y) * W + x] = f.y;
+    }
+}
+
+// Effective 3x3 weights [Cout][Cin_eff][3][3] of one FeatureNet layer from its native [Cout][Cin][k][k]:
+// k = 3: channels padded with zeros up to Cin_eff;  k = 5 (stride 2): the space-to-depth form, Cin_eff = 4 Cin,
+// effective channel = (py*2+px)*Cin + ci, tap (KH,KW) <- (kh,kw) = (2KH+py, 2KW+px) when both are < 5.
+__global__ void featurenet_effective_weights_kernel(const float *__restrict__ w, float *__restrict__ out, int cout, int cin,
+                                                    int cin_eff, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cout * cin_eff * 9) return;
+    const int KW = i % 3, KH = (i / 3) % 3, ce = (i / 9) % cin_eff, co = i / (9 * cin_eff);
+    float v = 0.f;
+    if (k == 3) {
+        if (ce < cin) v = w[((size_t)(co * cin + ce) * 3 + KH) * 3 + KW];
+    } else {
+        const int par = ce / cin, ci = ce % cin, kh = 2 * KH + (par >> 1), kw = 2 * KW + (par & 1);
+        if (kh < 5 && kw < 5) v = w[((size_t)(co * cin + ci) * 5 + kh) * 5 + kw];
+    }
+    out[i] = v;
+}
+
+// layer table: native Cin, Cout, kernel size (stride 2 when 5), effective Cin of the 3x3 form
+static const int kFeatCin[MVS_FEATURENET_LAYERS] = {3, 8, 8, 16, 16, 16, 32, 32};
+static const int kFeatCout[MVS_FEATURENET_LAYERS] = {8, 8, 16, 16, 16, 32, 32, 32};
+static const int kFeatK[MVS_FEATURENET_LAYERS] = {3, 3, 5, 3, 3, 5, 3, 3};
+static const int kFeatCinEff[MVS_FEATURENET_LAYERS] = {8, 8, 32, 16, 16, 64, 32, 32};
+
+size_t featurenet_tc_workspace_bytes(int N, int H, int W) {
+    // per input pixel and image: in 16 | a0 16 | a1 (s2d) 16 | a2 8 | a3 8 | a4 (s2d) 8 | a5 4 | a6 4 bytes
+    return align_up((size_t)N * H * W * 80, 1024) + 8 * 1024 + MVS_FEATURENET_LAYERS * (kWScratch + 128 * 1024) + 16 * 1024;
+}
+
+// imgs fp32 [N][3][H][W] -> fea fp16 RCP8 [N][H/4][4][W/4][8]
+int featurenet_tc(const float *imgs, const mvs_featurenet_params *p, void *fea, void *workspace, int N, int H, int W,
+                  cudaStream_t st) {
+    int dev = 0, num_sms = 148;
+    MVS_CUDA(cudaGetDevice(&dev));
+    MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t px = (size_t)N * H * W;
+    uint8_t *ws = (uint8_t *)workspace;
+    auto take = [&](size_t bytes) { uint8_t *r = ws; ws += align_up(bytes, 1024); return r; };
+    void *in0 = take(px * 16), *a0 = take(px * 16), *a1 = take(px * 16), *a2 = take(px * 8), *a3 = take(px * 8),
+         *a4 = take(px * 8), *a5 = take(px * 4), *a6 = take(px * 4);
+    uint8_t *wsc = take(MVS_FEATURENET_LAYERS * (kWScratch + 128 * 1024));
+    {
+        const long long total = (long long)px;
+        nchw_to_cp8n_f16_kernel<<<cdiv(total, 256), 256, 0, st>>>(imgs, (uint4 *)in0, N, 3, H, W, 0, total);
+        MVS_LAUNCH_CHECK(1);
+    }
+    const void *ins[MVS_FEATURENET_LAYERS] = {in0, a0, a1, a2, a3, a4, a5, a6};
+    void *outs[MVS_FEATURENET_LAYERS] = {a0, a1, a2, a3, a4, a5, a6, fea};
+    const int scale[MVS_FEATURENET_LAYERS] = {1, 1, 2, 2, 2, 4, 4, 4};   // resolution divisor of each layer's input
+    const int out_mode[MVS_FEATURENET_LAYERS] = {0, 1, 0, 0, 1, 0, 0, 2};  // last layer: RCP8 for the warp kernel
+    for (int l = 0; l < MVS_FEATURENET_LAYERS; ++l) {
+        float *weff = (float *)(wsc + (size_t)l * (kWScratch + 128 * 1024));
+        void *wpk = (uint8_t *)weff + 128 * 1024;
+        const int nw = kFeatCout[l] * kFeatCinEff[l] * 9;
+        featurenet_effective_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(p->w[l], weff, kFeatCout[l], kFeatCin[l],
+                                                                          kFeatCinEff[l], kFeatK[l]);
+        MVS_LAUNCH_CHECK(1);
+        if (int rc = run_layer(TC_CONV2D, ins[l], weff, p->shift[l], l != MVS_FEATURENET_LAYERS - 1, nullptr, outs[l], 0, wpk,
+                               1, kFeatCinEff[l], kFeatCout[l], N, H / scale[l], W / scale[l], num_sms, st, 1, out_mode[l]))
+            return rc;
+    }
+    return MVS_OK;
+}
+
+// Single 2-D layer for tests: fp32 NCHW in/out.  ksize 3 (stride 1) or 5 (stride 2, through the space-to-depth form).
+int tc_conv2d_nchw(const float *x, const float *w, const float *shift, int relu, float *y, int N, int cin, int cout, int H,
+                   int W, int ksize, int s2d_out, cudaStream_t st) {
+    int dev = 0, num_sms = 148;
+    MVS_CUDA(cudaGetDevice(&dev));
+    MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int s2d_in = (ksize == 5);
+    const int cin8 = (cin + 7) / 8 * 8, cin_eff = s2d_in ? 4 * cin8 : cin8;
+    const int Hi = s2d_in ? H / 2 : H, Wi = s2d_in ? W / 2 : W;
+    const size_t in_b = align_up((size_t)N * Hi * Wi * cin_eff * 2, 1024), out_b = align_up((size_t)N * Hi * Wi * cout * 2, 1024);
+    uint8_t *ws = nullptr;
+    MVS_CUDA(cudaMallocAsync((void **)&ws, in_b + out_b + kWScratch + 128 * 1024, st));
+    void *xin = ws, *yout = ws + in_b;
+    float *weff = (float *)(ws + in_b + out_b);
+    void *wpk = (uint8_t *)weff + 128 * 1024;
+    const long long tin = (long long)N * Hi * Wi * (cin_eff / 8);
+    nchw_to_cp8n_f16_kernel<<<cdiv(tin, 256), 256, 0, st>>>(x, (uint4 *)xin, N, cin, H, W, s2d_in, tin);
+    // with cin not a multiple of 8 the s2d channel order is parity * cin8 + ci: build the weights on the padded count
+    featurenet_effective_weights_kernel<<<cdiv(cout * cin_eff * 9, 256), 256, 0, st>>>(w, weff, cout, cin, cin_eff, ksize);
+    int rc = (s2d_in && cin != cin8) ? set_error(MVS_ERR_UNSUPPORTED, "5x5 stride-2 layer needs Cin %% 8 == 0") : MVS_OK;
+    if (rc == MVS_OK)
+        rc = run_layer(TC_CONV2D, xin, weff, shift, relu, nullptr, yout, 0, wpk, 1, cin_eff, cout, N, Hi, Wi, num_sms, st, 1, s2d_out);
+    if (rc == MVS_OK) {
+        const int Co = s2d_out ? 4 * cout : cout, Ho = s2d_out ? Hi / 2 : Hi, Wo = s2d_out ? Wi / 2 : Wi;
+        const long long tout = (long long)N * Ho * Wo * (Co / 8);
+        cp8n_f16_to_nchw_kernel<<<cdiv(tout, 256), 256, 0, st>>>((const uint4 *)yout, y, N, Co, Ho, Wo, tout);
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (rc != MVS_OK) return rc;
+    if (e != cudaSuccess) return set_error(MVS_ERR_CUDA, "tc_conv2d launch failed: %s", cudaGetErrorString(e));
+    count_launches(3);
+    return MVS_OK;
+}
+
 }  // namespace mvs
 
 using namespace mvs;
@@ -1208,4 +1399,30 @@ extern "C" int mvs_tc_plan_describe(int kind, int B, int Cin, int Cout, int D, i
              pl.smem_bytes, L.npad, L.ngroups, L.nacc, L.nops, L.tiles_x, L.tiles_y, L.zsegs, L.zseg_len, L.n_items,
              pl.grid, (double)L.Wt * L.Ht / ((double)L.tiles_x * L.tiles_y * L.MT * 128));
     return MVS_OK;
+}
+
+// ---- FeatureNet on the tensor cores (mvsnet.py:10-30, eval mode) --------------------------------
+extern "C" size_t mvs_featurenet_tc_workspace_bytes(int N, int H, int W) {
+    if (N <= 0 || H <= 0 || W <= 0 || (H % 4) || (W % 4)) return 0;
+    return featurenet_tc_workspace_bytes(N, H, W);
+}
+
+extern "C" int mvs_featurenet_tc_fwd(const float *imgs, const mvs_featurenet_params *params, void *fea_rcp8_f16,
+                                     void *workspace, int N, int H, int W, void *stream) {
+    MVS_REQUIRE(imgs && params && fea_rcp8_f16 && workspace, "null pointer argument");
+    MVS_REQUIRE(N > 0 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0,
+                "FeatureNet needs H, W divisible by 4 (two stride-2 stages), got %dx%d", H, W);
+    for (int i = 0; i < MVS_FEATURENET_LAYERS; ++i)
+        MVS_REQUIRE(params->w[i] && params->shift[i], "featurenet params: layer %d has a null pointer", i);
+    return featurenet_tc(imgs, params, fea_rcp8_f16, workspace, N, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin,
+                                     int Cout, int H, int W, int ksize, int stride, int s2d_out, void *stream) {
+    MVS_REQUIRE(x && w && shift && y, "null pointer argument");
+    MVS_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "bad shape");
+    MVS_REQUIRE((ksize == 3 && stride == 1) || (ksize == 5 && stride == 2), "conv2d: 3x3 stride 1 or 5x5 stride 2 only");
+    MVS_REQUIRE(Cout % 8 == 0 && Cout <= 32, "tensor-core conv2d needs Cout in {8, 16, 24, 32}");
+    MVS_REQUIRE(ksize == 3 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv2d needs even H, W");
+    return tc_conv2d_nchw(x, w, shift, relu, y, N, Cin, Cout, H, W, ksize, s2d_out, (cudaStream_t)stream);
 }

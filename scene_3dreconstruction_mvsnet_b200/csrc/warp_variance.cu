@@ -1113,6 +1113,15 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
     return MVS_OK;
 }
 
+// fp16 RCP8 features of all V views in ([B*V][H][4][W][8], what the tensor-core FeatureNet writes): no layout pass.
+int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
+                           int B, int V, int D, int H, int W, cudaStream_t st) {
+    float *rt = (float *)workspace;
+    if (V > 1)
+        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+}
+
 // fp16 channels-last features of all V views in ([B][V][H*W][32]), bf16 CP8 volume out: no layout pre-pass at all.
 int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                           int B, int V, int D, int H, int W, cudaStream_t st) {

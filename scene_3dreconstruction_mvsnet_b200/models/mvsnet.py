@@ -59,6 +59,22 @@ class FeatureNet(nn.Module):
             self._folded, self._folded_key = out, key
         return self._folded
 
+    def folded_native(self):
+        """[(weight [Cout,Cin,k,k] fp32, shift)] x 8 in layer order with eval-mode BN folded in (the last entry is the
+        plain `feature` conv and its bias): the parameter set of ops.featurenet_tc.  Cached like folded_params()."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if getattr(self, "_native", None) is None or key != self._native_key:
+            with torch.no_grad():
+                out = []
+                for n in self._ORDER:
+                    layer = getattr(self, n)
+                    w, b = fold_bn(layer.conv.weight, layer.bn, out_dim=0)
+                    out.append((w.float().contiguous(), b.float().contiguous()))
+                out.append((self.feature.weight.detach().float().contiguous(), self.feature.bias.detach().float().contiguous()))
+            self._native, self._native_key = out, key
+        return self._native
+
     def infer_half(self, x):
         """fp16 variant of infer() for the tensor-core mode: x fp16 channels-last -> fp16 channels-last features
         (1.34 ms vs 1.64 ms with TF32 at 5 x 1152x1600, same 1e-4 accuracy class), emitted in exactly the texel layout
@@ -155,14 +171,21 @@ class MVSNet(nn.Module):
                         and accumulates Sum / Sum^2 in fp32 (TMA-window kernel, csrc/warp_variance_win.cu);
                         FeatureNet on cuDNN with TF32 allowed (PyTorch's default, i.e. what the reference itself
                         does on a GPU);
-               "fast" - "bf16" with FeatureNet in fp16 as well (its channels-last output feeds the warp kernel's
-                        layout pass directly).
+               "fast" - "bf16" with a cuDNN FeatureNet in fp16 (its channels-last output feeds the warp kernel's
+                        layout pass directly); only differs from "bf16" when featurenet="cudnn".
+    featurenet: "auto" (default) - in the tensor-core modes FeatureNet runs on the same tcgen05 implicit-GEMM
+                        kernel as CostRegNet (fp16 operands, fp32 accumulate, ops.featurenet_tc) and writes the warp
+                        kernel's texel layout directly; "cudnn" keeps it on cuDNN (always the case in "fp32" mode,
+                        in train() mode and under autograd).
     """
 
-    def __init__(self, refine=True, debug=0, precision="fp32"):
+    def __init__(self, refine=True, debug=0, precision="fp32", featurenet="auto"):
         super().__init__()
         if precision not in ("fp32", "bf16", "fast"):
             raise ValueError("precision must be 'fp32', 'bf16' or 'fast', got %r" % (precision,))
+        if featurenet not in ("auto", "tc", "cudnn"):
+            raise ValueError("featurenet must be 'auto', 'tc' or 'cudnn', got %r" % (featurenet,))
+        self.featurenet = featurenet
         self.refine = refine
         self.debug = debug
         self.precision = precision
@@ -223,8 +246,13 @@ class MVSNet(nn.Module):
                 marks.append((name, e))
 
         mark("start")
-        fast = (not torch.is_grad_enabled()) and (not self.training) and self.precision == "fast"
-        fea = self.extract_features_half(imgs) if fast else self.extract_features(imgs)
+        infer = (not torch.is_grad_enabled()) and (not self.training)
+        if infer and self.precision in ("bf16", "fast") and self.featurenet != "cudnn":
+            fea = ops.featurenet_tc(imgs.float(), self.feature.folded_native())
+        elif infer and self.precision == "fast":
+            fea = self.extract_features_half(imgs)
+        else:
+            fea = self.extract_features(imgs)
         mark("features")
         proj_matrices = proj_matrices.float()
         depth_values = depth_values.float()

@@ -251,25 +251,93 @@ def _costreg_params(folded):
     return params, keep
 
 
+class Rcp8Features:
+    """fp16 features of all views in the row-chunk-planar layout [B*V][h][4][w][8] written by the tensor-core
+    FeatureNet (ops.featurenet_tc) and sampled by the fused warp kernel's TMA windows."""
+
+    def __init__(self, data, B, V, h, w):
+        self.data, self.B, self.V, self.h, self.w = data, B, V, h, w
+        self.device = data.device
+
+    def to_nchw(self):
+        """[B,V,32,h,w] fp32 (tests / diagnostics)."""
+        t = self.data.view(self.B, self.V, self.h, 4, self.w, 8).permute(0, 1, 3, 5, 2, 4)
+        return t.reshape(self.B, self.V, 32, self.h, self.w).float()
+
+
+def conv2d_bn_relu_tc(x, w_folded, shift, relu=True, stride=1, s2d_out=False):
+    """One ConvBnReLU (reference models/module.py:8-15) with folded BN on the tensor-core kernel, fp16 operands.
+    3x3 stride 1 or 5x5 stride 2; fp32 NCHW in / out (s2d_out: the space-to-depth form [N,4*Cout,H/2,W/2])."""
+    x = _prep(x, "x", 4)
+    w_folded = _prep(w_folded, "weight", 4)
+    shift = _prep(shift, "shift", 1)
+    N, Cin, H, W = x.shape
+    Cout, k = w_folded.shape[0], w_folded.shape[2]
+    if w_folded.shape != (Cout, Cin, k, k) or shift.shape[0] != Cout:
+        raise RuntimeError("conv2d: weight %s / shift %s do not match input %s" % (tuple(w_folded.shape),
+                                                                                   tuple(shift.shape), tuple(x.shape)))
+    Ho, Wo = (H // stride, W // stride)
+    shape = (N, 4 * Cout, Ho // 2, Wo // 2) if s2d_out else (N, Cout, Ho, Wo)
+    y = torch.empty(shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mvs_conv2d_bn_relu_tc(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(y), N, Cin, Cout, H, W,
+                                               k, stride, int(s2d_out), _stream(x))
+    _lib.check(rc, "mvs_conv2d_bn_relu_tc")
+    return y
+
+
+def featurenet_tc(imgs, folded):
+    """FeatureNet.forward (reference models/mvsnet.py:10-30, eval mode) on the tensor cores.
+    imgs [B,V,3,H,W] fp32; folded = 8 (weight, shift) CUDA tensors in layer order (native shapes, BN folded)
+    -> Rcp8Features (fp16 [B*V][H/4][4][W/4][8])."""
+    imgs = _prep(imgs, "imgs", 5)
+    B, V, C, H, W = imgs.shape
+    if C != 3:
+        raise RuntimeError("FeatureNet expects 3-channel images, got %d" % C)
+    lib = _lib.load()
+    nbytes = lib.mvs_featurenet_tc_workspace_bytes(B * V, H, W)
+    if nbytes == 0:
+        raise RuntimeError("FeatureNet needs H, W divisible by 4 (got %dx%d)" % (H, W))
+    params = _lib.FeatureNetParams()
+    keep = []
+    for i, (w, s) in enumerate(folded):
+        w = _prep(w, "featurenet weight %d" % i)
+        s = _prep(s, "featurenet shift %d" % i, 1)
+        keep += [w, s]
+        params.w[i] = w.data_ptr()
+        params.shift[i] = s.data_ptr()
+    ws = _ws(nbytes, imgs.device, "featurenet")
+    out = torch.empty((B * V, H // 4, 4, W // 4, 8), dtype=torch.float16, device=imgs.device)
+    with torch.cuda.device(imgs.device):
+        rc = lib.mvs_featurenet_tc_fwd(_ptr(imgs), ctypes.byref(params), _ptr(out), _ptr(ws), B * V, H, W, _stream(imgs))
+    _lib.check(rc, "mvs_featurenet_tc_fwd")
+    return Rcp8Features(out, B, V, H // 4, W // 4)
+
+
 def warp_variance_cp8(fea, proj, depth_values):
     """Fused warp+variance with the bf16 chunk-planar output: returns a bf16 tensor [B, 4, D, h, w, 8]
     (channel = chunk*8 + last index).  fea: fp32 [B,V,32,h,w] (exact fp32 arithmetic) or fp16 channels-last
     [B,V,h,w,32] (fp16 texels).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
-    half_nhwc = fea.dtype == torch.float16
-    if half_nhwc:
+    lib = _lib.load()
+    rcp8 = isinstance(fea, Rcp8Features)
+    half_nhwc = (not rcp8) and fea.dtype == torch.float16
+    if rcp8:
+        B, V, H, W, C = fea.B, fea.V, fea.h, fea.w, 32
+        fn, fea = lib.mvs_warp_variance_fwd_cp8_feat, fea.data
+    elif half_nhwc:
         fea = fea.detach().contiguous()
         B, V, H, W, C = fea.shape
+        fn = lib.mvs_warp_variance_fwd_cp8_f16
     else:
         fea = _prep(fea, "features", 5)
         B, V, C, H, W = fea.shape
+        fn = lib.mvs_warp_variance_fwd_cp8
     proj = _prep(proj, "proj_matrices", 4)
     depth_values = _prep(depth_values, "depth_values", 2)
     D = depth_values.shape[1]
-    lib = _lib.load()
     vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.bfloat16, device=fea.device)
     ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
     with torch.cuda.device(fea.device):
-        fn = lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8
         rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
     _lib.check(rc, "mvs_warp_variance_fwd_cp8")
     return vol
@@ -279,8 +347,13 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
     """bf16 precision mode: fused warp+variance writing the bf16 CP8 volume, then the tcgen05 CostRegNet.
     fea: fp32 [B,V,32,h,w], or fp16 channels-last [B,V,h,w,32] (then no layout pre-pass runs) -> logits
     [B,D,h,w] (fp32).  `marks`, if a callable, is invoked between the two kernel families (stage timing)."""
+    lib = _lib.load()
+    rcp8 = isinstance(fea, Rcp8Features)
     half_nhwc = isinstance(fea, torch.Tensor) and fea.dtype == torch.float16
-    if half_nhwc:
+    if rcp8:
+        B, V, H, W, C = fea.B, fea.V, fea.h, fea.w, 32
+        fea = fea.data
+    elif half_nhwc:
         if not fea.is_cuda or fea.dim() != 5 or fea.shape[-1] != 32 or not fea.is_contiguous():
             raise RuntimeError("fp16 features must be a contiguous CUDA tensor [B,V,h,w,32], got %s" % (tuple(fea.shape),))
         fea = fea.detach()
@@ -294,7 +367,6 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
     if proj.shape != (B, V, 4, 4):
         raise RuntimeError("Different number of images and projection matrices: features %s proj %s"
                            % (tuple(fea.shape), tuple(proj.shape)))
-    lib = _lib.load()
     params, keep = _costreg_params(folded)
     nbytes = lib.mvs_costreg_workspace_bytes(B, D, H, W, _lib.PRECISION_BF16)
     if nbytes == 0:
@@ -304,7 +376,8 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
     ws2 = _ws(nbytes, fea.device, "costreg")
     logits = torch.empty((B, D, H, W), dtype=torch.float32, device=fea.device)
     with torch.cuda.device(fea.device):
-        fn = lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8
+        fn = lib.mvs_warp_variance_fwd_cp8_feat if rcp8 else (
+            lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8)
         rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
         _lib.check(rc, "mvs_warp_variance_fwd_cp8")
         if marks is not None:

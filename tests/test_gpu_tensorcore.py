@@ -166,3 +166,66 @@ def test_tc_costreg_and_depth_golden(case, precision, request, weights):
         out = m(cu(c["imgs"]), cu(c["proj"]), cu(c["dv"]))
     rng = float(c["dv"].max() - c["dv"].min())
     assert maxabs(out["depth"], c["depth"]) < 5e-3 * rng
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureNet on the tensor-core kernel (fp16 operands, fp32 accumulate).  Floating-point kernel: the reference is
+# torch's fp32 conv2d on the same fp16-rounded inputs and weights; tolerance = fp16 rounding of the stored output
+# (2^-11 relative) plus accumulation order: |y - ref| <= 2^-10 |ref| + 2e-3.
+# ------------------------------------------------------------------------------------------------
+def f16_round(t):
+    return t.half().float()
+
+
+def check16(y, ref, what):
+    err = (y.cpu().double() - ref.double()).abs()
+    tol = ref.double().abs() * 2.0 ** -10 + 2e-3
+    assert bool((err <= tol).all()), "%s: max err %.4g (ref absmax %.4g)" % (what, err.max().item(), ref.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,N", [(3, 8, 3, (20, 44), 2), (8, 8, 3, (37, 130), 1), (16, 16, 3, (24, 40), 3),
+                                             (32, 32, 3, (9, 13), 2), (8, 16, 5, (24, 52), 2), (16, 32, 5, (20, 36), 1),
+                                             (8, 16, 5, (6, 260), 1)])
+def test_tc_conv2d(cin, cout, k, hw, N):
+    g = torch.Generator().manual_seed(cin * 31 + cout + hw[1])
+    x = f16_round(torch.randn(N, cin, *hw, generator=g))
+    w = f16_round(torch.randn(cout, cin, k, k, generator=g) * (1.0 / (k * k * cin) ** 0.5))
+    shift = torch.randn(cout, generator=g) * 0.3
+    stride = 2 if k == 5 else 1
+    y = ops.conv2d_bn_relu_tc(x.to(DEV), w.to(DEV), shift.to(DEV), relu=True, stride=stride)
+    ref = torch.relu(torch.nn.functional.conv2d(x, w, shift, stride=stride, padding=k // 2))
+    assert tuple(y.shape) == tuple(ref.shape)
+    check16(y, ref, "conv2d %d->%d k%d %s" % (cin, cout, k, hw))
+
+
+def test_tc_conv2d_space_to_depth_output():
+    """A layer that feeds a stride-2 layer writes [N, 4*C, H/2, W/2] with channel = ((y&1)*2 + (x&1))*C + c."""
+    g = torch.Generator().manual_seed(5)
+    x = f16_round(torch.randn(2, 8, 12, 40, generator=g))
+    w = f16_round(torch.randn(8, 8, 3, 3, generator=g) * 0.1)
+    shift = torch.randn(8, generator=g) * 0.3
+    y = ops.conv2d_bn_relu_tc(x.to(DEV), w.to(DEV), shift.to(DEV), relu=True, s2d_out=True)
+    ref = torch.relu(torch.nn.functional.conv2d(x, w, shift, padding=1))
+    ref = torch.stack([ref[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], 1).reshape(2, 32, 6, 20)
+    check16(y, ref, "s2d output")
+
+
+@pytest.mark.parametrize("B,V,H,W", [(1, 3, 64, 96), (2, 2, 32, 160)])
+def test_featurenet_tc_matches_torch(B, V, H, W, weights):
+    """Whole FeatureNet (8 layers, fp16 activations) against the nn.Module in fp32 on the BN-calibrated checkpoint:
+    features are O(1); 8 layers of fp16 storage give ~1e-3 absolute."""
+    from test_gpu_parity import load_model
+    m = load_model(weights, precision="bf16")
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.rand(B, V, 3, H, W, generator=g).to(DEV)
+    with torch.no_grad():
+        fea = ops.featurenet_tc(imgs, m.feature.folded_native())
+        ref = m.extract_features(imgs)                        # cuDNN, TF32 allowed in this mode
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref32 = torch.stack([m.feature(img) for img in torch.unbind(imgs, 1)], 1)
+    got = fea.to_nchw()
+    scale = ref32.abs().max().item()
+    assert (got - ref32).abs().max().item() < 4e-3 * max(scale, 1.0), "max err %.4g, feature absmax %.4g" % (
+        (got - ref32).abs().max().item(), scale)
+    # and it is at least as close to the fp32 result as the TF32 cuDNN path of the same mode is, within a factor
+    assert (got - ref32).abs().mean().item() < 5 * (ref - ref32).abs().mean().item() + 1e-4

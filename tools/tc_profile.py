@@ -6,15 +6,17 @@ from scene_3dreconstruction_mvsnet_b200 import ops, _lib
 lib = _lib.load()
 D, H, W = 192, 288, 400
 layers = [("conv0", 0, 32, 8, D, H, W), ("conv2", 0, 16, 16, D // 2, H // 2, W // 2), ("conv11", 2, 16, 8, D // 2, H // 2, W // 2),
-          ("prob", 0, 8, 1, D, H, W), ("conv1", 1, 8, 16, D, H, W)]
+          ("prob", 0, 8, 1, D, H, W), ("conv1", 1, 8, 16, D, H, W), ("conv9", 2, 32, 16, D // 4, H // 4, W // 4),
+          ("conv3", 1, 16, 32, D // 2, H // 2, W // 2), ("conv4", 0, 32, 32, D // 4, H // 4, W // 4)]
 for name, kind, ci, co, d, h, w in layers:
     x = torch.randn(1, ci, d, h, w, device="cuda")
     wt = torch.randn((ci, co, 3, 3, 3) if kind == 2 else (co, ci, 3, 3, 3), device="cuda") * 0.05
     sh = torch.zeros(co, device="cuda")
     dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    skip = torch.randn(1, co, 2 * d, 2 * h, 2 * w, device="cuda") if kind == 2 and "noskip" not in sys.argv else None
     def run():
         if kind == 2:
-            return ops.conv_transpose3d_bn_relu(x, wt, sh, tensor_cores=True)
+            return ops.conv_transpose3d_bn_relu(x, wt, sh, skip=skip, tensor_cores=True)
         return ops.conv3d_bn_relu(x, wt, sh, relu=co != 1, stride=2 if kind == 1 else 1, tensor_cores=True)
     run(); torch.cuda.synchronize()
     lib.mvs_tc_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
