@@ -102,7 +102,7 @@ int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, const float 
 
 /* Diagnostics (no GPU needed): describes the tile/ring/grid plan of one tensor-core layer.
  * kind: 0 = conv stride 1, 1 = conv stride 2, 2 = transposed conv. */
-int mvs_tc_set_debug_buffer(void *device_buf_or_null); /* [grid][8] int64 cycle counters of the next tc launches */
+int mvs_tc_set_debug_buffer(void *device_buf_or_null); /* [grid][12] int64 cycle counters of the next tc launches */
 int mvs_tc_plan_describe(int kind, int B, int Cin, int Cout, int D, int H, int W, int num_sms, char *buf, int buflen);
 
 /* Whole CostRegNet.forward (mvsnet.py:64-73), eval mode.  Layer order in the arrays:

@@ -86,7 +86,7 @@ struct TcLayer {
     const uint4 *skip;
     const float *shift;
     const uint4 *wpacked;
-    long long *dbg;  // optional [gridDim.x][8] cycle counters (tools/tc_profile.py); nullptr in production
+    long long *dbg;  // optional [gridDim.x][12] cycle counters (tools/tc_profile.py); nullptr in production
     int f16;         // 1: fp16 operands / fp16 outputs (FeatureNet); 0: bf16
     int out_mode;    // 0: CP8 [C/8][D][H][W][8]; 1: space-to-depth [4 parities x C/8][D][H/2][W/2][8];
                      // 2: row-chunk-planar "RCP8" [D][H][C/8][W][8] (what the fused warp kernel's TMA windows read)
@@ -235,7 +235,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     }
                 }
             }
-            if (L.dbg) L.dbg[blockIdx.x * 8 + 0] = prod_wait;
+            if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -246,7 +246,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         uint32_t st = 0;
         uint32_t s0 = 0;    // ring slot of the oldest plane of the current step
         uint32_t par = 0;   // bit s: parity of the fill of slot s that is current (toggles when the slot is released)
-        long long w_full = 0, w_tempty = 0, t_issue = 0;
+        long long w_full = 0, w_tempty = 0, t_issue = 0, t_release = 0;
         const long long t_start = clock64();
         const uint32_t nslot = L.nslot, need = L.need, adv = L.adv;
         auto wrap = [&](uint32_t s) { return s >= nslot ? s - nslot : s; };
@@ -283,6 +283,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     t_issue += clock64() - ci;
                 }
                 // release the planes this step was the last user of (all of them at the end of an item)
+                const long long cr = clock64();
                 const uint32_t nrel = (t == T - 1) ? need : adv;
                 for (uint32_t r = 0; r < nrel; ++r) {
                     const uint32_t sl = wrap(s0 + r);
@@ -292,14 +293,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 if (leader) ptx::tcgen05_commit(tfull_bar(buf));
                 s0 = wrap(s0 + nrel);
                 __syncwarp();
+                t_release += clock64() - cr;
             }
         }
         if (leader && L.dbg) {
-            L.dbg[blockIdx.x * 8 + 1] = w_full;
-            L.dbg[blockIdx.x * 8 + 2] = w_tempty;
-            L.dbg[blockIdx.x * 8 + 3] = t_issue;
-            L.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
-            L.dbg[blockIdx.x * 8 + 5] = st;
+            L.dbg[blockIdx.x * 12 + 1] = w_full;
+            L.dbg[blockIdx.x * 12 + 2] = w_tempty;
+            L.dbg[blockIdx.x * 12 + 3] = t_issue;
+            L.dbg[blockIdx.x * 12 + 4] = clock64() - t_start;
+            L.dbg[blockIdx.x * 12 + 5] = st;
+            L.dbg[blockIdx.x * 12 + 8] = t_release;
         }
     } else {
         // ================= epilogue (4 warps = 128 TMEM lanes) =================
@@ -483,8 +486,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
         }
         if (warp == 2 && lane == 0 && L.dbg) {
-            L.dbg[blockIdx.x * 8 + 6] = epi_wait;
-            L.dbg[blockIdx.x * 8 + 7] = epi_work;
+            L.dbg[blockIdx.x * 12 + 6] = epi_wait;
+            L.dbg[blockIdx.x * 12 + 7] = epi_work;
         }
     }
 
@@ -625,7 +628,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                                      b * L.chunks);
                 }
             }
-            if (L.dbg) L.dbg[blockIdx.x * 8 + 0] = prod_wait;
+            if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -686,11 +689,11 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             }
         }
         if (leader && L.dbg) {
-            L.dbg[blockIdx.x * 8 + 1] = w_full;
-            L.dbg[blockIdx.x * 8 + 2] = w_tempty;
-            L.dbg[blockIdx.x * 8 + 3] = t_issue;
-            L.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
-            L.dbg[blockIdx.x * 8 + 5] = g;
+            L.dbg[blockIdx.x * 12 + 1] = w_full;
+            L.dbg[blockIdx.x * 12 + 2] = w_tempty;
+            L.dbg[blockIdx.x * 12 + 3] = t_issue;
+            L.dbg[blockIdx.x * 12 + 4] = clock64() - t_start;
+            L.dbg[blockIdx.x * 12 + 5] = g;
         }
     } else {
         // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating over the M-tiles =================
@@ -775,8 +778,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             blk = (blk + 2) % R;  // the two lead-in blocks of the next item are never drained
         }
         if (warp == 2 && lane == 0 && L.dbg) {
-            L.dbg[blockIdx.x * 8 + 6] = epi_wait;
-            L.dbg[blockIdx.x * 8 + 7] = epi_work;
+            L.dbg[blockIdx.x * 12 + 6] = epi_wait;
+            L.dbg[blockIdx.x * 12 + 7] = epi_work;
         }
     }
 
@@ -1445,7 +1448,7 @@ extern "C" int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, c
     return tc_layer_ncdhw(TC_CONVT, x, w, shift, relu, skip, y, B, Cin, Cout, D, H, W, (cudaStream_t)stream);
 }
 
-// Diagnostics: device buffer of [grid][8] int64 cycle counters filled by the next tensor-core layer launches
+// Diagnostics: device buffer of [grid][12] int64 cycle counters filled by the next tensor-core layer launches
 // (producer wait, MMA wait-full / wait-tmem / issue / total / steps, epilogue wait / work).  nullptr disables.
 extern "C" int mvs_tc_set_debug_buffer(void *buf) {
     g_tc_dbg = (long long *)buf;

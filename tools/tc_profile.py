@@ -12,7 +12,7 @@ for name, kind, ci, co, d, h, w in layers:
     x = torch.randn(1, ci, d, h, w, device="cuda")
     wt = torch.randn((ci, co, 3, 3, 3) if kind == 2 else (co, ci, 3, 3, 3), device="cuda") * 0.05
     sh = torch.zeros(co, device="cuda")
-    dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(148 * 12, dtype=torch.int64, device="cuda")
     skip = torch.randn(1, co, 2 * d, 2 * h, 2 * w, device="cuda") if kind == 2 and "noskip" not in sys.argv else None
     def run():
         if kind == 2:
@@ -22,9 +22,9 @@ for name, kind, ci, co, d, h, w in layers:
     lib.mvs_tc_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
     run(); torch.cuda.synchronize()
     lib.mvs_tc_set_debug_buffer(None)
-    t = dbg.view(148, 8).double()
+    t = dbg.view(148, 12).double()
     t = t[t[:, 5] > 0]
     steps = t[:, 5].mean().item()
     m = t.mean(0) / steps
-    print("%-7s steps/CTA %6.1f | per step cycles: total %7.0f  mma: wait_full %6.0f wait_tmem %6.0f issue %6.0f | epi: wait %6.0f work %6.0f | producer wait_empty %6.0f"
-          % (name, steps, m[4], m[1], m[2], m[3], m[6], m[7], m[0]))
+    print("%-7s steps/CTA %6.1f | per step cycles: total %7.0f  mma: wait_full %6.0f wait_tmem %6.0f issue %6.0f | epi: wait %6.0f work %6.0f | producer wait_empty %6.0f | release %5.0f"
+          % (name, steps, m[4], m[1], m[2], m[3], m[6], m[7], m[0], m[8]))
