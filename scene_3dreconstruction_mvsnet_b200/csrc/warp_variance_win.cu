@@ -85,6 +85,27 @@ __device__ __forceinline__ void accumulate_chunk(const uint4 a, const uint4 b, c
     }
 }
 
+// Deviation form (HACC): the variance is shift invariant, so the running sums are kept over d = x_v - x_ref (zero for
+// the reference view itself) instead of x_v.  The subtraction is free -- the interpolation chain starts from -x_ref --
+// and the deviations are small exactly where the cost volume matters (matching pixels), so Sum d and Sum d^2 can stay
+// in packed half: 24 heavy-pipe instructions per 8 channels instead of 32 and one conversion per plane instead of one
+// per view.  Relative error of the sums 2^-11, the same class as the fp16 interpolation itself; |d| must stay below
+// 255 / sqrt(V-1) for d^2 not to overflow fp16 (features are O(1)).
+__device__ __forceinline__ void accumulate_chunk_dev(const uint4 a, const uint4 b, const uint4 c, const uint4 d, const __half2 h00,
+                                                     const __half2 h01, const __half2 h10, const __half2 h11,
+                                                     const uint4 nref, __half2 *S, __half2 *Q) {
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t wc[4] = {c.x, c.y, c.z, c.w}, wd[4] = {d.x, d.y, d.z, d.w};
+    const uint32_t wr[4] = {nref.x, nref.y, nref.z, nref.w};  // -x_ref
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half2 dv = __hfma2(as_half2(wd[j]), h11,
+                                   __hfma2(as_half2(wc[j]), h10, __hfma2(as_half2(wb[j]), h01, __hfma2(as_half2(wa[j]), h00, as_half2(wr[j])))));
+        S[j] = __hadd2(S[j], dv);
+        Q[j] = __hfma2(dv, dv, Q[j]);
+    }
+}
+
 // fp32 NCHW [B,V,32,HW] -> fp16 RCP8 [B*V][H][4][W][8]; one thread per output 16-byte chunk
 __global__ void nchw_to_rcp8_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int H, int W, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +145,7 @@ __global__ void nhwc16_to_rcp8_kernel(const uint4 *__restrict__ in, uint4 *__res
 // grid = (ceil(W / TW), ceil(H / TH), B * ceil(D / dchunk)), block = 32 * TWW * TH threads (warp = 32 consecutive x of a row)
 // dynamic smem: nwin windows of WY rows x [4 chunks][WX cols] x 16 B | homographies | window origins | depths | mbarrier
 // ------------------------------------------------------------------------------------------------
-template <int TWW, int TH, int WX>
+template <int TWW, int TH, int WX, bool HACC>
 __global__ void __launch_bounds__(32 * TWW * TH, (TWW * TH <= 8) ? 2 : 1)
 warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 RCP8 features, all views
                          const uint4 *__restrict__ tex,                  // the same memory
@@ -255,16 +276,24 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
 
         for (int d = ds; d < ds + L; ++d) {
             const float dep = s_dep[d - d_begin];
-            float2 S[16], Q[16];
+            float2 S[HACC ? 1 : 16], Q[HACC ? 1 : 16];
+            __half2 Sh[HACC ? 16 : 1], Qh[HACC ? 16 : 1];
+            uint4 nref[HACC ? 4 : 1];  // -x_ref, the start value of every interpolation chain
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const uint4 rv = __ldg(ref_px + (size_t)c * W);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                if constexpr (HACC) {
+                    nref[c] = make_uint4(rv.x ^ 0x80008000u, rv.y ^ 0x80008000u, rv.z ^ 0x80008000u, rv.w ^ 0x80008000u);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 f = __half22float2(as_half2(rw[j]));
-                    S[4 * c + j] = f;
-                    Q[4 * c + j] = __fmul2_rn(f, f);
+                    for (int j = 0; j < 4; ++j) Sh[4 * c + j] = Qh[4 * c + j] = __float2half2_rn(0.f);
+                } else {
+                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(as_half2(rw[j]));
+                        S[4 * c + j] = f;
+                        Q[4 * c + j] = __fmul2_rn(f, f);
+                    }
                 }
             }
             for (int v = 0; v < nsrc; ++v) {
@@ -294,7 +323,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint4 ta = wp[c * WX], tb = wp[c * WX + 1], tc = wp[ROWQ + c * WX], td = wp[ROWQ + c * WX + 1];
-                        accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
+                        if constexpr (HACC) accumulate_chunk_dev(ta, tb, tc, td, h00, h01, h10, h11, nref[c], Sh + 4 * c, Qh + 4 * c);
+                        else accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
                     }
                 } else {
                     // per-tap global gather with explicit zero padding (footprint too large for a window)
@@ -310,7 +340,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                     for (int c = 0; c < 4; ++c) {
                         const uint4 ta = __ldg(r0 + c * W + cx0), tb = __ldg(r0 + c * W + cx1);
                         const uint4 tc = __ldg(r1 + c * W + cx0), td = __ldg(r1 + c * W + cx1);
-                        accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
+                        if constexpr (HACC) accumulate_chunk_dev(ta, tb, tc, td, h00, h01, h10, h11, nref[c], Sh + 4 * c, Qh + 4 * c);
+                        else accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
                     }
                 }
             }
@@ -321,8 +352,10 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         // Q/V - (S/V)^2   (mvsnet.py:177), packed fp32x2
-                        const float2 m = __fmul2_rn(S[4 * c + j], invV2);
-                        const float2 r = __ffma2_rn(Q[4 * c + j], invV2, __fmul2_rn(m, make_float2(-m.x, -m.y)));
+                        const float2 sv = HACC ? __half22float2(Sh[HACC ? 4 * c + j : 0]) : S[HACC ? 0 : 4 * c + j];
+                        const float2 qv = HACC ? __half22float2(Qh[HACC ? 4 * c + j : 0]) : Q[HACC ? 0 : 4 * c + j];
+                        const float2 m = __fmul2_rn(sv, invV2);
+                        const float2 r = __ffma2_rn(qv, invV2, __fmul2_rn(m, make_float2(-m.x, -m.y)));
                         const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
                         pk[j] = *reinterpret_cast<const uint32_t *>(&o);
                     }
@@ -377,14 +410,14 @@ int encode_window_map(CUtensorMap *tmap, const void *tex, int N, int H, int W, i
     return MVS_OK;
 }
 
-template <int TWW, int TH, int WX>
+template <int TWW, int TH, int WX, bool HACC>
 int launch_win(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D, int H,
                int W, int dchunk, int smem_budget, cudaStream_t st) {
     const int nsrc = V - 1;
     const WinPlan p = plan_windows(nsrc, TH, WX, dchunk, smem_budget);
     CUtensorMap tmap;
     if (int rc = encode_window_map(&tmap, tex16, B * V, H, W, WX, p.wy)) return rc;
-    auto kern = warp_variance_win_kernel<TWW, TH, WX>;
+    auto kern = warp_variance_win_kernel<TWW, TH, WX, HACC>;
     static thread_local int configured_dev = -1;
     int dev = 0;
     MVS_CUDA(cudaGetDevice(&dev));
@@ -412,8 +445,12 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
     if (const char *e = getenv("MVS_WARP_DCHUNK")) dchunk = std::max(1, std::min(32, atoi(e)));
     while ((long long)B * cdiv(D, dchunk) > 65535 && dchunk < 32) dchunk <<= 1;
     MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
-    if (cfg == 1) return launch_win<2, 8, 80>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 227 * 1024, st);
-    return launch_win<1, 8, 40>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
+    // MVS_WIN_ACC32=1: running sums of the warped values themselves in fp32 (the first formulation) instead of packed-half
+    // sums of deviations from the reference view
+    static const bool acc32 = getenv("MVS_WIN_ACC32") != nullptr;
+    if (cfg == 1) return launch_win<2, 8, 80, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 227 * 1024, st);
+    if (acc32) return launch_win<1, 8, 40, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
+    return launch_win<1, 8, 40, true>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
 }
 
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st) {
