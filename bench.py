@@ -234,6 +234,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps / (float(t.item()) * 1e-3)
 
+    # same call with the images as 8-bit host buffers (as decoded from disk): /255 runs on the device, the upload is
+    # 4x smaller.  Reported next to `e2e` (which keeps the reference loader's float32 images), not instead of it.
+    u8_imgs = (imgs * 255.0).round().to(torch.uint8).pin_memory()
+    runner.run_views([(u8_imgs, p_proj, p_dv)] * max(2, args.warmup), sink)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    runner.run_views([(u8_imgs, p_proj, p_dv)] * args.steps, sink)
+    e1.record()
+    barrier()
+    t = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * args.steps / (float(t.item()) * 1e-3)
+    e2e_u8_h2d = runner.h2d_bytes_per_view
+    runner.run_views([(p_imgs, p_proj, p_dv)], sink)  # back to the float32 slots (h2d_bytes_per_view below refers to them)
+
     if rank == 0:
         hbm_peak, tf_peak, peak_kind = measured_peaks()
         wv_ms = stage_ms.get("warp_variance")
@@ -249,20 +266,24 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": {"fp32": "f32",
-                      "bf16": "bf16 operands / f32 accumulate in CostRegNet (tcgen05); fp16 texels + packed-half tap interpolation, f32 sums in the fused warp kernel; FeatureNet cuDNN TF32",
+                      "bf16": "bf16 operands / f32 accumulate in CostRegNet, fp16 operands / f32 accumulate in FeatureNet (both tcgen05); fp16 texels + packed-half tap interpolation and deviation sums in the fused warp kernel",
                       "fast": "as bf16, FeatureNet in fp16 as well"}[args.precision],
             "data": "synthetic",
             "config": {"workload": args.workload, "views": V, "image": [H, W], "depth_planes": D, "batch": 1,
                        "feature_map": [h, w], "weights": "random-init (seed 1), eval mode",
                        "precision": args.precision,
-                       "featurenet": "cuDNN NHWC fused conv+bias+relu, " + {"fp32": "fp32 (TF32 off)", "bf16": "TF32 allowed (PyTorch default)",
-                                                                           "fast": "fp16"}[args.precision],
+                       "featurenet": {"fp32": "cuDNN NHWC fused conv+bias+relu, fp32 (TF32 off)",
+                                      "bf16": "tcgen05 implicit GEMM, fp16 operands / f32 accumulate (ops.featurenet_tc)",
+                                      "fast": "tcgen05 implicit GEMM, fp16 operands / f32 accumulate (ops.featurenet_tc)"}[args.precision],
                        "l2": "per-step working set (1.4-2.8 GB cost volume) >> 126 MB L2; no flush needed",
                        "sharding": "one reference view stream per rank, no collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes_per_view,
                     "d2h_bytes_per_step": runner.d2h_bytes_per_view, "api": "DepthMapRunner.run_views (pinned host "
                     "inputs -> H2D -> MVSNet.forward -> D2H depth+confidence, double-buffered)"},
+            "e2e_uint8_images": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": e2e_u8_h2d,
+                                 "d2h_bytes_per_step": runner.d2h_bytes_per_view,
+                                 "note": "same API, images as uint8 host buffers; /255 on the device (reference: on the host)"},
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": {"kernel": ("warp_variance_fwd2_kernel" if args.precision == "fp32" else "warp_variance_win_kernel") +

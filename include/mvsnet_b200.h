@@ -100,6 +100,11 @@ int mvs_conv3d_bn_relu_tc(const float *x, const float *w, const float *shift, in
 int mvs_conv_transpose3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, const float *skip,
                                     float *y, int B, int Cin, int Cout, int D, int H, int W, void *stream);
 
+/* The tensor-core layers pack their weights (fp32 -> 16-bit MMA operand blocks) once per weight POINTER and layer
+ * configuration and reuse the packed copy in later calls.  Call this after changing weights in place or freeing and
+ * re-creating them (nn.Module.load_state_dict, an optimizer step, re-folding BatchNorm). */
+int mvs_weight_cache_clear(void);
+
 /* Diagnostics (no GPU needed): describes the tile/ring/grid plan of one tensor-core layer.
  * kind: 0 = conv stride 1, 1 = conv stride 2, 2 = transposed conv. */
 int mvs_tc_set_debug_buffer(void *device_buf_or_null); /* [grid][12] int64 cycle counters of the next tc launches */
@@ -145,6 +150,10 @@ typedef struct {
 size_t mvs_featurenet_tc_workspace_bytes(int N, int H, int W);
 int mvs_featurenet_tc_fwd(const float *imgs, const mvs_featurenet_params *params, void *fea_rcp8_f16, void *workspace,
                           int N, int H, int W, void *stream);
+/* Same, images as 8-bit [N,3,H,W] (as decoded from disk): value/255 in fp32 -- what the reference's loader computes on
+ * the host (datasets/data_io.py) -- happens on the device after a 4x smaller host->device copy. */
+int mvs_featurenet_tc_fwd_u8(const uint8_t *imgs_u8, const mvs_featurenet_params *params, void *fea_rcp8_f16,
+                             void *workspace, int N, int H, int W, void *stream);
 /* One ConvBnReLU (models/module.py:8-15) on the same kernel, fp32 NCHW in/out (tests, diagnostics):
  * ksize 3 / stride 1 / pad 1, or ksize 5 / stride 2 / pad 2.  s2d_out = 1 returns the space-to-depth form
  * [N, 4*Cout, H'/2, W'/2] (channel = (y&1)*2+(x&1) major) that a following stride-2 layer consumes. */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mvs_conv3d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
     "mvs_conv_transpose3d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p, _c_float_p] + [_i] * 6 +
                                         [ctypes.c_void_p]),
+    "mvs_weight_cache_clear": (_i, []),
     "mvs_tc_set_debug_buffer": (_i, [ctypes.c_void_p]),
     "mvs_tc_plan_describe": (_i, [_i] * 8 + [ctypes.c_char_p, _i]),
     "mvs_costreg_workspace_bytes": (ctypes.c_size_t, [_i] * 5),
@@ -58,6 +59,8 @@ SIGNATURES = {
     "mvs_featurenet_tc_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "mvs_featurenet_tc_fwd": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
                               [ctypes.c_void_p]),
+    "mvs_featurenet_tc_fwd_u8": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
+                                 [ctypes.c_void_p]),
     "mvs_conv2d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 8 + [ctypes.c_void_p]),
     "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
                             [ctypes.c_void_p]),

@@ -228,5 +228,7 @@ extern "C" int mvs_depth_from_features_host(const float *fea_host, const float *
     MVS_CUDA(cudaMemcpyAsync(depth_host, depth.p, (size_t)B * HW * 4, cudaMemcpyDeviceToHost, st));
     MVS_CUDA(cudaMemcpyAsync(conf_host, conf.p, (size_t)B * HW * 4, cudaMemcpyDeviceToHost, st));
     MVS_CUDA(cudaStreamSynchronize(st));
+    // the weights lived in device memory owned by this call: packed copies keyed by those pointers must not outlive it
+    if (precision == MVS_PRECISION_BF16) mvs_weight_cache_clear();
     return MVS_OK;
 }

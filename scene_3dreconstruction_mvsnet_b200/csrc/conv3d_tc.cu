@@ -23,6 +23,7 @@
 // loaded exactly once into a ring of NSLOT planes and reused by the 3 (or 2) z-steps that need it.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-9 = epilogue.
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <string.h>
 #include <vector>
@@ -1146,9 +1147,69 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
 
 static long long *g_tc_dbg = nullptr;  // set by mvs_tc_set_debug_buffer (diagnostics only)
 
+// ------------------------------------------------------------------------------------------------
+// Packed-weight cache.  Packing (fp32 -> bf16/fp16 B-operand blocks in op order) depends only on the weights and the
+// layer's op table, not on the activations, so it is done once per (device, weight pointer, layer configuration) and
+// reused by later calls: 27 tiny launches per depth map disappear from the step.  The cache is keyed by POINTER: a
+// caller that changes weights in place or frees and re-creates them must call mvs_weight_cache_clear() (the Python
+// host does whenever it re-folds BatchNorm).  An event orders first use on one stream before reuse on another.
+// ------------------------------------------------------------------------------------------------
+struct WCacheKey {
+    int dev;
+    const void *w;
+    uint64_t cfg;  // hash of WPackParams (op order, padding, dtype) or a caller tag
+    bool operator<(const WCacheKey &o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (w != o.w) return w < o.w;
+        return cfg < o.cfg;
+    }
+};
+struct WCacheEntry {
+    void *ptr;
+    cudaEvent_t ready;
+};
+static std::mutex g_wcache_mu;
+static std::map<WCacheKey, WCacheEntry> g_wcache;
+
+static uint64_t fnv1a(const void *data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const uint8_t *p = (const uint8_t *)data;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Returns the cached device buffer for `key`, creating it with fill(dst) (which must enqueue work on st) on a miss.
+template <typename F>
+static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void **out, F fill) {
+    std::lock_guard<std::mutex> lock(g_wcache_mu);
+    auto it = g_wcache.find(key);
+    if (it == g_wcache.end()) {
+        WCacheEntry e;
+        MVS_CUDA(cudaMalloc(&e.ptr, bytes));
+        MVS_CUDA(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+        if (int rc = fill(e.ptr)) { cudaFree(e.ptr); cudaEventDestroy(e.ready); return rc; }
+        MVS_CUDA(cudaEventRecord(e.ready, st));
+        it = g_wcache.emplace(key, e).first;
+    } else {
+        MVS_CUDA(cudaStreamWaitEvent(st, it->second.ready, 0));
+    }
+    *out = it->second.ptr;
+    return MVS_OK;
+}
+
+int weight_cache_clear() {
+    std::lock_guard<std::mutex> lock(g_wcache_mu);
+    for (auto &kv : g_wcache) {
+        cudaSetDevice(kv.first.dev);
+        cudaFree(kv.second.ptr);  // synchronises with every stream that may still read it
+        cudaEventDestroy(kv.second.ready);
+    }
+    g_wcache.clear();
+    return MVS_OK;
+}
+
 static int run_layer(TcKind kind, const void *in, const float *w_fp32, const float *shift, int relu, const void *skip,
                      void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
-                     int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0) {
+                     int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false) {
     static thread_local TcPlan pl;  // ~3 KB; not kept across calls
     if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms)) return rc;
     MVS_REQUIRE(!f16 || (kind == TC_CONV2D && pl.npad <= 32 && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
@@ -1162,11 +1223,26 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     pl.L.shift = shift;
     pl.L.relu = relu;
     pl.L.out_f32 = out_f32;
-    pl.L.wpacked = (const uint4 *)wpacked_scratch;
     pl.L.dbg = g_tc_dbg;
-    const int nw = (int)(pl.wpacked_bytes / 2);
-    pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)wpacked_scratch, pl.W);
-    MVS_LAUNCH_CHECK(1);
+    if (!cache_weights) {  // single-layer entry points: ad-hoc weight tensors, pack into the caller's scratch every call
+        const int nw = (int)(pl.wpacked_bytes / 2);
+        pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)wpacked_scratch, pl.W);
+        MVS_LAUNCH_CHECK(1);
+        pl.L.wpacked = (const uint4 *)wpacked_scratch;
+    } else {
+        int dev = 0;
+        MVS_CUDA(cudaGetDevice(&dev));
+        const int nw = (int)(pl.wpacked_bytes / 2);
+        void *wp = nullptr;
+        const WCacheKey key{dev, w_fp32, fnv1a(&pl.W, sizeof(pl.W))};
+        if (int rc = wcache_get(key, pl.wpacked_bytes, st, &wp, [&](void *dst) -> int {
+                pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)dst, pl.W);
+                MVS_LAUNCH_CHECK(1);
+                return MVS_OK;
+            }))
+            return rc;
+        pl.L.wpacked = (const uint4 *)wp;
+    }
     auto launch = [&](auto kern) -> int {
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
         kern<<<pl.grid, kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
@@ -1222,17 +1298,17 @@ int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_pa
     }
     int rc;
 #define RUN(expr) if ((rc = (expr)) != MVS_OK) return rc
-    RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st));
-    RUN(run_layer(TC_CONV_S2, c0, p->w[1], p->shift[1], 1, nullptr, c1, 0, wsc + 1 * kWScratch, B, 8, 16, D, H, W, num_sms, st));
-    RUN(run_layer(TC_CONV_S1, c1, p->w[2], p->shift[2], 1, nullptr, c2, 0, wsc + 2 * kWScratch, B, 16, 16, D / 2, H / 2, W / 2, num_sms, st));
-    RUN(run_layer(TC_CONV_S2, c2, p->w[3], p->shift[3], 1, nullptr, c3, 0, wsc + 3 * kWScratch, B, 16, 32, D / 2, H / 2, W / 2, num_sms, st));
-    RUN(run_layer(TC_CONV_S1, c3, p->w[4], p->shift[4], 1, nullptr, c4, 0, wsc + 4 * kWScratch, B, 32, 32, D / 4, H / 4, W / 4, num_sms, st));
-    RUN(run_layer(TC_CONV_S2, c4, p->w[5], p->shift[5], 1, nullptr, c5, 0, wsc + 5 * kWScratch, B, 32, 64, D / 4, H / 4, W / 4, num_sms, st));
-    RUN(run_layer(TC_CONV_S1, c5, p->w[6], p->shift[6], 1, nullptr, c6, 0, wsc + 6 * kWScratch, B, 64, 64, D / 8, H / 8, W / 8, num_sms, st));
-    RUN(run_layer(TC_CONVT, c6, p->w[7], p->shift[7], 1, c4, u7, 0, wsc + 7 * kWScratch, B, 64, 32, D / 8, H / 8, W / 8, num_sms, st));
-    RUN(run_layer(TC_CONVT, u7, p->w[8], p->shift[8], 1, c2, u9, 0, wsc + 8 * kWScratch, B, 32, 16, D / 4, H / 4, W / 4, num_sms, st));
-    RUN(run_layer(TC_CONVT, u9, p->w[9], p->shift[9], 1, c0, u11, 0, wsc + 9 * kWScratch, B, 16, 8, D / 2, H / 2, W / 2, num_sms, st));
-    RUN(run_layer(TC_CONV_S1, u11, p->w[10], p->shift[10], 0, nullptr, logits, 1, wsc + 10 * kWScratch, B, 8, 1, D, H, W, num_sms, st));
+    RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S2, c0, p->w[1], p->shift[1], 1, nullptr, c1, 0, wsc + 1 * kWScratch, B, 8, 16, D, H, W, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S1, c1, p->w[2], p->shift[2], 1, nullptr, c2, 0, wsc + 2 * kWScratch, B, 16, 16, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S2, c2, p->w[3], p->shift[3], 1, nullptr, c3, 0, wsc + 3 * kWScratch, B, 16, 32, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S1, c3, p->w[4], p->shift[4], 1, nullptr, c4, 0, wsc + 4 * kWScratch, B, 32, 32, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S2, c4, p->w[5], p->shift[5], 1, nullptr, c5, 0, wsc + 5 * kWScratch, B, 32, 64, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S1, c5, p->w[6], p->shift[6], 1, nullptr, c6, 0, wsc + 6 * kWScratch, B, 64, 64, D / 8, H / 8, W / 8, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONVT, c6, p->w[7], p->shift[7], 1, c4, u7, 0, wsc + 7 * kWScratch, B, 64, 32, D / 8, H / 8, W / 8, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONVT, u7, p->w[8], p->shift[8], 1, c2, u9, 0, wsc + 8 * kWScratch, B, 32, 16, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONVT, u9, p->w[9], p->shift[9], 1, c0, u11, 0, wsc + 9 * kWScratch, B, 16, 8, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S1, u11, p->w[10], p->shift[10], 0, nullptr, logits, 1, wsc + 10 * kWScratch, B, 8, 1, D, H, W, num_sms, st, 0, 0, true));
 #undef RUN
     return MVS_OK;
 }
@@ -1278,8 +1354,16 @@ int tc_layer_ncdhw(int kind, const float *x, const float *w, const float *shift,
 // parity sub-images (py, px), i.e. a 3x3 conv with 4 Cin channels and the 5x5 weights scattered into 6x6
 // (row/column 5 zero).  The layer before each of them writes that layout straight from its epilogue.
 // ------------------------------------------------------------------------------------------------
-// fp32 NCHW [N][C][H][W] -> fp16 [ceil(C/8) (x4 if s2d)][N][Ho][Wo][8]; channels beyond C are zero
-__global__ void nchw_to_cp8n_f16_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int N, int C, int H, int W,
+// fp32 (or 8-bit, see below) NCHW [N][C][H][W] -> fp16 [ceil(C/8) (x4 if s2d)][N][Ho][Wo][8]; channels beyond C are zero.
+// T = uint8_t: the image as decoded from disk; value / 255 in fp32 is what the reference's loader computes on the
+// host before the upload (datasets/data_io.py: np.array(img, dtype=np.float32) / 255.), done here after a 4x smaller copy.
+template <typename T>
+__device__ __forceinline__ float load_pixel(const T *p) {
+    if constexpr (sizeof(T) == 1) return __fdiv_rn((float)__ldg(p), 255.f);
+    else return __ldg(p);
+}
+template <typename T>
+__global__ void nchw_to_cp8n_f16_kernel(const T *__restrict__ in, uint4 *__restrict__ out, int N, int C, int H, int W,
                                         int s2d, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -1298,7 +1382,7 @@ __global__ void nchw_to_cp8n_f16_kernel(const float *__restrict__ in, uint4 *__r
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = cc * 8 + 2 * j + h;
-            f[h] = (c < C) ? __ldg(in + (((size_t)n * C + c) * H + ys) * W + xs) : 0.f;
+            f[h] = (c < C) ? load_pixel(in + (((size_t)n * C + c) * H + ys) * W + xs) : 0.f;
         }
         w[j] = pack_f16x2(f[0], f[1]);
     }
@@ -1355,8 +1439,8 @@ size_t featurenet_tc_workspace_bytes(int N, int H, int W) {
 }
 
 // imgs fp32 [N][3][H][W] -> fea fp16 RCP8 [N][H/4][4][W/4][8]
-int featurenet_tc(const float *imgs, const mvs_featurenet_params *p, void *fea, void *workspace, int N, int H, int W,
-                  cudaStream_t st) {
+int featurenet_tc(const void *imgs, int imgs_u8, const mvs_featurenet_params *p, void *fea, void *workspace, int N, int H,
+                  int W, cudaStream_t st) {
     int dev = 0, num_sms = 148;
     MVS_CUDA(cudaGetDevice(&dev));
     MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1368,7 +1452,8 @@ int featurenet_tc(const float *imgs, const mvs_featurenet_params *p, void *fea, 
     uint8_t *wsc = take(MVS_FEATURENET_LAYERS * (kWScratch + 128 * 1024));
     {
         const long long total = (long long)px;
-        nchw_to_cp8n_f16_kernel<<<cdiv(total, 256), 256, 0, st>>>(imgs, (uint4 *)in0, N, 3, H, W, 0, total);
+        if (imgs_u8) nchw_to_cp8n_f16_kernel<uint8_t><<<cdiv(total, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
+        else nchw_to_cp8n_f16_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
         MVS_LAUNCH_CHECK(1);
     }
     const void *ins[MVS_FEATURENET_LAYERS] = {in0, a0, a1, a2, a3, a4, a5, a6};
@@ -1376,14 +1461,20 @@ int featurenet_tc(const float *imgs, const mvs_featurenet_params *p, void *fea, 
     const int scale[MVS_FEATURENET_LAYERS] = {1, 1, 2, 2, 2, 4, 4, 4};   // resolution divisor of each layer's input
     const int out_mode[MVS_FEATURENET_LAYERS] = {0, 1, 0, 0, 1, 0, 0, 2};  // last layer: RCP8 for the warp kernel
     for (int l = 0; l < MVS_FEATURENET_LAYERS; ++l) {
-        float *weff = (float *)(wsc + (size_t)l * (kWScratch + 128 * 1024));
-        void *wpk = (uint8_t *)weff + 128 * 1024;
+        void *wpk = wsc;  // unused since the packed weights are cached; kept for the signature
         const int nw = kFeatCout[l] * kFeatCinEff[l] * 9;
-        featurenet_effective_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(p->w[l], weff, kFeatCout[l], kFeatCin[l],
-                                                                          kFeatCinEff[l], kFeatK[l]);
-        MVS_LAUNCH_CHECK(1);
+        void *weff_v = nullptr;
+        const WCacheKey key{dev, p->w[l], 0xFEA70000ull + (uint64_t)l};
+        if (int rc = wcache_get(key, (size_t)nw * sizeof(float), st, &weff_v, [&](void *dst) -> int {
+                featurenet_effective_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(p->w[l], (float *)dst, kFeatCout[l], kFeatCin[l],
+                                                                                  kFeatCinEff[l], kFeatK[l]);
+                MVS_LAUNCH_CHECK(1);
+                return MVS_OK;
+            }))
+            return rc;
+        const float *weff = (const float *)weff_v;
         if (int rc = run_layer(TC_CONV2D, ins[l], weff, p->shift[l], l != MVS_FEATURENET_LAYERS - 1, nullptr, outs[l], 0, wpk,
-                               1, kFeatCinEff[l], kFeatCout[l], N, H / scale[l], W / scale[l], num_sms, st, 1, out_mode[l]))
+                               1, kFeatCinEff[l], kFeatCout[l], N, H / scale[l], W / scale[l], num_sms, st, 1, out_mode[l], true))
             return rc;
     }
     return MVS_OK;
@@ -1405,7 +1496,7 @@ int tc_conv2d_nchw(const float *x, const float *w, const float *shift, int relu,
     float *weff = (float *)(ws + in_b + out_b);
     void *wpk = (uint8_t *)weff + 128 * 1024;
     const long long tin = (long long)N * Hi * Wi * (cin_eff / 8);
-    nchw_to_cp8n_f16_kernel<<<cdiv(tin, 256), 256, 0, st>>>(x, (uint4 *)xin, N, cin, H, W, s2d_in, tin);
+    nchw_to_cp8n_f16_kernel<float><<<cdiv(tin, 256), 256, 0, st>>>(x, (uint4 *)xin, N, cin, H, W, s2d_in, tin);
     // with cin not a multiple of 8 the s2d channel order is parity * cin8 + ci: build the weights on the padded count
     featurenet_effective_weights_kernel<<<cdiv(cout * cin_eff * 9, 256), 256, 0, st>>>(w, weff, cout, cin, cin_eff, ksize);
     int rc = (s2d_in && cin != cin8) ? set_error(MVS_ERR_UNSUPPORTED, "5x5 stride-2 layer needs Cin %% 8 == 0") : MVS_OK;
@@ -1484,7 +1575,17 @@ extern "C" int mvs_featurenet_tc_fwd(const float *imgs, const mvs_featurenet_par
                 "FeatureNet needs H, W divisible by 4 (two stride-2 stages), got %dx%d", H, W);
     for (int i = 0; i < MVS_FEATURENET_LAYERS; ++i)
         MVS_REQUIRE(params->w[i] && params->shift[i], "featurenet params: layer %d has a null pointer", i);
-    return featurenet_tc(imgs, params, fea_rcp8_f16, workspace, N, H, W, (cudaStream_t)stream);
+    return featurenet_tc(imgs, 0, params, fea_rcp8_f16, workspace, N, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_featurenet_tc_fwd_u8(const uint8_t *imgs_u8, const mvs_featurenet_params *params, void *fea_rcp8_f16,
+                                        void *workspace, int N, int H, int W, void *stream) {
+    MVS_REQUIRE(imgs_u8 && params && fea_rcp8_f16 && workspace, "null pointer argument");
+    MVS_REQUIRE(N > 0 && H >= 4 && W >= 4 && H % 4 == 0 && W % 4 == 0,
+                "FeatureNet needs H, W divisible by 4 (two stride-2 stages), got %dx%d", H, W);
+    for (int i = 0; i < MVS_FEATURENET_LAYERS; ++i)
+        MVS_REQUIRE(params->w[i] && params->shift[i], "featurenet params: layer %d has a null pointer", i);
+    return featurenet_tc(imgs_u8, 1, params, fea_rcp8_f16, workspace, N, H, W, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin,
@@ -1496,3 +1597,6 @@ extern "C" int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float
     MVS_REQUIRE(ksize == 3 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv2d needs even H, W");
     return tc_conv2d_nchw(x, w, shift, relu, y, N, Cin, Cout, H, W, ksize, s2d_out, (cudaStream_t)stream);
 }
+
+/* Drops every cached packed-weight buffer (see the cache comment above run_layer). */
+extern "C" int mvs_weight_cache_clear(void) { return weight_cache_clear(); }

@@ -73,6 +73,7 @@ class FeatureNet(nn.Module):
                     out.append((w.float().contiguous(), b.float().contiguous()))
                 out.append((self.feature.weight.detach().float().contiguous(), self.feature.bias.detach().float().contiguous()))
             self._native, self._native_key = out, key
+            ops.weights_changed()
         return self._native
 
     def infer_half(self, x):
@@ -152,6 +153,7 @@ class CostRegNet(nn.Module):
                     out.append(fold_bn(seq[0].weight, seq[1], out_dim=1))
                 out.append((self.prob.weight.detach().contiguous(), self.prob.bias.detach().contiguous()))
             self._folded, self._folded_key = out, key
+            ops.weights_changed()
         return self._folded
 
     def infer(self, volume, precision="fp32"):
@@ -247,8 +249,13 @@ class MVSNet(nn.Module):
 
         mark("start")
         infer = (not torch.is_grad_enabled()) and (not self.training)
-        if infer and self.precision in ("bf16", "fast") and self.featurenet != "cudnn":
-            fea = ops.featurenet_tc(imgs.float(), self.feature.folded_native())
+        tc_features = infer and self.precision in ("bf16", "fast") and self.featurenet != "cudnn"
+        if imgs.dtype == torch.uint8 and not tc_features:
+            # 8-bit images: the reference loader's normalisation (datasets/data_io.py).  A true fp32 division like
+            # numpy's -- dividing by a Python scalar on CUDA multiplies by the rounded reciprocal instead.
+            imgs = imgs.float() / torch.full((), 255.0, dtype=torch.float32, device=imgs.device)
+        if tc_features:
+            fea = ops.featurenet_tc(imgs if imgs.dtype == torch.uint8 else imgs.float(), self.feature.folded_native())
         elif infer and self.precision == "fast":
             fea = self.extract_features_half(imgs)
         else:

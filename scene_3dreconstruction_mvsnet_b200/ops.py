@@ -48,6 +48,14 @@ def _ws(nbytes, device, tag=None):
     return buf
 
 
+def weights_changed():
+    """Tell the native library that weight tensors were replaced or modified: its packed-weight cache is keyed by
+    pointer (mvs_weight_cache_clear in include/mvsnet_b200.h).  Called by the models whenever BatchNorm is re-folded."""
+    import os
+    if os.path.exists(_lib.LIB_PATH):
+        _lib.load().mvs_weight_cache_clear()
+
+
 def release_workspaces():
     """Drop every cached scratch buffer (they are re-created on demand)."""
     _WS_CACHE.clear()
@@ -290,7 +298,13 @@ def featurenet_tc(imgs, folded):
     """FeatureNet.forward (reference models/mvsnet.py:10-30, eval mode) on the tensor cores.
     imgs [B,V,3,H,W] fp32; folded = 8 (weight, shift) CUDA tensors in layer order (native shapes, BN folded)
     -> Rcp8Features (fp16 [B*V][H/4][4][W/4][8])."""
-    imgs = _prep(imgs, "imgs", 5)
+    u8 = isinstance(imgs, torch.Tensor) and imgs.dtype == torch.uint8
+    if u8:  # 8-bit images as decoded from disk: /255 happens on the device (see mvs_featurenet_tc_fwd_u8)
+        if not imgs.is_cuda or imgs.dim() != 5:
+            raise RuntimeError("uint8 imgs must be a CUDA tensor [B,V,3,H,W], got %s on %s" % (tuple(imgs.shape), imgs.device))
+        imgs = imgs.detach().contiguous()
+    else:
+        imgs = _prep(imgs, "imgs", 5)
     B, V, C, H, W = imgs.shape
     if C != 3:
         raise RuntimeError("FeatureNet expects 3-channel images, got %d" % C)
@@ -309,7 +323,8 @@ def featurenet_tc(imgs, folded):
     ws = _ws(nbytes, imgs.device, "featurenet")
     out = torch.empty((B * V, H // 4, 4, W // 4, 8), dtype=torch.float16, device=imgs.device)
     with torch.cuda.device(imgs.device):
-        rc = lib.mvs_featurenet_tc_fwd(_ptr(imgs), ctypes.byref(params), _ptr(out), _ptr(ws), B * V, H, W, _stream(imgs))
+        fn = lib.mvs_featurenet_tc_fwd_u8 if u8 else lib.mvs_featurenet_tc_fwd
+        rc = fn(_ptr(imgs), ctypes.byref(params), _ptr(out), _ptr(ws), B * V, H, W, _stream(imgs))
     _lib.check(rc, "mvs_featurenet_tc_fwd")
     return Rcp8Features(out, B, V, H // 4, W // 4)
 

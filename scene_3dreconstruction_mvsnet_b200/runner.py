@@ -30,10 +30,10 @@ class DepthMapRunner:
         slots = []
         for _ in range(self.depth):
             s = {
-                "h_imgs": torch.empty(imgs.shape, dtype=torch.float32).pin_memory(),
+                "h_imgs": torch.empty(imgs.shape, dtype=imgs.dtype).pin_memory(),
                 "h_proj": torch.empty(proj.shape, dtype=torch.float32).pin_memory(),
                 "h_dv": torch.empty(dv.shape, dtype=torch.float32).pin_memory(),
-                "d_imgs": torch.empty(imgs.shape, dtype=torch.float32, device=self.device),
+                "d_imgs": torch.empty(imgs.shape, dtype=imgs.dtype, device=self.device),
                 "d_proj": torch.empty(proj.shape, dtype=torch.float32, device=self.device),
                 "d_dv": torch.empty(dv.shape, dtype=torch.float32, device=self.device),
                 "h_out": torch.empty((2, B, h, w), dtype=torch.float32).pin_memory(),
@@ -41,14 +41,15 @@ class DepthMapRunner:
             }
             slots.append(s)
         self._slots = slots
-        self._shape = (tuple(imgs.shape), tuple(proj.shape), tuple(dv.shape))
-        self.h2d_bytes_per_view = 4 * (imgs.numel() + proj.numel() + dv.numel())
+        self._shape = (tuple(imgs.shape), tuple(proj.shape), tuple(dv.shape), imgs.dtype)
+        self.h2d_bytes_per_view = imgs.numel() * imgs.element_size() + 4 * (proj.numel() + dv.numel())
         self.d2h_bytes_per_view = 4 * 2 * B * h * w
 
     @torch.no_grad()
     def run_views(self, views, sink=None):
         """views: iterable of (imgs [B,V,3,H,W], proj [B,V,4,4], depth_values [B,D]) HOST arrays
-        (numpy or CPU tensors).  For every view calls sink(index, depth_np, conf_np) (numpy views of a
+        (numpy or CPU tensors).  imgs are float32 in [0,1] like the reference's loader output, or uint8 as decoded
+        from disk (then /255 runs on the device and the upload is 4x smaller).  For every view calls sink(index, depth_np, conf_np) (numpy views of a
         pinned buffer, valid until the next call) or, without a sink, returns the list of copies."""
         results = [] if sink is None else None
         compute = torch.cuda.current_stream(self.device)
@@ -64,8 +65,11 @@ class DepthMapRunner:
                 sink(idx, d, c)
 
         for idx, (imgs, proj, dv) in enumerate(views):
-            imgs, proj, dv = (torch.as_tensor(a, dtype=torch.float32) for a in (imgs, proj, dv))
-            if self._slots is None or self._shape != (tuple(imgs.shape), tuple(proj.shape), tuple(dv.shape)):
+            imgs = torch.as_tensor(imgs)
+            if imgs.dtype != torch.uint8:
+                imgs = imgs.to(torch.float32)
+            proj, dv = (torch.as_tensor(a, dtype=torch.float32) for a in (proj, dv))
+            if self._slots is None or self._shape != (tuple(imgs.shape), tuple(proj.shape), tuple(dv.shape), imgs.dtype):
                 for e in pending:
                     drain(e)
                 pending = []

@@ -229,3 +229,20 @@ def test_featurenet_tc_matches_torch(B, V, H, W, weights):
         (got - ref32).abs().max().item(), scale)
     # and it is at least as close to the fp32 result as the TF32 cuDNN path of the same mode is, within a factor
     assert (got - ref32).abs().mean().item() < 5 * (ref - ref32).abs().mean().item() + 1e-4
+
+
+def test_uint8_images_equal_float_images(weights):
+    """8-bit images (as decoded from disk) give bit-identical depth maps to the float32 images the reference's loader
+    produces from them (value / 255 in fp32), on the tensor-core path and -- through the torch fallback -- in fp32 mode."""
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    imgs, proj, dv = synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=2)
+    u8 = (imgs * 255.0).round().to(torch.uint8)
+    f32 = u8.float() / 255.0
+    for precision in ("bf16", "fp32"):
+        m = load_model(weights, precision=precision)
+        with torch.no_grad():
+            a = m(u8.to(DEV), proj.to(DEV), dv.to(DEV))
+            b = m(f32.to(DEV), proj.to(DEV), dv.to(DEV))
+        assert torch.equal(a["depth"], b["depth"]), "%s: max diff %g" % (precision, (a["depth"] - b["depth"]).abs().max().item())
+        assert torch.equal(a["photometric_confidence"], b["photometric_confidence"]), precision
