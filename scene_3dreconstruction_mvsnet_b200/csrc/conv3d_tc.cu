@@ -49,6 +49,7 @@ tmap_encode_fn get_tmap_encode() {
 constexpr int kMaxOps = 112;
 constexpr int kMaxAcc = 8;
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int kTcThreadsDual = 352;  // + warp 10: second MMA issuer (layers whose steps share no input plane)
 
 struct TcOp {
     uint32_t a_off;     // byte offset of the A operand inside its ring plane (sub-plane + tap + chunk pair)
@@ -91,6 +92,7 @@ struct TcLayer {
     int f16;         // 1: fp16 operands / fp16 outputs (FeatureNet); 0: bf16
     int out_mode;    // 0: CP8 [C/8][D][H][W][8]; 1: space-to-depth [4 parities x C/8][D][H/2][W/2][8];
                      // 2: row-chunk-planar "RCP8" [D][H][C/8][W][8] (what the fused warp kernel's TMA windows read)
+    int dual;        // 1: two MMA issuer warps alternate over the steps (need == 1: steps share no input plane)
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     TcOp ops[kMaxOps];
@@ -134,7 +136,7 @@ __device__ __forceinline__ void issue_step(const TcLayer &L, const uint2 *__rest
 }
 
 template <int NPAD, bool F16 = false, bool SIMPLE = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreadsDual, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // [0,256): mbarriers + tmem address; then packed weights; then the plane ring (128-byte aligned)
@@ -165,9 +167,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     {
         const uint4 *src = L.wpacked + (size_t)group * (L.wbytes_group / 16);
         uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
-        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    for (int o = threadIdx.x; o < L.nops; o += kTcThreads)
+    for (int o = threadIdx.x; o < L.nops; o += blockDim.x)
         optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
     if (threadIdx.x < 64)
         s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + group * L.cout_group + threadIdx.x) : 0.f;
@@ -238,10 +240,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
             if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || warp == 10) {
+        // ================= MMA issuer(s) =================
         // The whole warp runs this loop with warp-uniform values (kernel parameters, loop counters) so that
         // descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+        // Dual mode (L.dual, warp 10 present): when every step reads only its own input plane, two issuer warps
+        // alternate over the steps -- warp 1 owns TMEM buffer 0, warp 10 buffer 1.  The barrier waits, commits and
+        // bookkeeping of one step (~1000 cycles, as long as its 20-70 MMAs take to execute) then overlap the other
+        // warp's MMAs instead of leaving the tensor pipe idle.
+        const uint32_t me = (warp == 10) ? 1u : 0u;
         const bool leader = ptx::elect_one();
         const uint32_t idesc = F16 ? ptx::make_idesc_f16_m128(NPAD) : ptx::make_idesc_bf16_m128(NPAD);
         uint32_t st = 0;
@@ -256,8 +263,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             decode(it, b, x0, y0, zs, T);
             for (int t = 0; t < T; ++t, ++st) {
                 const uint32_t buf = st & 1;
+                const bool mine = !L.dual || buf == me;  // dual mode: the other warp's steps only advance the ring state
                 const uint32_t sl0 = s0, sl1 = wrap(s0 + 1), sl2 = wrap(s0 + 2);
-                if (leader) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
+                if (leader && mine) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
                     const long long c0 = clock64();
                     // planes already waited for in earlier steps of this item need no second look
                     for (uint32_t r = (t == 0) ? 0 : need - adv; r < need; ++r) {
@@ -271,7 +279,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 }
                 __syncwarp();
                 ptx::tcgen05_fence_after();
-                if (leader) {
+                if (leader && mine) {
                     const long long ci = clock64();
                     const uint32_t sb0 = (ring_base + sl0 * L.slot_bytes) >> 4;
                     const uint32_t sb1 = (ring_base + sl1 * L.slot_bytes) >> 4;
@@ -288,16 +296,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 const uint32_t nrel = (t == T - 1) ? need : adv;
                 for (uint32_t r = 0; r < nrel; ++r) {
                     const uint32_t sl = wrap(s0 + r);
-                    if (leader) ptx::tcgen05_commit(empty_bar(sl));
+                    if (leader && mine) ptx::tcgen05_commit(empty_bar(sl));
                     par ^= 1u << sl;
                 }
-                if (leader) ptx::tcgen05_commit(tfull_bar(buf));
+                if (leader && mine) ptx::tcgen05_commit(tfull_bar(buf));
                 s0 = wrap(s0 + nrel);
                 __syncwarp();
                 t_release += clock64() - cr;
             }
         }
-        if (leader && L.dbg) {
+        if (leader && L.dbg && me == 0) {
             L.dbg[blockIdx.x * 12 + 1] = w_full;
             L.dbg[blockIdx.x * 12 + 2] = w_tempty;
             L.dbg[blockIdx.x * 12 + 3] = t_issue;
@@ -1013,6 +1021,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.fold_cw = fold ? 16 : 0;
     W.ntaps = is2d ? 9 : 27;
     L.fold = fold ? 1 : 0;
+    static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
+    L.dual = (!fold && need == 1 && nacc == 1 && !nodual) ? 1 : 0;
     L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * 16)) : 0;
     const int chunk_stride = rows * P * 16;
     int nops = 0;
@@ -1245,7 +1255,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     }
     auto launch = [&](auto kern) -> int {
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        kern<<<pl.grid, kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
+        kern<<<pl.grid, pl.L.dual ? kTcThreadsDual : kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };
