@@ -92,6 +92,7 @@ struct TcLayer {
     int f16;         // 1: fp16 operands / fp16 outputs (FeatureNet); 0: bf16
     int out_mode;    // 0: CP8 [C/8][D][H][W][8]; 1: space-to-depth [4 parities x C/8][D][H/2][W/2][8];
                      // 2: row-chunk-planar "RCP8" [D][H][C/8][W][8] (what the fused warp kernel's TMA windows read)
+    int merged_t;    // 1: transposed conv with the 8 output-parity classes merged along N (column block = class)
     int dual;        // 1: two MMA issuer warps alternate over the steps (need == 1: steps share no input plane)
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
@@ -135,9 +136,13 @@ __device__ __forceinline__ void issue_step(const TcLayer &L, const uint2 *__rest
     }
 }
 
-template <int NPAD, bool F16 = false, bool SIMPLE = false>
+// EPI: epilogue flavour, chosen on the host.  0 = general (several accumulators per M-tile, skip, fp32 output);
+// 1 = lean (one accumulator per M-tile, no skip, 16-bit output); 2 = class-merged transposed conv (+skip).
+template <int NPAD, bool F16 = false, int EPI = 0>
 __global__ void __launch_bounds__(kTcThreadsDual, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
+    constexpr bool SIMPLE = (EPI == 1);
+    constexpr bool STEPWISE = (EPI != 0);  // epilogue warp sets alternate over steps (one TMEM buffer each)
     extern __shared__ __align__(1024) uint8_t smem[];
     // [0,256): mbarriers + tmem address; then packed weights; then the plane ring (128-byte aligned)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -181,7 +186,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(tfull_bar(b), 1);
             // lean epilogue: the 4 quadrant warps of the set that owns this buffer; general: all 8 epilogue warps
-            ptx::mbar_init(tempty_bar(b), SIMPLE ? 4 : 8);
+            ptx::mbar_init(tempty_bar(b), STEPWISE ? 4 : 8);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmap);
@@ -235,6 +240,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                             ptx::tma_load_5d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot), 0,
                                              L.in_scale * x0 + L.sub_xoff[s], L.in_scale * y0 + L.sub_yoff[s], pz,
                                              b * L.chunks);
+                    }
+                    // Skip connection of a class-merged transposed conv: the epilogue reads it with only a few KB in flight
+                    // per SM.  This otherwise idle thread pulls the rows of output step j into L2 a few steps ahead
+                    // (bulk prefetch: no registers, no completion tracking); skipped when a step has too many rows.
+                    if (EPI == 2 && L.skip != nullptr && j < T) {
+                        const int cpc = L.cout_total >> 3;
+                        const int xo = 2 * x0, nvox = min(2 * L.TXB, L.Wout - xo), nrow = min(2 * L.TY, L.Hout - 2 * y0);
+                        if (2 * cpc * nrow <= 24) {
+                            const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
+                            for (int cc = 0; cc < cpc; ++cc)
+                                for (int pz = 0; pz < 2; ++pz) {
+                                    const uint4 *rowp = L.skip + ((size_t)b * cpc + cc) * plane +
+                                                        ((size_t)(2 * (zs + j) + pz) * L.Hout + 2 * y0) * L.Wout + xo;
+                                    for (int ry = 0; ry < nrow; ++ry) ptx::prefetch_l2_bulk(rowp + (size_t)ry * L.Wout, (uint32_t)nvox * 16u);
+                                }
+                        }
                     }
                 }
             }
@@ -319,7 +340,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // only z advances.  Per z-step the (M-tile, accumulator) pairs are drained in batches of G = 64/NPAD:
         // all tcgen05.ld of a batch are issued back to back, the skip-connection loads of the batch are issued
         // while they fly, then one tcgen05.wait::ld -- so TMEM and global latencies overlap instead of adding up.
-        constexpr int G = 64 / NPAD;
+        constexpr int G = (NPAD <= 64) ? 64 / NPAD : 1;
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int eset = (warp - 2) >> 2;  // the two warps of a quadrant alternate over the batches of a step
         const uint4 *skip = L.skip;
@@ -332,6 +353,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const size_t zstride = s2d ? (size_t)(L.Hout / 2) * (L.Wout / 2)
                                    : (rcp8 ? (size_t)L.Hout * (L.cout_total >> 3) * L.Wout : (size_t)L.out_scale * L.Hout * L.Wout);
         const int nacc_shift = (L.nacc == 8) ? 3 : 0;
+        const size_t mvoff[4] = {(size_t)L.acc_voff[0], (size_t)L.acc_voff[2], (size_t)L.acc_voff[4], (size_t)L.acc_voff[6]};
         const int npairs = L.MT << nacc_shift;
         const int nchunk = (L.cout_group + 7) >> 3;
         const int chunk0 = (group * L.cout_group) >> 3;  // first output chunk of this CTA's channel group
@@ -373,7 +395,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 // tcgen05.wait::ld round trip, release) are paid once per step.  General path (skip loads in the loop):
                 // both warps work on every step and split its (M-tile, accumulator) pairs -- measured faster there.
                 const uint32_t buf = st & 1;
-                if (SIMPLE && buf != (uint32_t)eset) continue;
+                if (STEPWISE && buf != (uint32_t)eset) continue;
                 const long long c0 = clock64();
                 ptx::mbar_wait(tfull_bar(buf), (st >> 1) & 1);
                 const long long c1 = clock64();
@@ -381,7 +403,74 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 ptx::tcgen05_fence_after();
                 const size_t zoff = (size_t)(zs + t) * zstride;
                 const uint32_t tbuf = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ncols_buf;
-                if constexpr (SIMPLE) {
+                if constexpr (EPI == 2) {
+                    // Class-merged transposed conv: the M-tile's NPAD columns are [class (pz,py,px)][Cout].  A "pair" is
+                    // the two x-parity classes of one (pz, py, channel chunk): their output chunks are adjacent in
+                    // memory (voxels 2x and 2x+1), so each thread moves 32 contiguous bytes with one 256-bit load /
+                    // store and a warp covers 1 KB per instruction.  Everything is unrolled over compile-time
+                    // (pz, py, chunk); the skip loads of a group are issued before its tcgen05.ld so both latencies
+                    // overlap, and the producer warp has pulled the skip rows into L2 a few steps earlier.
+                    constexpr int COUT = NPAD / 8, CPC = COUT / 8;
+                    const uint4 *skp = skip ? skip + zoff : nullptr;
+                    uint4 *outp = reinterpret_cast<uint4 *>(L.out) + zoff;
+                    for (int mt = 0; mt < L.MT; ++mt) {
+                        const bool ok = (vmask >> mt) & 1u;
+                        const size_t mb = mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3));
+#pragma unroll
+                        for (int pz = 0; pz < 2; ++pz) {
+                            uint32_t sk[2 * CPC][8];
+                            if (skp != nullptr && ok) {
+#pragma unroll
+                                for (int py = 0; py < 2; ++py)
+#pragma unroll
+                                    for (int cc = 0; cc < CPC; ++cc)
+                                        ptx::ldg256(skp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], sk[py * CPC + cc]);
+                            }
+                            uint32_t r[2 * CPC][16];
+#pragma unroll
+                            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                                for (int cc = 0; cc < CPC; ++cc) {
+                                    const int col0 = 2 * (pz * 2 + py) * COUT + cc * 8;
+                                    ptx::tmem_ld_x8(tbuf + mt * NPAD + col0, &r[py * CPC + cc][0]);
+                                    ptx::tmem_ld_x8(tbuf + mt * NPAD + col0 + COUT, &r[py * CPC + cc][8]);
+                                }
+                            ptx::tmem_ld_wait();
+                            if (mt == L.MT - 1 && pz == 1) {  // last group: the buffer can be refilled
+                                ptx::tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+                            }
+                            if (!ok) continue;
+#pragma unroll
+                            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                                for (int cc = 0; cc < CPC; ++cc) {
+                                    const int u = py * CPC + cc;
+                                    uint32_t pk[8];
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {  // h = x parity
+                                        float v[8];
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e)
+                                            v[e] = fmaxf(__uint_as_float(r[u][h * 8 + e]) + s_shift[cc * 8 + e], relu_lo);
+                                        if (skp != nullptr) {
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&sk[u][h * 4 + e]));
+                                                v[2 * e] += f.x;
+                                                v[2 * e + 1] += f.y;
+                                            }
+                                        }
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) pk[h * 4 + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+                                    }
+                                    ptx::stg256(outp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], pk);
+                                }
+                        }
+                    }
+                    epi_work += clock64() - c1;
+                } else if constexpr (SIMPLE) {
                     uint4 *oz = reinterpret_cast<uint4 *>(L.out) + ((size_t)b * (L.cout_total >> 3) + chunk0) * plane + zoff;
                     constexpr int MB = (NPAD <= 16) ? 4 : (NPAD <= 32 ? 2 : 1);  // M-tiles per batch: 64 accumulator registers
                     for (int m0 = 0; m0 < L.MT; m0 += MB) {
@@ -422,7 +511,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                         }
                     }
                     epi_work += clock64() - c1;
-                } else {
+                } else if constexpr (NPAD <= 64) {
                 const int gsz = min(G, (npairs + 1) >> 1);
                 for (int p0 = eset * gsz; p0 < npairs; p0 += 2 * gsz) {
                     uint32_t r[G][NPAD];
@@ -846,6 +935,7 @@ struct WSrc {
 struct WPackParams {
     int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
     int fold_cw;  // > 0: depth-folded layout, B row n = (kd = 2 - n / fold_cw, cout = n % fold_cw); src taps are kh*3+kw
+    int merged_t; // 1: class-merged transposed conv, B row n = (class n / cout, cout n % cout); src taps are dz*4+dy*2+dx
     int ntaps;    // taps per (cout, cin) pair in the source weights: 27 (3-D) or 9 (2-D, [Cout][Cin][3][3])
     int f16;      // 1: fp16 output, 0: bf16
     WSrc src[kMaxOps];
@@ -870,6 +960,18 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
         nn = n % p.fold_cw;
         co = nn;
         if (tap >= 0) tap += (2 - n / p.fold_cw) * 9;
+    }
+    if (p.merged_t) {
+        // output parity class a = (pz,py,px) uses input offset d = (dz,dy,dx) iff d <= p componentwise, through
+        // the kernel tap k = 1 (p = 0), 2 (p = 1, d = 0) or 0 (p = 1, d = 1) per dimension
+        const int a = n / p.cout_total;
+        nn = n % p.cout_total;
+        co = nn;
+        if (tap >= 0) {
+            const int pz = a >> 2, py = (a >> 1) & 1, px = a & 1, dz = tap >> 2, dy = (tap >> 1) & 1, dx = tap & 1;
+            if (a >= 8 || dz > pz || dy > py || dx > px) tap = -1;
+            else tap = (pz ? (dz ? 0 : 2) : 1) * 9 + (py ? (dy ? 0 : 2) : 1) * 3 + (px ? (dx ? 0 : 2) : 1);
+        }
     }
     float v = 0.f;
     if (tap >= 0 && nn < p.cout_group && co < p.cout_total && cin < p.cin_total)
@@ -912,23 +1014,27 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
     const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
     const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
+    // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
+    static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
+    const bool merged_t = (kind == TC_CONVT) && cin >= 16 && 8 * cout <= 128 && !nomerge;
     int ntaps_ops;  // MMA instructions per step
-    if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
+    if (merged_t) ntaps_ops = 8 * kpairs_tap;
+    else if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
     else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
     else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
     MVS_REQUIRE(!(kind == TC_CONVT && cin < 16), "tc convT needs Cin >= 16");
     MVS_REQUIRE(ntaps_ops <= kMaxOps, "tc conv: too many ops");
     int ngroups = 1;
     int cout_group = cout;
-    while (true) {
+    while (!merged_t) {
         const int npad_try = fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
         if ((size_t)ntaps_ops * npad_try * 32 <= 112 * 1024 && cout_group <= 64) break;
         ngroups *= 2;
         cout_group = cout / ngroups;
         MVS_REQUIRE(cout_group >= 8 && cout % ngroups == 0, "tc conv: cannot split Cout=%d", cout);
     }
-    const int npad = fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
-    const int nacc = (kind == TC_CONVT) ? 8 : 1;
+    const int npad = merged_t ? 8 * cout : (fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64)));
+    const int nacc = (kind == TC_CONVT && !merged_t) ? 8 : 1;
     const int wbytes = ntaps_ops * npad * 32;
     // ring geometry
     const int need = (fold || is2d) ? 1 : ((kind == TC_CONVT) ? 2 : 3);
@@ -1020,6 +1126,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.transposed = (kind == TC_CONVT);
     W.fold_cw = fold ? 16 : 0;
     W.ntaps = is2d ? 9 : 27;
+    W.merged_t = merged_t ? 1 : 0;
+    L.merged_t = merged_t ? 1 : 0;
     L.fold = fold ? 1 : 0;
     static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
     L.dual = (!fold && need == 1 && nacc == 1 && !nodual) ? 1 : 0;
@@ -1063,6 +1171,23 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         }
         L.acc_first[1] = nops;
         L.acc_pz[0] = L.acc_py[0] = L.acc_px[0] = 0;
+    } else if (merged_t) {
+        // one op per input offset d = (dz,dy,dx) and K-chunk; the packed B block holds, for every parity class, the
+        // tap that class applies to this offset (or zeros), see pack_weights_kernel
+        L.acc_first[0] = 0;
+        for (int d = 0; d < 8; ++d) {
+            const int dz = d >> 2, dy = (d >> 1) & 1, dx = d & 1;
+            for (int kc = 0; kc < cin / 16; ++kc) {
+                TcOp &op = L.ops[nops];
+                op.a_off = (dy * P + dx) * 16 + 2 * kc * chunk_stride;
+                op.lbo = chunk_stride;
+                op.widx = nops; op.plane_rel = dz; op.acc = 0;
+                W.src[nops] = WSrc{{(int16_t)d, (int16_t)d}, {(int16_t)(16 * kc), (int16_t)(16 * kc + 8)}};
+                ++nops;
+            }
+        }
+        L.acc_first[1] = nops;
+        for (int a = 0; a < 8; ++a) { L.acc_pz[a] = a >> 2; L.acc_py[a] = (a >> 1) & 1; L.acc_px[a] = a & 1; }
     } else {
         // 8 output-parity classes; per dimension: parity 0 -> (k=1, d=0); parity 1 -> (k=2, d=0), (k=0, d=1)
         for (int a = 0; a < 8; ++a) {
@@ -1087,7 +1212,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         L.acc_first[8] = nops;
     }
     MVS_REQUIRE(nops == ntaps_ops, "tc conv: internal op count mismatch (%d vs %d)", nops, ntaps_ops);
-    for (int a = 0; a < nacc; ++a) L.acc_voff[a] = (L.acc_pz[a] * L.Hout + L.acc_py[a]) * L.Wout + L.acc_px[a];
+    for (int a = 0; a < (merged_t ? 8 : nacc); ++a) L.acc_voff[a] = (L.acc_pz[a] * L.Hout + L.acc_py[a]) * L.Wout + L.acc_px[a];
     MVS_REQUIRE((long long)L.Dout * L.Hout * L.Wout < (1LL << 31), "tc conv: volume too large for 32-bit class offsets");
     L.nops = nops;
     W.nblocks = nops;
@@ -1261,12 +1386,13 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     };
     if (pl.L.fold) return launch(conv3d_tc_fold_kernel<16>);
     // lean epilogue when there is one accumulator per M-tile, no skip connection and a 16-bit output
-    const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32;
-    if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true, true>) : launch(conv3d_tc_kernel<32, true, true>);
+    const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32 && !pl.L.merged_t;
+    if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true, 1>) : launch(conv3d_tc_kernel<32, true, 1>);
+    if (pl.L.merged_t) return pl.npad == 64 ? launch(conv3d_tc_kernel<64, false, 2>) : launch(conv3d_tc_kernel<128, false, 2>);
     if (simple) {
-        if (pl.npad == 16) return launch(conv3d_tc_kernel<16, false, true>);
-        if (pl.npad == 32) return launch(conv3d_tc_kernel<32, false, true>);
-        return launch(conv3d_tc_kernel<64, false, true>);
+        if (pl.npad == 16) return launch(conv3d_tc_kernel<16, false, 1>);
+        if (pl.npad == 32) return launch(conv3d_tc_kernel<32, false, 1>);
+        return launch(conv3d_tc_kernel<64, false, 1>);
     }
     if (pl.npad == 16) return launch(conv3d_tc_kernel<16>);
     if (pl.npad == 32) return launch(conv3d_tc_kernel<32>);

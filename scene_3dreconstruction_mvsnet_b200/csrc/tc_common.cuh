@@ -65,6 +65,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
+// bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16-byte aligned global address
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                             int c2, int c3, int c4) {
     asm volatile(
@@ -142,6 +146,17 @@ __device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr) {
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
         "r"(z)
         : "memory");
+}
+// 256-bit global load (read-only path) / store; the address must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const void *p, uint32_t *r) {
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, const uint32_t *r) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
