@@ -65,10 +65,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
-// bulk L2 prefetch of `bytes` (multiple of 16) contiguous bytes at a 16-byte aligned global address
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                             int c2, int c3, int c4) {
     asm volatile(
