@@ -263,6 +263,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const long long t_start = clock64();
         const uint32_t nslot = L.nslot, need = L.need, adv = L.adv;
         auto wrap = [&](uint32_t s) { return s >= nslot ? s - nslot : s; };
+        // one lane runs the whole loop: no warp-level re-convergence points between a step's waits and its MMAs
+        if (leader)
         for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
@@ -282,7 +284,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     w_full += c1 - c0;
                     w_tempty += clock64() - c1;
                 }
-                __syncwarp();
                 ptx::tcgen05_fence_after();
                 if (leader && mine) {
                     const long long ci = clock64();
@@ -306,7 +307,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 }
                 if (leader && mine) ptx::tcgen05_commit(tfull_bar(buf));
                 s0 = wrap(s0 + nrel);
-                __syncwarp();
                 t_release += clock64() - cr;
             }
         }
@@ -726,6 +726,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const int nops = L.nops;
         const uint32_t nslot = L.nslot, uR = (uint32_t)R;
         auto wrapR = [&](uint32_t v) { return v >= uR ? v - uR : v; };
+        // one lane runs the whole loop: no warp-level re-convergence points between a step's waits and its MMAs
+        if (leader)
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b_, x0, y0, zs, T;
             decode(it, b_, x0, y0, zs, T);
@@ -744,7 +746,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     w_tempty += clock64() - c1;
                 }
                 if (first_touch) epar ^= 1u << ft_blk;
-                __syncwarp();
                 ptx::tcgen05_fence_after();
                 const uint32_t p0 = wrapR(pj + k0);
                 const int cnt = k1 - k0 + 1;
@@ -766,7 +767,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     ptx::tcgen05_commit(empty_bar(slot));
                     if (j >= 2) ptx::tcgen05_commit(tfull_bar(pj));  // output plane zs + j - 2 is complete
                 }
-                __syncwarp();
                 if (++slot == nslot) { slot = 0; fpar ^= 1u; }
                 pj = wrapR(pj + 1);
             }
