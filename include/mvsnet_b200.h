@@ -160,9 +160,12 @@ int mvs_featurenet_tc_fwd_u8(const uint8_t *imgs_u8, const mvs_featurenet_params
 int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin, int Cout,
                           int H, int W, int ksize, int stride, int s2d_out, void *stream);
 /* Fused warp+variance on features in the layout mvs_featurenet_tc_fwd produces: fea [B*V][H][4][W][8] fp16 with
- * image index n = b*V + v (view 0 = reference view).  workspace: mvs_warp_variance_workspace_bytes(). */
+ * image index n = b*V + v (view 0 = reference view).  workspace: mvs_warp_variance_workspace_bytes().
+ * half_sums = 0: fp32 running sums of the warped values (|var - ref| <= 2^-7 |ref| + 8e-3 on N(0,1) features);
+ * half_sums = 1: packed-half sums of the deviations from the reference view (7 % faster; variances >> 1, i.e.
+ * mismatched voxels, can be off by up to 2^-6 relative). */
 int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const float *proj, const float *depth_values, void *vol_cp8,
-                                   void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
+                                   void *workspace, int B, int V, int C, int D, int H, int W, int half_sums, void *stream);
 
 /* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
  *                                                        models/mvsnet.py:192-193,204,214-218

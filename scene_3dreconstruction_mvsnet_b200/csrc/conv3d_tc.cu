@@ -96,6 +96,8 @@ struct TcLayer {
     int dual;        // 1: two MMA issuer warps alternate over the steps (need == 1: steps share no input plane)
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
+    int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
+                     //    the three partial sums of x, x+1, x+2 (lane shifts)
     TcOp ops[kMaxOps];
 };
 
@@ -630,8 +632,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
     float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
-    constexpr uint32_t kHdr = 1664;
-    static_assert(400 + kMaxOps * 8 + 256 <= kHdr, "fold kernel header overflow");
+    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 step parities][16 groups of 32 positions][3] (fold_kw)
+    constexpr uint32_t kHdr = 2176;
+    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + 2 * 16 * 3 * 4 <= kHdr, "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
@@ -786,6 +789,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const size_t zstride = (size_t)L.Hout * L.Wout;
         const int nchunk = (L.cout_group + 7) >> 3;
         uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
+        uint32_t estep = 0;              // steps drained so far (parity selects the edge-exchange buffer)
         long long epi_wait = 0, epi_work = 0;
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b, x0, y0, zs, T;
@@ -830,6 +834,40 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(blk));
                 const size_t zoff = (size_t)(zs + e) * zstride;
+                if (L.fold_kw) {
+                    // columns 0..2 of the block are U_kw[p] = sum_{kh,ci} in[p + kh*P] w[kh,kw]; out[p] = U_0[p] + U_1[p+1] +
+                    // U_2[p+2].  p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the
+                    // first two lanes of the next group (another warp: TMEM lane quadrants are private), through shared
+                    // memory and one named barrier of the 8 epilogue warps per step.
+                    float *edge = s_edge + (estep & 1u) * 48;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int grp = (eset + 2 * i) * 4 + q;
+                        if (eset + 2 * i < MT && lane < 2) {
+                            if (lane == 0) edge[grp * 3 + 0] = __uint_as_float(r[i][1]);
+                            edge[grp * 3 + 1 + lane] = __uint_as_float(r[i][2]);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int mt = eset + 2 * i;
+                        if (mt >= MT) continue;  // warp-uniform
+                        const int ng = mt * 4 + q + 1;  // next group of 32 positions (none after the tile's last one)
+                        float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][1]), 1);
+                        float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2]), 2);
+                        if (lane >= 30) {
+                            const bool has = ng < MT * 4;
+                            if (lane == 31) v1 = has ? edge[ng * 3 + 0] : 0.f;
+                            v2 = has ? edge[ng * 3 + 1 + (lane - 30)] : 0.f;
+                        }
+                        if (!valid[i]) continue;
+                        float v = __uint_as_float(r[i][0]) + v1 + v2 + s_shift[0];
+                        if (L.relu) v = fmaxf(v, 0.f);
+                        reinterpret_cast<float *>(L.out)[(size_t)b * plane + base[i] + zoff] = v;
+                    }
+                    ++estep;
+                } else
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     if (eset + 2 * i >= MT || !valid[i]) continue;
@@ -920,6 +958,7 @@ struct WSrc {
 struct WPackParams {
     int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
     int fold_cw;  // > 0: depth-folded layout, B row n = (kd = 2 - n / fold_cw, cout = n % fold_cw); src taps are kh*3+kw
+    int fold_kw;  // 1: depth-folded layout with kw in N too: B row n = (kd = 2 - n / 16, kw = n % 16 < 3), Cout = 1; src taps are kh*3
     int merged_t; // 1: class-merged transposed conv, B row n = (class n / cout, cout n % cout); src taps are dz*4+dy*2+dx
     int ntaps;    // taps per (cout, cin) pair in the source weights: 27 (3-D) or 9 (2-D, [Cout][Cin][3][3])
     int f16;      // 1: fp16 output, 0: bf16
@@ -941,7 +980,13 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     const int cin = p.src[blk].cin0[c] + e;
     int co = g * p.cout_group + n;
     int nn = n;
-    if (p.fold_cw > 0) {
+    if (p.fold_cw > 0 && p.fold_kw) {
+        const int kw = n % p.fold_cw;
+        nn = 0;
+        co = 0;
+        if (kw >= 3) tap = -1;
+        else if (tap >= 0) tap += (2 - n / p.fold_cw) * 9 + kw;
+    } else if (p.fold_cw > 0) {
         nn = n % p.fold_cw;
         co = nn;
         if (tap >= 0) tap += (2 - n / p.fold_cw) * 9;
@@ -998,12 +1043,15 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // depth-folded variant (conv3d_tc_fold_kernel): stride-1 layers whose Cout fits one 16-column block
     static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
     const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
+    static const bool nofoldkw = getenv("MVS_TC_NOFOLDKW") != nullptr;  // A/B knob
+    const bool fold_kw = fold && cin == 8 && cout == 1 && !nofoldkw;
     const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
     // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
     static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
     const bool merged_t = (kind == TC_CONVT) && cin >= 16 && 8 * cout <= 128 && !nomerge;
     int ntaps_ops;  // MMA instructions per step
     if (merged_t) ntaps_ops = 8 * kpairs_tap;
+    else if (fold_kw) ntaps_ops = 2;
     else if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
     else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
     else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
@@ -1043,7 +1091,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
-                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 512;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -1110,6 +1158,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.npad = npad; W.cout_group = cout_group; W.cout_total = cout; W.cin_total = cin; W.ngroups = ngroups;
     W.transposed = (kind == TC_CONVT);
     W.fold_cw = fold ? 16 : 0;
+    W.fold_kw = fold_kw ? 1 : 0;
+    L.fold_kw = fold_kw ? 1 : 0;
     W.ntaps = is2d ? 9 : 27;
     W.merged_t = merged_t ? 1 : 0;
     L.merged_t = merged_t ? 1 : 0;
@@ -1139,6 +1189,15 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
                             W.src[nops] = WSrc{{(int16_t)tap, (int16_t)tap}, {(int16_t)(16 * kc), (int16_t)(16 * kc + 8)}};
                             ++nops;
                         }
+            } else if (fold_kw) {  // K = (kh, 8 channels): kh = 0,1 in one instruction, kh = 2 (+ a zero chunk) in the other
+                for (int i = 0; i < 2; ++i) {
+                    TcOp &op = L.ops[nops];
+                    op.a_off = tap_off(2 * i, 0);
+                    op.lbo = (i == 0) ? tap_off(1, 0) - tap_off(0, 0) : 0;
+                    op.widx = nops; op.plane_rel = kd; op.acc = 0;
+                    W.src[nops] = WSrc{{(int16_t)(6 * i), (int16_t)(i == 0 ? 3 : -1)}, {0, 0}};
+                    ++nops;
+                }
             } else {  // cin == 8: one K=16 instruction covers two taps of the same plane (sorted by offset)
                 int order[9];
                 for (int i = 0; i < 9; ++i) order[i] = i;
@@ -1231,7 +1290,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     }
     pl.npad = npad;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
-    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024;
+    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 512;
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 

@@ -1043,7 +1043,7 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
 // Internal: same op, output written as bf16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
 namespace mvs {
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, cudaStream_t st);
+                          int H, int W, int half_sums, cudaStream_t st);
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st);
 int features_nhwc16_to_rcp8(const void *fea16, void *tex16, int N, int H, int W, cudaStream_t st);
 static int warp_generation() {
@@ -1064,7 +1064,7 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
         if (nsrc > 0)
             if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
         if (int rc = features_nchw_to_rcp8(fea, tex16, B * V, H, W, st)) return rc;
-        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
     }
     // fp32 features in: fp32 texels and the reference's exact fp32 arithmetic by default (only the stored volume is
     // bf16).  MVS_TEXEL_FMT=fp16|bf16 converts the source views to 16-bit texels first (tuning knob; the production
@@ -1115,11 +1115,11 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
 
 // fp16 RCP8 features of all V views in ([B*V][H][4][W][8], what the tensor-core FeatureNet writes): no layout pass.
 int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
-                           int B, int V, int D, int H, int W, cudaStream_t st) {
+                           int B, int V, int D, int H, int W, int half_sums, cudaStream_t st) {
     float *rt = (float *)workspace;
     if (V > 1)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, half_sums, st);
 }
 
 // fp16 channels-last features of all V views in ([B][V][H*W][32]), bf16 CP8 volume out: no layout pre-pass at all.
@@ -1132,7 +1132,7 @@ int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *dep
     if (warp_generation() == 3) {
         void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
         if (int rc = features_nhwc16_to_rcp8(fea16, tex16, B * V, H, W, st)) return rc;
-        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
     }
     const int dchunk = pick_dchunk(B, D, H, W);
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));

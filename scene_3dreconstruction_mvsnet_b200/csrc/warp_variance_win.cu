@@ -435,8 +435,10 @@ int launch_win(const void *tex16, const float *rt, const float *depth_values, vo
 }  // namespace
 
 // tex16: fp16 RCP8 features of all views [B*V][H][4][W][8].  Asynchronous on st.
+// half_sums: packed-half sums of deviations from the reference view (faster; relative error of large variances up to
+// 2^-6) instead of fp32 sums of the warped values (2^-7 everywhere, the tolerance stated for the tensor-core mode).
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, cudaStream_t st) {
+                          int H, int W, int half_sums, cudaStream_t st) {
     static const int cfg = [] {
         const char *e = getenv("MVS_WIN_CONFIG");  // tuning knob: 0 = 32x8 tile, 2 CTAs/SM; 1 = 64x8 tile, 1 CTA/SM
         return e ? atoi(e) : 0;
@@ -445,11 +447,11 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
     if (const char *e = getenv("MVS_WARP_DCHUNK")) dchunk = std::max(1, std::min(32, atoi(e)));
     while ((long long)B * cdiv(D, dchunk) > 65535 && dchunk < 32) dchunk <<= 1;
     MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
-    // MVS_WIN_ACC32=1: running sums of the warped values themselves in fp32 (the first formulation) instead of packed-half
-    // sums of deviations from the reference view
-    static const bool acc32 = getenv("MVS_WIN_ACC32") != nullptr;
+    // MVS_WIN_HACC=0/1 overrides the caller's choice (tools/win_tune.py)
+    static const int force = [] { const char *e = getenv("MVS_WIN_HACC"); return e ? atoi(e) : -1; }();
+    const bool hacc = force >= 0 ? force != 0 : half_sums != 0;
     if (cfg == 1) return launch_win<2, 8, 80, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 227 * 1024, st);
-    if (acc32) return launch_win<1, 8, 40, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
+    if (!hacc) return launch_win<1, 8, 40, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
     return launch_win<1, 8, 40, true>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
 }
 

@@ -246,3 +246,52 @@ def test_uint8_images_equal_float_images(weights):
             b = m(f32.to(DEV), proj.to(DEV), dv.to(DEV))
         assert torch.equal(a["depth"], b["depth"]), "%s: max diff %g" % (precision, (a["depth"] - b["depth"]).abs().max().item())
         assert torch.equal(a["photometric_confidence"], b["photometric_confidence"]), precision
+
+
+# ------------------------------------------------------------------------------------------------ full size (C2)
+def _to_rcp8(fea):
+    """[B,V,32,h,w] -> ops.Rcp8Features (fp16 [B*V][h][4][w][8]), the layout the tensor-core FeatureNet writes."""
+    B, V, C, h, w = fea.shape
+    t = fea.half().view(B * V, 4, 8, h, w).permute(0, 3, 1, 4, 2).contiguous()
+    return ops.Rcp8Features(t, B, V, h, w)
+
+
+@pytest.mark.parametrize("half_sums", [False, True])
+def test_full_size_c2_window_kernel_matches_strict_kernel(half_sums):
+    """DTU eval shape (5 views, 288x400 feature maps, D=192): the TMA-window kernel against the strict fp32 kernel
+    (itself pinned to the oracle at small sizes) on the same fp16-rounded features.  Covers every tile / depth-chunk /
+    window-segment combination of the benchmark geometry (708 M voxels x channels).  Tolerance: the one stated for the
+    tensor-core mode (2^-7 |ref| + 8e-3) with fp32 sums; with packed-half deviation sums ("fast" mode) large variances
+    carry fp16 rounding of d^2 and their sum: 2^-6 |ref| + 8e-3."""
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    B, V, h, w, D = 1, 5, 288, 400, 192
+    fea = synth.make_features(B, V, 32, h, w, seed=4).half().float()
+    _, proj, dv = synth.make_named("c2_dtu_5view_1152x1600")
+    cp8 = ops.warp_variance_cp8(_to_rcp8(fea.to(DEV)), proj.to(DEV), dv.to(DEV), half_sums=half_sums)
+    ref = ops.warp_variance(fea.to(DEV), proj.to(DEV), dv.to(DEV))
+    got = cp8.permute(0, 1, 5, 2, 3, 4).reshape(B, 32, D, h, w).float()
+    err = (got - ref).abs()
+    tol = ref.abs() * (2.0 ** -6 if half_sums else 2.0 ** -7) + 8e-3
+    assert bool((err <= tol).all()), "max err %.4g, max err/tol %.3f" % (err.max().item(), (err / tol).max().item())
+    assert err.mean().item() < 1.5e-3
+
+
+def test_full_size_c2_forward_properties(weights):
+    """DTU eval shape through MVSNet.forward in the tensor-core mode: deterministic, depth inside the hypothesis
+    range, confidence in [0, 1], and close to the strict-fp32 mode within the stated tolerance."""
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    imgs, proj, dv = (t.to(DEV) for t in synth.make_named("c2_dtu_5view_1152x1600"))
+    m = load_model(weights, precision="bf16")
+    with torch.no_grad():
+        a = m(imgs, proj, dv)
+        b = m(imgs, proj, dv)
+        s = load_model(weights, precision="fp32")(imgs, proj, dv)
+    assert torch.equal(a["depth"], b["depth"]) and torch.equal(a["photometric_confidence"], b["photometric_confidence"])
+    assert a["depth"].shape == (1, 288, 400)
+    assert float(a["depth"].min()) >= float(dv.min()) - 1e-2 and float(a["depth"].max()) <= float(dv.max()) + 1e-2
+    c = a["photometric_confidence"]
+    assert float(c.min()) >= 0 and float(c.max()) <= 1 + 1e-5
+    rng = float(dv.max() - dv.min())
+    assert float((a["depth"] - s["depth"]).abs().mean()) < 2e-3 * rng
+    assert float((a["depth"] - s["depth"]).abs().max()) < 2e-2 * rng

@@ -22,13 +22,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         return e0.elapsed_time(e1) / n
     a = t(lambda: ops.warp_variance_cp8(fea16, proj, dv))
     b = t(lambda: ops.warp_variance_cp8(fea, proj, dv))
-    print("gen=%s cfg=%s acc32=%s dchunk=%s yaw=%g: fp16-nhwc in %.3f ms, fp32-nchw in %.3f ms (layout pass included)" % (
-        os.environ.get("MVS_WARP_GEN", "3"), os.environ.get("MVS_WIN_CONFIG", "0"), os.environ.get("MVS_WIN_ACC32", "0"),
+    print("gen=%s cfg=%s hacc=%s dchunk=%s yaw=%g: fp16-nhwc in %.3f ms, fp32-nchw in %.3f ms (layout pass included)" % (
+        os.environ.get("MVS_WARP_GEN", "3"), os.environ.get("MVS_WIN_CONFIG", "0"), os.environ.get("MVS_WIN_HACC", "default"),
         os.environ.get("MVS_WARP_DCHUNK", "16"), yaw, a, b),
         flush=True)
 else:
     yaw = sys.argv[1] if len(sys.argv) > 1 else "0"
-    runs = [dict(MVS_WARP_GEN="2"), dict(MVS_WIN_ACC32="1"), dict(MVS_WIN_CONFIG="1")]
+    runs = [dict(MVS_WARP_GEN="2"), dict(MVS_WIN_HACC="1"), dict(MVS_WIN_CONFIG="1")]
     for dc in ("8", "16", "32"):
         runs.append(dict(MVS_WARP_DCHUNK=dc))
     for r in runs:
