@@ -632,7 +632,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
     float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
-    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 step parities][16 groups of 32 positions][3] (fold_kw)
+    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 epilogue sets][16 groups of 32 positions][3] (fold_kw)
     constexpr uint32_t kHdr = 2176;
     static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + 2 * 16 * 3 * 4 <= kHdr, "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
@@ -642,8 +642,13 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = L.MT;
-    const int R = L.fold_R;                 // accumulator blocks per M-tile
-    const uint32_t cols_mt = R * CW;        // TMEM columns per M-tile
+    // Accumulator blocks per M-tile: PB physical blocks hold a ring of R = PB - 2 logical blocks.  The window of step j
+    // is always the physical blocks [p, p+1, p+2], p = logical ring position of its first block, so it never wraps: when
+    // p = R-2 or R-1 its tail lands in the two extra blocks R, R+1, which are "mirrors" of logical blocks 0 and 1 -- the
+    // epilogue adds a mirror to its block when it drains it.  One MMA per op and M-tile in every step.
+    const int PB = L.fold_R;
+    const int R = PB - 2;
+    const uint32_t cols_mt = PB * CW;       // TMEM columns per M-tile
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)MT * cols_mt) tmem_cols <<= 1;
 
@@ -662,7 +667,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         }
         for (int b = 0; b < R; ++b) {
             ptx::mbar_init(tfull_bar(b), 1);
-            ptx::mbar_init(tempty_bar(b), 8);
+            ptx::mbar_init(tempty_bar(b), 4);  // the 4 quadrant warps of the epilogue set that drains the block
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmap);
@@ -750,22 +755,17 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 }
                 if (first_touch) epar ^= 1u << ft_blk;
                 ptx::tcgen05_fence_after();
-                const uint32_t p0 = wrapR(pj + k0);
                 const int cnt = k1 - k0 + 1;
-                const int len0 = min(cnt, (int)(uR - p0));
                 if (leader) {
                     const long long ci = clock64();
                     const uint32_t sb = (ring_base + slot * L.slot_bytes) >> 4;
-                    for (int pass = 0; pass < 2; ++pass) {
-                        if (pass == 1 && len0 == cnt) break;  // no wrap: one pass
-                        const uint32_t d = tmem_base + (pass == 0 ? p0 * CW : 0);
-                        const uint32_t brow = (pass == 0 ? k0 : k0 + len0) * CW;
-                        const uint32_t idesc = ptx::make_idesc_bf16_m128((pass == 0 ? len0 : cnt - len0) * CW);
-                        if (MT == 4) issue_fold_pass<4>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                        else if (MT == 3) issue_fold_pass<3>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                        else if (MT == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                        else issue_fold_pass<1>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                    }
+                    const uint32_t d = tmem_base + (pj + k0) * CW;  // physical window start: never wraps (mirror blocks)
+                    const uint32_t brow = k0 * CW;
+                    const uint32_t idesc = ptx::make_idesc_bf16_m128(cnt * CW);
+                    if (MT == 4) issue_fold_pass<4>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                    else if (MT == 3) issue_fold_pass<3>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                    else if (MT == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                    else issue_fold_pass<1>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
                     t_issue += clock64() - ci;
                     ptx::tcgen05_commit(empty_bar(slot));
                     if (j >= 2) ptx::tcgen05_commit(tfull_bar(pj));  // output plane zs + j - 2 is complete
@@ -782,119 +782,177 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             L.dbg[blockIdx.x * 12 + 5] = g;
         }
     } else {
-        // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating over the M-tiles =================
+        // ================= epilogue: 8 warps = 2 sets of 4 TMEM lane quadrants =================
+        // The two sets alternate over the OUTPUT PLANES: set e drains every other completed accumulator block, all M-tiles of
+        // its quadrant, so the fixed costs of a drain (barrier wait, tcgen05.ld / st round trips, release) are paid once per
+        // plane and quadrant and two planes are in the epilogue at any time.
         const int q = warp & 3;
         const int eset = (warp - 2) >> 2;
         const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
         const size_t zstride = (size_t)L.Hout * L.Wout;
         const int nchunk = (L.cout_group + 7) >> 3;
+        const bool kwf = L.fold_kw != 0;
         uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
-        uint32_t estep = 0;              // steps drained so far (parity selects the edge-exchange buffer)
+        uint32_t estep = 0;              // output planes seen so far (parity: which set drains it)
         long long epi_wait = 0, epi_work = 0;
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
-            size_t base[2] = {0, 0};
-            bool valid[2] = {false, false};
+            size_t base[4] = {0, 0, 0, 0};
+            uint32_t vmask = 0;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int mt = eset + 2 * i;
+            for (int mt = 0; mt < 4; ++mt) {
                 if (mt < MT) {
                     const int pos = mt * 128 + q * 32 + lane;
                     const int y = pos / L.P, x = pos - y * L.P;
-                    valid[i] = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
-                    base[i] = (size_t)(y0 + y) * L.Wout + (size_t)(x0 + x);
+                    if ((y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt)) vmask |= 1u << mt;
+                    base[mt] = (size_t)(y0 + y) * L.Wout + (size_t)(x0 + x);
                 }
             }
-            for (int e = 0; e < T; ++e) {
+            for (int e = 0; e < T; ++e, ++estep) {
+                const uint32_t myblk = blk;
+                if (++blk == (uint32_t)R) blk = 0;
+                if ((estep & 1u) != (uint32_t)eset) continue;  // the other set's plane
                 const long long c0 = clock64();
-                ptx::mbar_wait(tfull_bar(blk), (fpar >> blk) & 1u);
-                fpar ^= 1u << blk;
+                ptx::mbar_wait(tfull_bar(myblk), (fpar >> myblk) & 1u);
+                fpar ^= 1u << myblk;
                 const long long c1 = clock64();
                 epi_wait += c1 - c0;
                 ptx::tcgen05_fence_after();
-                const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + blk * CW;
-                uint32_t r[2][CW];
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int mt = eset + 2 * i;
-                    if (mt < MT) {
-#pragma unroll
-                        for (int c8 = 0; c8 < CW / 8; ++c8)
-                            if (c8 < nchunk) ptx::tmem_ld_x8(tb + mt * cols_mt + c8 * 8, &r[i][c8 * 8]);
-                    }
-                }
-                ptx::tmem_ld_wait();
-                // values are in registers: zero the block for its next use and hand it back
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-                    if (eset + 2 * i < MT) ptx::tmem_st_zero_x16(tb + (eset + 2 * i) * cols_mt);
-                ptx::tmem_st_wait();
-                ptx::tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(blk));
+                const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + myblk * CW;
+                const bool mirrored = myblk < 2;  // logical blocks 0 and 1 have a second part in physical blocks R, R+1
                 const size_t zoff = (size_t)(zs + e) * zstride;
-                if (L.fold_kw) {
-                    // columns 0..2 of the block are U_kw[p] = sum_{kh,ci} in[p + kh*P] w[kh,kw]; out[p] = U_0[p] + U_1[p+1] +
-                    // U_2[p+2].  p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the
-                    // first two lanes of the next group (another warp: TMEM lane quadrants are private), through shared
-                    // memory and one named barrier of the 8 epilogue warps per step.
-                    float *edge = s_edge + (estep & 1u) * 48;
+                if (kwf) {
+                    // prob layer (Cout = 1, kw folded into N): only columns 0..2 of a block are ever non-zero
+                    uint32_t r[4][4];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int grp = (eset + 2 * i) * 4 + q;
-                        if (eset + 2 * i < MT && lane < 2) {
-                            if (lane == 0) edge[grp * 3 + 0] = __uint_as_float(r[i][1]);
-                            edge[grp * 3 + 1 + lane] = __uint_as_float(r[i][2]);
-                        }
+                    for (int mt = 0; mt < 4; ++mt)
+                        if (mt < MT) ptx::tmem_ld_x4(tb + mt * cols_mt, r[mt]);
+                    ptx::tmem_ld_wait();
+                    if (mirrored) {
+                        uint32_t r2[4][4];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+                            if (mt < MT) ptx::tmem_ld_x4(tb + R * CW + mt * cols_mt, r2[mt]);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) r[mt][k] = __float_as_uint(__uint_as_float(r[mt][k]) + __uint_as_float(r2[mt][k]));
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int mt = eset + 2 * i;
+                    for (int mt = 0; mt < 4; ++mt)
+                        if (mt < MT) {
+                            ptx::tmem_st_zero_x4(tb + mt * cols_mt);
+                            if (mirrored) ptx::tmem_st_zero_x4(tb + R * CW + mt * cols_mt);
+                        }
+                    ptx::tmem_st_wait();
+                    ptx::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
+                    // columns 0..2 are U_kw[p] = sum_{kh,ci} in[p + kh*P] w[kh,kw]; out[p] = U_0[p] + U_1[p+1] + U_2[p+2].
+                    // p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the first two
+                    // lanes of the next group (another warp of this set: TMEM lane quadrants are private), through shared
+                    // memory and one named barrier of the set's 4 warps per plane.
+                    float *edge = s_edge + eset * 48;
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+                        if (mt < MT && lane < 2) {
+                            const int grp = mt * 4 + q;
+                            if (lane == 0) edge[grp * 3 + 0] = __uint_as_float(r[mt][1]);
+                            edge[grp * 3 + 1 + lane] = __uint_as_float(r[mt][2]);
+                        }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
                         if (mt >= MT) continue;  // warp-uniform
                         const int ng = mt * 4 + q + 1;  // next group of 32 positions (none after the tile's last one)
-                        float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][1]), 1);
-                        float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2]), 2);
+                        float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][1]), 1);
+                        float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][2]), 2);
                         if (lane >= 30) {
                             const bool has = ng < MT * 4;
                             if (lane == 31) v1 = has ? edge[ng * 3 + 0] : 0.f;
                             v2 = has ? edge[ng * 3 + 1 + (lane - 30)] : 0.f;
                         }
-                        if (!valid[i]) continue;
-                        float v = __uint_as_float(r[i][0]) + v1 + v2 + s_shift[0];
+                        if (!((vmask >> mt) & 1u)) continue;
+                        float v = __uint_as_float(r[mt][0]) + v1 + v2 + s_shift[0];
                         if (L.relu) v = fmaxf(v, 0.f);
-                        reinterpret_cast<float *>(L.out)[(size_t)b * plane + base[i] + zoff] = v;
+                        reinterpret_cast<float *>(L.out)[(size_t)b * plane + base[mt] + zoff] = v;
                     }
-                    ++estep;
-                } else
+                    // the set's next plane reuses the edge buffer: everyone must have read this plane's edges first
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+                } else {
+                    // M-tiles in pairs: 2 x CW accumulator registers at a time
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    if (eset + 2 * i >= MT || !valid[i]) continue;
-                    const size_t vox = base[i] + zoff;
+                    for (int m0 = 0; m0 < 4; m0 += 2) {
+                        if (m0 >= MT) break;  // warp-uniform
+                        uint32_t r[2][CW];
 #pragma unroll
-                    for (int c8 = 0; c8 < CW / 8; ++c8) {
-                        if (c8 >= nchunk) break;
-                        float v[8];
+                        for (int i = 0; i < 2; ++i)
+                            if (m0 + i < MT) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            v[k] = __uint_as_float(r[i][c8 * 8 + k]) + s_shift[c8 * 8 + k];
-                            if (L.relu) v[k] = fmaxf(v[k], 0.f);
+                                for (int c8 = 0; c8 < CW / 8; ++c8)
+                                    if (c8 < nchunk) ptx::tmem_ld_x8(tb + (m0 + i) * cols_mt + c8 * 8, &r[i][c8 * 8]);
+                            }
+                        ptx::tmem_ld_wait();
+                        if (mirrored) {
+                            uint32_t r2[2][CW];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                if (m0 + i < MT) {
+#pragma unroll
+                                    for (int c8 = 0; c8 < CW / 8; ++c8)
+                                        if (c8 < nchunk) ptx::tmem_ld_x8(tb + R * CW + (m0 + i) * cols_mt + c8 * 8, &r2[i][c8 * 8]);
+                                }
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int k = 0; k < CW; ++k)
+                                    if (k < 8 * nchunk) r[i][k] = __float_as_uint(__uint_as_float(r[i][k]) + __uint_as_float(r2[i][k]));
                         }
-                        if (L.out_f32) {
-                            reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
-                        } else {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[0], v[1]);
-                            pk.y = pack_bf16x2(v[2], v[3]);
-                            pk.z = pack_bf16x2(v[4], v[5]);
-                            pk.w = pack_bf16x2(v[6], v[7]);
-                            reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + c8) * plane + vox] = pk;
+                        // values are in registers: zero the block (and its mirror) for its next use
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (m0 + i < MT) {
+                                ptx::tmem_st_zero_x16(tb + (m0 + i) * cols_mt);
+                                if (mirrored) ptx::tmem_st_zero_x16(tb + R * CW + (m0 + i) * cols_mt);
+                            }
+                        if (m0 + 2 >= MT) {  // last pair: hand the block back
+                            ptx::tmem_st_wait();
+                            ptx::tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const int mt = m0 + i;
+                            if (mt >= MT || !((vmask >> mt) & 1u)) continue;
+                            const size_t vox = base[mt] + zoff;
+#pragma unroll
+                            for (int c8 = 0; c8 < CW / 8; ++c8) {
+                                if (c8 >= nchunk) break;
+                                float v[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    v[k] = __uint_as_float(r[i][c8 * 8 + k]) + s_shift[c8 * 8 + k];
+                                    if (L.relu) v[k] = fmaxf(v[k], 0.f);
+                                }
+                                if (L.out_f32) {
+                                    reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
+                                } else {
+                                    uint4 pk;
+                                    pk.x = pack_bf16x2(v[0], v[1]);
+                                    pk.y = pack_bf16x2(v[2], v[3]);
+                                    pk.z = pack_bf16x2(v[4], v[5]);
+                                    pk.w = pack_bf16x2(v[6], v[7]);
+                                    reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + c8) * plane + vox] = pk;
+                                }
+                            }
                         }
                     }
                 }
                 epi_work += clock64() - c1;
-                if (++blk == (uint32_t)R) blk = 0;
             }
             blk = (blk + 2) % R;  // the two lead-in blocks of the next item are never drained
         }

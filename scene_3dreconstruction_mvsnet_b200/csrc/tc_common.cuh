@@ -134,6 +134,11 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t *r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // zero 16 consecutive columns of this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr) {
@@ -153,6 +158,10 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t *r) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                  "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st_zero_x4(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
