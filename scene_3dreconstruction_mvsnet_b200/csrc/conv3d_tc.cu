@@ -632,9 +632,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
     float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
-    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 epilogue sets][16 groups of 32 positions][3] (fold_kw)
-    constexpr uint32_t kHdr = 2176;
-    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + 2 * 16 * 3 * 4 <= kHdr, "fold kernel header overflow");
+    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 epilogue sets][2 parities][16 groups of 32 positions][3] (fold_kw)
+    constexpr uint32_t kHdr = 2432;
+    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + 2 * 2 * 16 * 3 * 4 <= kHdr, "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
@@ -854,7 +854,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     // p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the first two
                     // lanes of the next group (another warp of this set: TMEM lane quadrants are private), through shared
                     // memory and one named barrier of the set's 4 warps per plane.
-                    float *edge = s_edge + eset * 48;
+                    float *edge = s_edge + (eset * 2 + ((estep >> 1) & 1u)) * 48;  // double-buffered per set: one barrier per plane
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (mt < MT && lane < 2) {
@@ -879,8 +879,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                         if (L.relu) v = fmaxf(v, 0.f);
                         reinterpret_cast<float *>(L.out)[(size_t)b * plane + base[mt] + zoff] = v;
                     }
-                    // the set's next plane reuses the edge buffer: everyone must have read this plane's edges first
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
                 } else {
                     // M-tiles in pairs: 2 x CW accumulator registers at a time
 #pragma unroll
@@ -1149,7 +1147,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
-                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 512;
+                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -1348,7 +1346,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     }
     pl.npad = npad;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
-    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 512;
+    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768;
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
