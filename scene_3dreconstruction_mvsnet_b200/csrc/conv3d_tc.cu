@@ -598,9 +598,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 // CW-column blocks of a ring of R blocks in TMEM (per M-tile), so the three contributions land in the right
 // accumulators by construction: same TMEM lane (= voxel), adjacent column blocks.  Every instruction accumulates:
 // the epilogue zeroes a block (tcgen05.st) right after draining it, so the issue loop stays as lean as the
-// output-stationary one (one descriptor add per MMA, everything else loop-invariant).  A window that wraps around
-// the ring is issued as two passes over the op table; partial windows at the ends of a z-segment are a B-row
-// offset plus a smaller N.  An output plane is complete -- and handed to the epilogue through its own mbarrier --
+// output-stationary one (one descriptor add per MMA, everything else loop-invariant).  Windows never wrap: the ring
+// of R logical blocks lives in R+2 physical blocks (see the kernel); partial windows at the ends of a z-segment are a
+// B-row offset plus a smaller N.  An output plane is complete -- and handed to the epilogue through its own mbarrier --
 // one step after its centre plane.  Each input plane is used by exactly one step, so the plane ring is pure TMA
 // prefetch depth.
 // ------------------------------------------------------------------------------------------------
