@@ -259,6 +259,14 @@ def run_ours(args):
         vol_elem = 4 if args.precision == "fp32" else 2
         alg_bytes = vol_elem * 32 * D * h * w + 4 * V * 32 * h * w
         achieved = alg_bytes / (wv_ms * 1e-3) / 1e9 if wv_ms else None
+        # DRAM bytes per launch of the same kernel at the same shape, from the committed ncu capture (not measured live)
+        traffic = {}
+        if args.workload == "c2_dtu_5view_1152x1600":
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+                    traffic = json.load(f).get(args.precision, {}) or {}
+            except (OSError, ValueError):
+                traffic = {}
         cr_ms = stage_ms.get("cost_regularization")
         flops = 20304.0 * D * h * w
         line = {
@@ -289,7 +297,8 @@ def run_ours(args):
             "roofline": {"kernel": ("warp_variance_fwd2_kernel" if args.precision == "fp32" else "warp_variance_win_kernel") +
                                    " (+ homography compose and feature layout pre-passes, ~2% of the stage)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak if achieved else None, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / hbm_peak if achieved else None, "traffic": traffic.get("dram_bytes"),
+                         "traffic_source": traffic.get("capture"), "peak_kind": peak_kind,
                          "algorithmic_bytes": alg_bytes, "ms": wv_ms},
             "roofline_costreg": {"kernel": "CostRegNet (11 fused conv launches)", "flop": flops, "ms": cr_ms,
                                  "achieved": flops / (cr_ms * 1e-3) / 1e12 if cr_ms else None, "unit": "TFLOP/s",
