@@ -325,9 +325,9 @@ warp_volume_fwd_kernel(const float *__restrict__ fea,       // [B,V,32,H,W]; vie
 // index + the two clamp-aware increments in bits 30/31): LDS.128 + LDS.32 = 5 wavefronts; the four
 // weights are re-formed with 4 multiplies per step.  Masking the factors instead of the products
 // gives bit-identical weights (a product with a zeroed factor is the zero the mask would write).
-// OUT_CP8 writes the volume directly as bf16 [32/8][D][H][W][8] (the tensor-core CostRegNet's input
-// layout), pairing even/odd channel-group lanes with shuffles so that every store is a full 16-byte
-// voxel chunk: the fp32 volume and its conversion pass disappear and the HBM write halves.
+// This is the strict-fp32 kernel (fp32 texels, the reference's operation order, fp32 NCDHW volume); the
+// tensor-core precision modes use the TMA-window kernel of warp_variance_win.cu, which superseded the
+// 16-bit-texel variants of this generation (1.66 ms) at 1.06-1.14 ms.
 // ------------------------------------------------------------------------------------------------
 struct PackedTap {
     float4 f;       // ax, bx, ay, by  (zeroed where the corresponding column / row is out of range)
@@ -395,43 +395,14 @@ __device__ __forceinline__ PackedTap sample_packed_r(float rx, float ry, float r
     return t;
 }
 
-// Reduced-precision-mode variant of the position arithmetic: the same map with the two normalisations folded into
-// one FMA (ix = px * W/(W-1) - 0.5, the reference's align_corners mismatch in closed form) and approximate
-// reciprocal division.  Differs from the exact chain by ~1e-7 relative (1e-4 texel), far below the fp16 texel
-// quantisation of the mode that uses it; the coordinate pass drops from ~150 to ~55 instructions.
-__device__ __forceinline__ PackedTap sample_packed_fast(float rx, float ry, float rz, float tx, float ty, float tz, float d,
-                                                        float sx, float sy, int H, int W) {
-    const float qx = fmaf(rx, d, tx), qy = fmaf(ry, d, ty), qz = fmaf(rz, d, tz);
-    const float iz = __frcp_rn(qz);
-    const float ix = safe_coord(fmaf(qx * iz, sx, -0.5f));
-    const float iy = safe_coord(fmaf(qy * iz, sy, -0.5f));
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
-    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
-    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
-    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
-    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
-    const float bx = ix - fx0, by = iy - fy0;
-    PackedTap t;
-    t.f.x = vx0 ? 1.0f - bx : 0.f;
-    t.f.y = vx1 ? bx : 0.f;
-    t.f.z = vy0 ? 1.0f - by : 0.f;
-    t.f.w = vy1 ? by : 0.f;
-    t.base = (uint32_t)(cy0 * W + cx0) | ((uint32_t)(cx1 != cx0) << 30) | ((uint32_t)(cy1 != cy0) << 31);
-    return t;
-}
-
 constexpr int kMaxSrcSmem = 8;  // source views whose per-pixel rotation terms are kept in shared memory
 
-enum { OUT_F32 = 0, OUT_CP8 = 1 };
-
-template <int OUT>
 __global__ void __launch_bounds__(kThreads, 2)
 warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W]; view 0 = reference view
                           const float4 *__restrict__ src_cl,     // [B*nsrc][H*W][8] float4, channels-last
                           const float *__restrict__ rt,          // [B*nsrc][12]
                           const float *__restrict__ depth_values,  // [B,D]
-                          void *__restrict__ out_,               // OUT_F32: [B,32,D,H,W] fp32; OUT_CP8: bf16 [B,4,D,H,W,8]
+                          float *__restrict__ out,               // [B,32,D,H,W] fp32
                           int V, int nsrc, int D, int H, int W, int dchunk) {
     // Work mapping: a warp owns one 32-pixel row segment and walks `dchunk` consecutive depth planes (measured
     // best among row-/plane-major variants, tools/warp_tune.py).  Everything that does not depend on the plane is
@@ -456,7 +427,6 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
     const float invV = 1.0f / (float)V;
     const float xl = (float)(x0 + lane), yf = (float)y;
     const int W8 = W * 8;  // float4 units per texel row
-    const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
     const int nsm = min(nsrc, kMaxSrcSmem);
     if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
     for (int v = 0; v < nsm; ++v) {
@@ -494,20 +464,10 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
 
         for (int v = 0; v < nsrc; ++v) {
             const int n = b * nsrc + v;
-            PackedTap t;
-            if (OUT == OUT_CP8 && v < kMaxSrcSmem) {
-                // bf16-volume mode: closed-form coordinates (1e-7 relative from the reference's chain, invisible after the
-                // bf16 rounding of the stored variance) and the four tap weights formed once per pixel
-                t = sample_packed_fast(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0],
-                                       s_t[v][1], s_t[v][2], dep, sx, sy, H, W);
-                t.f = make_float4(t.f.x * t.f.z, t.f.y * t.f.z, t.f.x * t.f.w, t.f.y * t.f.w);
-            } else if (v < kMaxSrcSmem) {
-                t = sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0], s_t[v][1],
-                                    s_t[v][2], dep, H, W);
-            } else {
-                t = sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
-                if (OUT == OUT_CP8) t.f = make_float4(t.f.x * t.f.z, t.f.y * t.f.z, t.f.x * t.f.w, t.f.y * t.f.w);
-            }
+            const PackedTap t = (v < kMaxSrcSmem)
+                                    ? sample_packed_r(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane],
+                                                      s_t[v][0], s_t[v][1], s_t[v][2], dep, H, W)
+                                    : sample_packed(rt + (size_t)n * 12, xl, yf, dep, H, W);
             __syncwarp();
             s_f[warp][lane] = t.f;
             s_b[warp][lane] = t.base;
@@ -521,8 +481,7 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
                 const float4 *p01 = p00 + ((bb >> 30) & 1u) * 8;
                 const int dyo = (bb >> 31) ? W8 : 0;
                 const float4 a = __ldg(p00), bq = __ldg(p01), c = __ldg(p00 + dyo), dq = __ldg(p01 + dyo);
-                const float w00 = (OUT == OUT_CP8) ? fc.x : fc.x * fc.z, w01 = (OUT == OUT_CP8) ? fc.y : fc.y * fc.z;
-                const float w10 = (OUT == OUT_CP8) ? fc.z : fc.x * fc.w, w11 = (OUT == OUT_CP8) ? fc.w : fc.y * fc.w;
+                const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
                 const float vx = fmaf(dq.x, w11, fmaf(c.x, w10, fmaf(bq.x, w01, a.x * w00)));
                 const float vy = fmaf(dq.y, w11, fmaf(c.y, w10, fmaf(bq.y, w01, a.y * w00)));
                 const float vz = fmaf(dq.z, w11, fmaf(c.z, w10, fmaf(bq.z, w01, a.z * w00)));
@@ -534,8 +493,7 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
             }
         }
 
-        if (OUT == OUT_F32) {
-            float *out = reinterpret_cast<float *>(out_);
+        {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float r[8];
@@ -554,258 +512,11 @@ warp_variance_fwd2_kernel(const float *__restrict__ fea,        // [B,V,32,H,W];
                         if (xr + i < W) o[i] = r[i];
                 }
             }
-        } else {
-            // bf16 chunk-planar output.  This lane holds channels 4g..4g+3 of 8 pixels; its partner (g ^ 1) holds
-            // the other half of the same 8-channel chunk.  Even-g lanes keep even pixels, odd-g lanes odd pixels.
-            uint4 *out = reinterpret_cast<uint4 *>(out_);
-            const int odd = g & 1;
-#pragma unroll
-            for (int i2 = 0; i2 < 4; ++i2) {
-                uint32_t mine[2], give[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ik = 2 * i2 + h;  // h == odd: the pixel this lane keeps
-                    float r[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float m = S[ik][j] * invV;
-                        r[j] = fmaf(Q[ik][j], invV, -m * m);
-                    }
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&lo), w1 = *reinterpret_cast<const uint32_t *>(&hi);
-                    if (h == 0) { mine[0] = w0; mine[1] = w1; } else { give[0] = w0; give[1] = w1; }
-                }
-                // even lane: keeps pixel 2*i2 (mine), gives pixel 2*i2+1 (give); odd lane: the opposite
-                const uint32_t k0 = odd ? give[0] : mine[0], k1 = odd ? give[1] : mine[1];
-                const uint32_t s0 = odd ? mine[0] : give[0], s1 = odd ? mine[1] : give[1];
-                const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                const int x = xr + 2 * i2 + odd;
-                if (x < W) {
-                    const uint4 pk = odd ? make_uint4(r0, r1, k0, k1) : make_uint4(k0, k1, r0, r1);
-                    out[(((size_t)b * 4 + (g >> 1)) * D + d) * HW + (size_t)y * W + x] = pk;
-                }
-            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// bf16-texel variant of the forward kernel (tensor-core precision mode only).  Source-view features are stored
-// channels-last in bf16 (64-byte texels), so one 16-byte load carries 8 channels: per (pixel, view) the taps cost
-// 4 x 16 B instead of 4 x 2 x 16 B in registers -- the L1 data pipe (the measured limiter) moves half the bytes,
-// and the coordinate exchange is amortised over 8 channels per lane instead of 4.  Lanes are (q = L/4, g = L%4):
-// the 8 q-groups take 8 CONSECUTIVE pixels per step, so a tap load of the warp touches ~8 adjacent texels
-// (4 x 128-byte lines), and thread (q, g) owns channel chunk g of pixels q, q+8, q+16, q+24 -- exactly one
-// 16-byte voxel chunk of the CP8 output per pixel, stored without any shuffle.  Interpolation and the Sum/Sum^2
-// accumulation stay in fp32; the reference view is read in fp32.
-// ------------------------------------------------------------------------------------------------
-template <bool FP16>
-__global__ void nchw_to_nhwc32_lp_kernel(const float *__restrict__ in, uint16_t *__restrict__ out, int HW, int nsrc, int V) {
-    __shared__ float tile[32][33];
-    const int n = blockIdx.y;
-    const int b = n / nsrc, v = n % nsrc + (V - nsrc);
-    const float *src = in + ((size_t)b * V + v) * kC * HW;
-    uint16_t *dst = out + (size_t)n * HW * kC;
-    const int p0 = blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int c = ty; c < 32; c += 8) tile[c][tx] = (p0 + tx < HW) ? src[(size_t)c * HW + p0 + tx] : 0.f;
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8)
-        if (p0 + r < HW) {
-            const float v = tile[tx][r];
-            if (FP16) dst[(size_t)(p0 + r) * kC + tx] = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
-            else dst[(size_t)(p0 + r) * kC + tx] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-        }
-}
-
-// reference view only: [B,V,32,HW] view 0 -> [B][HW][32] fp32
-__global__ void ref_to_nhwc32_kernel(const float *__restrict__ in, float *__restrict__ out, int HW, int V) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.y;
-    const float *src = in + (size_t)b * V * kC * HW;
-    float *dst = out + (size_t)b * HW * kC;
-    const int p0 = blockIdx.x * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int c = ty; c < 32; c += 8) tile[c][tx] = (p0 + tx < HW) ? src[(size_t)c * HW + p0 + tx] : 0.f;
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8)
-        if (p0 + r < HW) dst[(size_t)(p0 + r) * kC + tx] = tile[tx][r];
-}
-
-__device__ __forceinline__ void unpack_bf16x8(const uint4 v, float *f) {
-    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
-    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
-    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
-    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
-}
-
-// ALLV16: `src_cl` is one fp16 channels-last tensor holding ALL V views, [B][V][H*W][32] (what the fp16 FeatureNet
-// emits); view 0 doubles as the reference view and `ref_cl` is unused.
-template <bool FP16, bool ALLV16>
-__global__ void __launch_bounds__(kThreads, 2)
-warp_variance_bf16tex_kernel(const float4 *__restrict__ ref_cl,   // [B][H*W][8] float4 (fp32 channels-last reference view)
-                             const uint4 *__restrict__ src_cl,     // [B*nsrc][H*W][4] uint4 (16-bit channels-last)
-                             const float *__restrict__ rt, const float *__restrict__ depth_values,
-                             uint4 *__restrict__ out,              // bf16 CP8 [B,4,D,H,W,8]
-                             int V, int nsrc, int D, int H, int W, int dchunk) {
-    __shared__ float4 s_f[kWarps][32];
-    __shared__ uint32_t s_b[kWarps][32];
-    __shared__ float s_r[kWarps][kMaxSrcSmem][3][32];
-    __shared__ float s_t[kMaxSrcSmem][4];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = lane >> 2, g = lane & 3;
-    const int nchunks = (D + dchunk - 1) / dchunk;
-    const int b = blockIdx.z / nchunks;
-    const int d_begin = (blockIdx.z % nchunks) * dchunk;
-    const int d_end = min(D, d_begin + dchunk);
-    const int y = blockIdx.y * kWarps + warp;
-    const int x0 = blockIdx.x * 32;
-    const size_t HW = (size_t)H * W;
-    const float invV = 1.0f / (float)V;
-    const float xl = (float)(x0 + lane), yf = (float)y;
-    const int W4 = W * 4;  // uint4 units per 16-bit texel row
-    const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
-    const int nsm = min(nsrc, kMaxSrcSmem);
-    if (threadIdx.x < nsm * 3) s_t[threadIdx.x / 3][threadIdx.x % 3] = rt[(size_t)(b * nsrc + threadIdx.x / 3) * 12 + 9 + threadIdx.x % 3];
-    for (int v = 0; v < nsm; ++v) {
-        float rx, ry, rz;
-        rot_pixel(rt + (size_t)(b * nsrc + v) * 12, xl, yf, rx, ry, rz);
-        s_r[warp][v][0][lane] = rx;
-        s_r[warp][v][1][lane] = ry;
-        s_r[warp][v][2][lane] = rz;
-    }
-    __syncthreads();
-    if (y >= H) return;  // warp-uniform
-
-    // reference-view values of this thread's 4 pixels x 8 channels do not depend on the plane
-    float2 R[4][4];  // channel pairs: the accumulators below are packed fp32x2 registers
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int x = x0 + q + 8 * i;
-        if (x < W && ALLV16) {
-            const uint4 rv = __ldg(src_cl + ((size_t)b * V * HW + (size_t)y * W + x) * 4 + g);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) R[i][j] = __half22float2(*reinterpret_cast<const __half2 *>(&rw[j]));
-        } else if (x < W) {
-            const float4 *r = ref_cl + ((size_t)b * HW + (size_t)y * W + x) * 8 + 2 * g;
-            const float4 a = __ldg(r), c = __ldg(r + 1);
-            R[i][0] = make_float2(a.x, a.y); R[i][1] = make_float2(a.z, a.w);
-            R[i][2] = make_float2(c.x, c.y); R[i][3] = make_float2(c.z, c.w);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) R[i][j] = make_float2(0.f, 0.f);
-        }
-    }
-
-    for (int d = d_begin; d < d_end; ++d) {
-        const float dep = __ldg(depth_values + (size_t)b * D + d);
-        float2 S[4][4], Q[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                S[i][j] = R[i][j];
-                Q[i][j] = make_float2(R[i][j].x * R[i][j].x, R[i][j].y * R[i][j].y);
-            }
-        for (int v = 0; v < nsrc; ++v) {
-            const int n = b * nsrc + v;
-            PackedTap t;
-            if (v < kMaxSrcSmem) {
-                t = sample_packed_fast(s_r[warp][v][0][lane], s_r[warp][v][1][lane], s_r[warp][v][2][lane], s_t[v][0],
-                                       s_t[v][1], s_t[v][2], dep, sx, sy, H, W);
-            } else {
-                float rx, ry, rz;
-                const float *rtv = rt + (size_t)n * 12;
-                rot_pixel(rtv, xl, yf, rx, ry, rz);
-                t = sample_packed_fast(rx, ry, rz, rtv[9], rtv[10], rtv[11], dep, sx, sy, H, W);
-            }
-            __syncwarp();
-            if (FP16) {  // publish the four tap weights ready-made as duplicated half2 (formed once per pixel, not per lane)
-                const __half2 h00 = __float2half2_rn(t.f.x * t.f.z), h01 = __float2half2_rn(t.f.y * t.f.z);
-                const __half2 h10 = __float2half2_rn(t.f.x * t.f.w), h11 = __float2half2_rn(t.f.y * t.f.w);
-                float4 pk;
-                pk.x = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h00));
-                pk.y = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h01));
-                pk.z = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h10));
-                pk.w = __uint_as_float(*reinterpret_cast<const uint32_t *>(&h11));
-                s_f[warp][lane] = pk;
-            } else {
-                s_f[warp][lane] = t.f;
-            }
-            s_b[warp][lane] = t.base;
-            __syncwarp();
-            const uint4 *f = src_cl + (size_t)(ALLV16 ? b * V + v + 1 : n) * HW * 4 + g;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 fc = s_f[warp][q + 8 * i];
-                const uint32_t bb = s_b[warp][q + 8 * i];
-                const uint4 *p00 = f + (size_t)(bb & 0x3FFFFFFFu) * 4;
-                const uint4 *p01 = p00 + ((bb >> 30) & 1u) * 4;
-                const int dyo = (bb >> 31) ? W4 : 0;
-                const uint4 ta = __ldg(p00), tb = __ldg(p01), tc = __ldg(p00 + dyo), td = __ldg(p01 + dyo);
-                const uint32_t wa[4] = {ta.x, ta.y, ta.z, ta.w}, wb[4] = {tb.x, tb.y, tb.z, tb.w};
-                const uint32_t wc[4] = {tc.x, tc.y, tc.z, tc.w}, wd[4] = {td.x, td.y, td.z, td.w};
-                const float2 one2 = make_float2(1.f, 1.f);
-                if (FP16) {
-                    // fp16 texels: the 4-tap interpolation runs as packed half2 FMAs (11-bit mantissa: storage + 4 roundings
-                    // ~1e-3 relative, tighter than bf16 storage alone); Sum / Sum^2 are accumulated in fp32 (packed FFMA2)
-                    const uint32_t u00 = __float_as_uint(fc.x), u01 = __float_as_uint(fc.y);
-                    const uint32_t u10 = __float_as_uint(fc.z), u11 = __float_as_uint(fc.w);
-                    const __half2 h00 = *reinterpret_cast<const __half2 *>(&u00), h01 = *reinterpret_cast<const __half2 *>(&u01);
-                    const __half2 h10 = *reinterpret_cast<const __half2 *>(&u10), h11 = *reinterpret_cast<const __half2 *>(&u11);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __half2 a2 = *reinterpret_cast<const __half2 *>(&wa[j]), b2 = *reinterpret_cast<const __half2 *>(&wb[j]);
-                        const __half2 c2 = *reinterpret_cast<const __half2 *>(&wc[j]), d2 = *reinterpret_cast<const __half2 *>(&wd[j]);
-                        const __half2 vh = __hfma2(d2, h11, __hfma2(c2, h10, __hfma2(b2, h01, __hmul2(a2, h00))));
-                        const float2 val = __half22float2(vh);
-                        S[i][j] = __ffma2_rn(val, one2, S[i][j]);
-                        Q[i][j] = __ffma2_rn(val, val, Q[i][j]);
-                    }
-                } else {
-                    // bf16 texels: each 32-bit word unpacks into an (even, odd) fp32 pair with one shift and one mask;
-                    // packed fp32x2 arithmetic (sm_100 FFMA2): two IEEE FMAs per issue slot
-                    const float w00 = fc.x * fc.z, w01 = fc.y * fc.z, w10 = fc.x * fc.w, w11 = fc.y * fc.w;
-                    const float2 w00p = make_float2(w00, w00), w01p = make_float2(w01, w01);
-                    const float2 w10p = make_float2(w10, w10), w11p = make_float2(w11, w11);
-                    const float2 zero2 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 a2 = make_float2(__uint_as_float(wa[j] << 16), __uint_as_float(wa[j] & 0xffff0000u));
-                        const float2 b2 = make_float2(__uint_as_float(wb[j] << 16), __uint_as_float(wb[j] & 0xffff0000u));
-                        const float2 c2 = make_float2(__uint_as_float(wc[j] << 16), __uint_as_float(wc[j] & 0xffff0000u));
-                        const float2 d2 = make_float2(__uint_as_float(wd[j] << 16), __uint_as_float(wd[j] & 0xffff0000u));
-                        const float2 val = __ffma2_rn(d2, w11p, __ffma2_rn(c2, w10p, __ffma2_rn(b2, w01p, __ffma2_rn(a2, w00p, zero2))));
-                        S[i][j] = __ffma2_rn(val, one2, S[i][j]);
-                        Q[i][j] = __ffma2_rn(val, val, Q[i][j]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int x = x0 + q + 8 * i;
-            float r[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float mx = S[i][j].x * invV, my = S[i][j].y * invV;
-                r[2 * j] = fmaf(Q[i][j].x, invV, -mx * mx);
-                r[2 * j + 1] = fmaf(Q[i][j].y, invV, -my * my);
-            }
-            if (x < W) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(r[0], r[1]), t1 = __floats2bfloat162_rn(r[2], r[3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(r[4], r[5]), t3 = __floats2bfloat162_rn(r[6], r[7]);
-                pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
-                pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                __stcs(out + (((size_t)b * 4 + g) * D + d) * HW + (size_t)y * W + x, pk);
-            }
-        }
-    }
-}
-
 // Generic-C fallback of the standalone homo_warping (any channel count, NCHW gathers).  Used only
 // when C != 32; one thread per (x, y, d), looping over channels.
 __global__ void homo_warp_generic_kernel(const float *__restrict__ src, const float *__restrict__ rt,
@@ -1034,7 +745,7 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
     }
     const int dchunk = pick_dchunk(B, D, H, W);
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-    warp_variance_fwd2_kernel<OUT_F32><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, var, V,
+    warp_variance_fwd2_kernel<<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, var, V,
                                                                   nsrc, D, H, W, dchunk);
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
@@ -1046,71 +757,17 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
                           int H, int W, int half_sums, cudaStream_t st);
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st);
 int features_nhwc16_to_rcp8(const void *fea16, void *tex16, int N, int H, int W, cudaStream_t st);
-static int warp_generation() {
-    static const int gen = [] {
-        const char *e = getenv("MVS_WARP_GEN");
-        return (e && atoi(e) == 2) ? 2 : 3;
-    }();
-    return gen;
-}
+// fp32 NCHW features in: one layout pass to fp16 RCP8 texels (all V views), then the TMA-window kernel
+// (warp_variance_win.cu).  workspace (sized for fp32 texels): rt | fp16 RCP8 features.
 int warp_variance_cp8(const float *fea, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                       int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
-    // Default: 16-bit texels through the TMA-window kernel (warp_variance_win.cu).  workspace (sized for fp32 texels):
-    // rt | fp16 RCP8 features of all V views.  MVS_WARP_GEN=2 keeps the previous-generation kernels selectable for A/B runs.
-    if (warp_generation() == 3) {
-        float *rt = (float *)workspace;
-        void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
-        if (nsrc > 0)
-            if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-        if (int rc = features_nchw_to_rcp8(fea, tex16, B * V, H, W, st)) return rc;
-        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
-    }
-    // fp32 features in: fp32 texels and the reference's exact fp32 arithmetic by default (only the stored volume is
-    // bf16).  MVS_TEXEL_FMT=fp16|bf16 converts the source views to 16-bit texels first (tuning knob; the production
-    // 16-bit path is mvs_warp_variance_fwd_cp8_f16, fed directly by a half-precision FeatureNet).
-    static const int texel_fmt = [] {
-        const char *e = getenv("MVS_TEXEL_FMT");
-        if (!e) return 32;
-        return !strcmp(e, "fp16") ? 16 : (!strcmp(e, "bf16") ? 17 : 32);
-    }();
-    if (texel_fmt != 32 && nsrc > 0) {
-        // workspace (sized for fp32 texels): rt | bf16 sources (half of the fp32 area) | fp32 reference view NHWC
-        float *rt = (float *)workspace;
-        char *base = (char *)workspace + align256((size_t)B * nsrc * 12 * sizeof(float));
-        uint16_t *src16 = (uint16_t *)base;
-        float *ref_cl = (float *)(base + align256((size_t)B * nsrc * H * W * kC * 2));
-        const int HW = H * W;
-        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-        if (texel_fmt == 16) nchw_to_nhwc32_lp_kernel<true><<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
-        else nchw_to_nhwc32_lp_kernel<false><<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src16, HW, nsrc, V);
-        ref_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B), dim3(32, 8), 0, st>>>(fea, ref_cl, HW, V);
-        MVS_LAUNCH_CHECK(2);
-        const int dchunk = pick_dchunk(B, D, H, W);
-        dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-        if (texel_fmt == 16)
-            warp_variance_bf16tex_kernel<true, false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
-                                                                                 depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
-        else
-            warp_variance_bf16tex_kernel<false, false><<<grid, kThreads, 0, st>>>((const float4 *)ref_cl, (const uint4 *)src16, rt,
-                                                                                  depth_values, (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
-        MVS_LAUNCH_CHECK(1);
-        return MVS_OK;
-    }
     float *rt = (float *)workspace;
-    float *src_cl = (float *)((char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float)));
-    const int HW = H * W;
-    if (nsrc > 0) {
+    void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
+    if (nsrc > 0)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-        nchw_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src_cl, HW, nsrc, V);
-        MVS_LAUNCH_CHECK(1);
-    }
-    const int dchunk = pick_dchunk(B, D, H, W);
-    dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-    warp_variance_fwd2_kernel<OUT_CP8><<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, vol_cp8,
-                                                                  V, nsrc, D, H, W, dchunk);
-    MVS_LAUNCH_CHECK(1);
-    return MVS_OK;
+    if (int rc = features_nchw_to_rcp8(fea, tex16, B * V, H, W, st)) return rc;
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
 }
 
 // fp16 RCP8 features of all V views in ([B*V][H][4][W][8], what the tensor-core FeatureNet writes): no layout pass.
@@ -1122,24 +779,16 @@ int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *de
     return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, half_sums, st);
 }
 
-// fp16 channels-last features of all V views in ([B][V][H*W][32]), bf16 CP8 volume out: no layout pre-pass at all.
+// fp16 channels-last features of all V views in ([B][V][H*W][32], what a half-precision cuDNN FeatureNet emits)
 int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                           int B, int V, int D, int H, int W, cudaStream_t st) {
     const int nsrc = V - 1;
     float *rt = (float *)workspace;
     if (nsrc > 0)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-    if (warp_generation() == 3) {
-        void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
-        if (int rc = features_nhwc16_to_rcp8(fea16, tex16, B * V, H, W, st)) return rc;
-        return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
-    }
-    const int dchunk = pick_dchunk(B, D, H, W);
-    dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-    warp_variance_bf16tex_kernel<true, true><<<grid, kThreads, 0, st>>>(nullptr, (const uint4 *)fea16, rt, depth_values,
-                                                                        (uint4 *)vol_cp8, V, nsrc, D, H, W, dchunk);
-    MVS_LAUNCH_CHECK(1);
-    return MVS_OK;
+    void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
+    if (int rc = features_nhwc16_to_rcp8(fea16, tex16, B * V, H, W, st)) return rc;
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
 }
 }  // namespace mvs
 

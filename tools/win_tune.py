@@ -1,5 +1,5 @@
 """Times the TMA-window warp+variance kernel (fp16 texels -> bf16 CP8) at the DTU shape for its tuning knobs
-(MVS_WIN_CONFIG, MVS_WARP_DCHUNK), next to the previous generation (MVS_WARP_GEN=2).
+(MVS_WIN_CONFIG, MVS_WIN_HACC, MVS_WARP_DCHUNK).
 Usage: python tools/win_tune.py [yaw]"""
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,13 +22,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         return e0.elapsed_time(e1) / n
     a = t(lambda: ops.warp_variance_cp8(fea16, proj, dv))
     b = t(lambda: ops.warp_variance_cp8(fea, proj, dv))
-    print("gen=%s cfg=%s hacc=%s dchunk=%s yaw=%g: fp16-nhwc in %.3f ms, fp32-nchw in %.3f ms (layout pass included)" % (
-        os.environ.get("MVS_WARP_GEN", "3"), os.environ.get("MVS_WIN_CONFIG", "0"), os.environ.get("MVS_WIN_HACC", "default"),
+    print("cfg=%s hacc=%s dchunk=%s yaw=%g: fp16-nhwc in %.3f ms, fp32-nchw in %.3f ms (layout pass included)" % (
+        os.environ.get("MVS_WIN_CONFIG", "0"), os.environ.get("MVS_WIN_HACC", "default"),
         os.environ.get("MVS_WARP_DCHUNK", "16"), yaw, a, b),
         flush=True)
 else:
     yaw = sys.argv[1] if len(sys.argv) > 1 else "0"
-    runs = [dict(MVS_WARP_GEN="2"), dict(MVS_WIN_HACC="1"), dict(MVS_WIN_CONFIG="1")]
+    runs = [dict(MVS_WIN_HACC="0"), dict(MVS_WIN_HACC="1"), dict(MVS_WIN_CONFIG="1")]
     for dc in ("8", "16", "32"):
         runs.append(dict(MVS_WARP_DCHUNK=dc))
     for r in runs:
