@@ -1625,6 +1625,31 @@ __global__ void nchw_to_cp8n_f16_kernel(const T *__restrict__ in, uint4 *__restr
     out[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// FeatureNet input: 3-channel images [N][3][H][W] (fp32, or uint8 / 255) -> fp16 [1][N][H][W][8] with channels 3..7 zero.
+// Four consecutive pixels per thread: one 16-byte (fp32) or 4-byte (uint8) load per colour plane, 64 contiguous bytes out.
+template <typename T>
+__global__ void images_to_cp8_kernel(const T *__restrict__ in, uint4 *__restrict__ out, size_t HW, long long quads) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const size_t px = (size_t)i * 4;  // first pixel (n*HW + y*W + x); W % 4 == 0 keeps the four in one row
+    const size_t n = px / HW, off = px - n * HW;
+    float c[3][4];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const T *p = in + (n * 3 + ch) * HW + off;
+        if constexpr (sizeof(T) == 1) {
+            const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(p));
+            c[ch][0] = __fdiv_rn((float)v.x, 255.f); c[ch][1] = __fdiv_rn((float)v.y, 255.f);
+            c[ch][2] = __fdiv_rn((float)v.z, 255.f); c[ch][3] = __fdiv_rn((float)v.w, 255.f);
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+            c[ch][0] = v.x; c[ch][1] = v.y; c[ch][2] = v.z; c[ch][3] = v.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(out + px + k, make_uint4(pack_f16x2(c[0][k], c[1][k]), pack_f16x2(c[2][k], 0.f), 0u, 0u));
+}
+
 // fp16 [C/8][N][H][W][8] -> fp32 NCHW (tests)
 __global__ void cp8n_f16_to_nchw_kernel(const uint4 *__restrict__ in, float *__restrict__ out, int N, int C, int H, int W,
                                         long long total) {
@@ -1688,7 +1713,10 @@ int featurenet_tc(const void *imgs, int imgs_u8, const mvs_featurenet_params *p,
     uint8_t *wsc = take(MVS_FEATURENET_LAYERS * (kWScratch + 128 * 1024));
     {
         const long long total = (long long)px;
-        if (imgs_u8) nchw_to_cp8n_f16_kernel<uint8_t><<<cdiv(total, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
+        const long long quads = total / 4;  // W % 4 == 0
+        const bool aligned = ((uintptr_t)imgs & 15) == 0;
+        if (imgs_u8) images_to_cp8_kernel<uint8_t><<<cdiv(quads, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, (size_t)H * W, quads);
+        else if (aligned) images_to_cp8_kernel<float><<<cdiv(quads, 256), 256, 0, st>>>((const float *)imgs, (uint4 *)in0, (size_t)H * W, quads);
         else nchw_to_cp8n_f16_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
         MVS_LAUNCH_CHECK(1);
     }
