@@ -179,6 +179,20 @@ int mvs_softmax_depth_conf(const float *logits, const float *depth_values, float
 int mvs_depth_regression(const float *p, const float *depth_values, int dv_batch_stride, float *out, int B, int D,
                          int H, int W, void *stream);
 
+/* ---- Geometric-consistency filter of the depth maps, per reference view     eval.py:508-585 (reproject_with_depth,
+ * check_geometric_consistency) and eval.py:660-703 (filter_depth: masks and averaged depth).  SURVEY.md 8(f) rank 3.
+ * ref_depth, confidence [H,W] fp32 and src_depths [S,H,W] fp32 are DEVICE pointers (confidence may be NULL: photo mask
+ * all true); the camera matrices are HOST pointers, row-major double: intrinsics 3x3, extrinsics 4x4 (world -> camera),
+ * as read by the reference's read_camera_parameters.  Outputs (device): depth_avg [H,W] float64 (the reference's
+ * depth_est_averaged is float64), geo_mask_sum [H,W] int32, photo/geo/final masks [H,W] uint8; optional (NULL to skip):
+ * reprojected [S,H,W] fp32 (0 where inconsistent), src_masks [S,H,W] uint8, xy_src [S,2,H,W] fp32 (x2d_src, y2d_src).
+ * Sampling reproduces cv2.remap(INTER_LINEAR): 1/32-pixel coordinate quantisation, constant border 0. */
+int mvs_filter_depth(const float *ref_depth, const float *confidence, const double *ref_K_host, const double *ref_E_host,
+                     const float *src_depths, const double *src_K_host, const double *src_E_host, int S, int H, int W,
+                     double condmask_pixel, double condmask_depth, int geomask, double photomask, double *depth_avg,
+                     int32_t *geo_mask_sum, uint8_t *photo_mask, uint8_t *geo_mask, uint8_t *final_mask, float *reprojected,
+                     uint8_t *src_masks, float *xy_src, void *stream);
+
 /* ---- Host-buffer entry point: features to depth map, everything this library owns in one call.
  * Copies fea/proj/depth_values host->device, runs warp+variance -> CostRegNet -> softmax/depth/conf,
  * copies depth/conf device->host and synchronises.  params_host holds HOST pointers to the folded

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mvs_conv2d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 8 + [ctypes.c_void_p]),
     "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
                             [ctypes.c_void_p]),
+    "mvs_filter_depth": (_i, [_c_float_p] * 7 + [_i] * 3 + [ctypes.c_double, ctypes.c_double, _i, ctypes.c_double] +
+                         [_c_float_p] * 8 + [ctypes.c_void_p]),
     "mvs_softmax_depth_conf": (_i, [_c_float_p] * 5 + [_i] * 4 + [ctypes.c_void_p]),
     "mvs_depth_regression": (_i, [_c_float_p, _c_float_p, _i, _c_float_p] + [_i] * 4 + [ctypes.c_void_p]),
     "mvs_depth_from_features_host": (_i, [_c_float_p] * 3 + [ctypes.POINTER(CostRegParams), _c_float_p, _c_float_p] +

@@ -90,3 +90,25 @@ def test_default_init_is_degenerate(case_a):
     dv = case_a["dv"]
     assert maxabs(d["depth"], np.full_like(d["depth"], dv.mean())) < 0.05
     assert maxabs(d["conf"], np.full_like(d["conf"], 4.0 / dv.shape[1])) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# Geometric-consistency filter (the step after the depth path, reference eval.py:508-585, 660-703)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["fusion_a", "fusion_b"])
+def test_fusion_oracle_matches_reference_golden(name):
+    """oracle/fusion_oracle.py (numpy restatement incl. cv2.remap) against outputs of the unmodified reference functions
+    (tests/make_golden_fusion.py).  Same float64 numpy operations: everything is bit-identical."""
+    import os
+    from oracle import fusion_oracle as fo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    pix, dep, geo, photo = g["params"]
+    for s in range(g["src_depths"].shape[0]):
+        m, dr, xs, ys = fo.check_geometric_consistency(g["ref_depth"], g["K"], g["E"], g["src_depths"][s], g["src_K"][s],
+                                                       g["src_E"][s], pix, dep)
+        assert np.array_equal(m, g["masks"][s])
+        assert np.array_equal(dr, g["reprojected"][s])
+        assert np.array_equal(xs, g["x_src"][s], equal_nan=True) and np.array_equal(ys, g["y_src"][s], equal_nan=True)
+    avg, pm, gm, fm, _ = fo.filter_view(g["ref_depth"], g["conf"], g["K"], g["E"], g["src_depths"], g["src_K"], g["src_E"],
+                                        photomask=photo, geomask=int(geo), condmask_pixel=pix, condmask_depth=dep)
+    assert np.array_equal(avg, g["depth_avg"]) and np.array_equal(gm, g["geo_mask"]) and np.array_equal(fm, g["final_mask"])
