@@ -295,3 +295,28 @@ def test_full_size_c2_forward_properties(weights):
     rng = float(dv.max() - dv.min())
     assert float((a["depth"] - s["depth"]).abs().mean()) < 2e-3 * rng
     assert float((a["depth"] - s["depth"]).abs().max()) < 2e-2 * rng
+
+
+def test_packed_weight_cache_follows_weight_changes(weights):
+    """The tensor-core layers cache their packed 16-bit weights per weight pointer; the models invalidate the cache
+    whenever BatchNorm is re-folded.  In-place updates (an optimizer step) and load_state_dict must be picked up."""
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    imgs, proj, dv = synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=5)
+    imgs, proj, dv = imgs.to(DEV), proj.to(DEV), dv.to(DEV)
+    m = load_model(weights, precision="bf16")
+    with torch.no_grad():
+        a = m(imgs, proj, dv)["depth"].clone()
+        m.cost_regularization.conv0.conv.weight.mul_(1.5)          # in place: same pointer, new version
+        m.feature.conv1.conv.weight.mul_(0.5)
+        b = m(imgs, proj, dv)["depth"].clone()
+    fresh = load_model(weights, precision="bf16")
+    with torch.no_grad():
+        fresh.cost_regularization.conv0.conv.weight.mul_(1.5)
+        fresh.feature.conv1.conv.weight.mul_(0.5)
+        c = fresh(imgs, proj, dv)["depth"]
+        m.load_state_dict(load_model(weights, precision="bf16").state_dict())
+        d = m(imgs, proj, dv)["depth"]
+    assert not torch.equal(a, b), "changed weights must change the result"
+    assert torch.equal(b, c), "in-place update must give the same result as a fresh model with those weights"
+    assert torch.equal(a, d), "load_state_dict back to the original weights must restore the original result"
