@@ -1431,14 +1431,28 @@ static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void 
     return MVS_OK;
 }
 
+// Entries are retired in two steps: a clear moves them to a graveyard and frees the previous graveyard, so a launch on
+// another host thread that looked its pointer up just before the clear still reads valid memory.
+static std::vector<WCacheEntry> g_wcache_graveyard;
+static std::vector<int> g_wcache_graveyard_dev;
+
 int weight_cache_clear() {
     std::lock_guard<std::mutex> lock(g_wcache_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (size_t i = 0; i < g_wcache_graveyard.size(); ++i) {
+        cudaSetDevice(g_wcache_graveyard_dev[i]);
+        cudaFree(g_wcache_graveyard[i].ptr);  // synchronises with every stream that may still read it
+        cudaEventDestroy(g_wcache_graveyard[i].ready);
+    }
+    g_wcache_graveyard.clear();
+    g_wcache_graveyard_dev.clear();
     for (auto &kv : g_wcache) {
-        cudaSetDevice(kv.first.dev);
-        cudaFree(kv.second.ptr);  // synchronises with every stream that may still read it
-        cudaEventDestroy(kv.second.ready);
+        g_wcache_graveyard.push_back(kv.second);
+        g_wcache_graveyard_dev.push_back(kv.first.dev);
     }
     g_wcache.clear();
+    cudaSetDevice(cur);
     return MVS_OK;
 }
 
