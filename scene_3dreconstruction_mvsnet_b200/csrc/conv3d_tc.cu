@@ -49,7 +49,7 @@ tmap_encode_fn get_tmap_encode() {
 constexpr int kMaxOps = 112;
 constexpr int kMaxAcc = 8;
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
-constexpr int kTcThreadsDual = 352;  // + warp 10: second MMA issuer (layers whose steps share no input plane)
+constexpr int kTcThreadsDual = 352;  // + warp 10: second MMA issuer
 
 struct TcOp {
     uint32_t a_off;     // byte offset of the A operand inside its ring plane (sub-plane + tap + chunk pair)
@@ -93,7 +93,7 @@ struct TcLayer {
     int out_mode;    // 0: CP8 [C/8][D][H][W][8]; 1: space-to-depth [4 parities x C/8][D][H/2][W/2][8];
                      // 2: row-chunk-planar "RCP8" [D][H][C/8][W][8] (what the fused warp kernel's TMA windows read)
     int merged_t;    // 1: transposed conv with the 8 output-parity classes merged along N (column block = class)
-    int dual;        // 1: two MMA issuer warps alternate over the steps (need == 1: steps share no input plane)
+    int dual;        // 1: two MMA issuer warps alternate over the steps
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
@@ -183,7 +183,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 1);
+            // dual issuers: a plane is free when BOTH issuer warps' MMAs that read it have completed
+            ptx::mbar_init(empty_bar(s), L.dual ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(tfull_bar(b), 1);
@@ -251,8 +252,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // ================= MMA issuer(s) =================
         // The whole warp runs this loop with warp-uniform values (kernel parameters, loop counters) so that
         // descriptors live in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
-        // Dual mode (L.dual, warp 10 present): when every step reads only its own input plane, two issuer warps
-        // alternate over the steps -- warp 1 owns TMEM buffer 0, warp 10 buffer 1.  The barrier waits, commits and
+        // Dual mode (L.dual, warp 10 present): two issuer warps alternate over the steps -- warp 1 owns TMEM buffer 0,
+        // warp 10 buffer 1.  Input planes shared by consecutive steps are released by both (empty barrier count 2).  The barrier waits, commits and
         // bookkeeping of one step (~1000 cycles, as long as its 20-70 MMAs take to execute) then overlap the other
         // warp's MMAs instead of leaving the tensor pipe idle.
         const uint32_t me = (warp == 10) ? 1u : 0u;
@@ -276,8 +277,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 const uint32_t sl0 = s0, sl1 = wrap(s0 + 1), sl2 = wrap(s0 + 2);
                 if (leader && mine) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
                     const long long c0 = clock64();
-                    // planes already waited for in earlier steps of this item need no second look
-                    for (uint32_t r = (t == 0) ? 0 : need - adv; r < need; ++r) {
+                    // planes already waited for in earlier steps of this item need no second look (single issuer; with
+                    // two issuers the previous step's waits were the other warp's)
+                    for (uint32_t r = (t == 0 || L.dual) ? 0 : need - adv; r < need; ++r) {
                         const uint32_t sl = wrap(s0 + r);
                         ptx::mbar_wait(full_bar(sl), (par >> sl) & 1u);
                     }
@@ -304,7 +306,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 const uint32_t nrel = (t == T - 1) ? need : adv;
                 for (uint32_t r = 0; r < nrel; ++r) {
                     const uint32_t sl = wrap(s0 + r);
-                    if (leader && mine) ptx::tcgen05_commit(empty_bar(sl));
+                    // dual mode: both issuers arrive -- the owner of this step for its MMAs, the other one for its MMAs of
+                    // the previous steps that read the plane (a commit covers everything the thread issued so far)
+                    if (leader && (mine || L.dual)) ptx::tcgen05_commit(empty_bar(sl));
                     par ^= 1u << sl;
                 }
                 if (leader && mine) ptx::tcgen05_commit(tfull_bar(buf));
@@ -1221,7 +1225,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     L.merged_t = merged_t ? 1 : 0;
     L.fold = fold ? 1 : 0;
     static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
-    L.dual = (!fold && need == 1 && nacc == 1 && !nodual) ? 1 : 0;
+    L.dual = (!fold && !nodual) ? 1 : 0;
     L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * 16)) : 0;
     const int chunk_stride = rows * P * 16;
     int nops = 0;
