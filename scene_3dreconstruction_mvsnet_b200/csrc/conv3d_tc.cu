@@ -625,7 +625,7 @@ __device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab,
 }
 
 template <int CW>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreadsDual, 1)
 conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar_base = ptx::smem_u32(smem);
@@ -659,18 +659,18 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     {
         const uint4 *src = L.wpacked;
         uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
-        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    for (int o = threadIdx.x; o < L.nops; o += kTcThreads)
+    for (int o = threadIdx.x; o < L.nops; o += blockDim.x)
         optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
     if (threadIdx.x < 64) s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + threadIdx.x) : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 2);  // both issuer warps release a plane
         }
         for (int b = 0; b < R; ++b) {
-            ptx::mbar_init(tfull_bar(b), 1);
+            ptx::mbar_init(tfull_bar(b), 2);  // both issuer warps complete a block (each its M-tiles)
             ptx::mbar_init(tempty_bar(b), 4);  // the 4 quadrant warps of the epilogue set that drains the block
         }
         ptx::fence_barrier_init();
@@ -725,8 +725,12 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             }
             if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || warp == 10) {
+        // ================= MMA issuers =================
+        // Two issuer warps split the M-TILES of every step (disjoint TMEM column regions, so no accumulator is shared between
+        // them): the barrier waits and commits of one overlap the other's MMAs.  Both arrive on the plane's empty barrier
+        // and on the block's full barrier.
+        const int mt_lo = (warp == 1) ? 0 : (MT + 1) / 2, mt_n = (warp == 1) ? (MT + 1) / 2 : MT / 2;
         const bool leader = ptx::elect_one();
         uint32_t g = 0;      // input planes consumed so far
         uint32_t slot = 0;   // ring slot of plane g, and the parity of its current fill (all tracked incrementally:
@@ -763,13 +767,12 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 if (leader) {
                     const long long ci = clock64();
                     const uint32_t sb = (ring_base + slot * L.slot_bytes) >> 4;
-                    const uint32_t d = tmem_base + (pj + k0) * CW;  // physical window start: never wraps (mirror blocks)
+                    const uint32_t d = tmem_base + (pj + k0) * CW + mt_lo * cols_mt;  // window start: never wraps (mirror blocks)
                     const uint32_t brow = k0 * CW;
                     const uint32_t idesc = ptx::make_idesc_bf16_m128(cnt * CW);
-                    if (MT == 4) issue_fold_pass<4>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                    else if (MT == 3) issue_fold_pass<3>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                    else if (MT == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
-                    else issue_fold_pass<1>(optab, nops, d, cols_mt, sb, brow, idesc, kDescHi);
+                    const uint32_t sbm = sb + mt_lo * 128;  // this warp's first M-tile
+                    if (mt_n == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sbm, brow, idesc, kDescHi);
+                    else if (mt_n == 1) issue_fold_pass<1>(optab, nops, d, cols_mt, sbm, brow, idesc, kDescHi);
                     t_issue += clock64() - ci;
                     ptx::tcgen05_commit(empty_bar(slot));
                     if (j >= 2) ptx::tcgen05_commit(tfull_bar(pj));  // output plane zs + j - 2 is complete
@@ -778,7 +781,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 pj = wrapR(pj + 1);
             }
         }
-        if (leader && L.dbg) {
+        if (leader && L.dbg && warp == 1) {
             L.dbg[blockIdx.x * 12 + 1] = w_full;
             L.dbg[blockIdx.x * 12 + 2] = w_tempty;
             L.dbg[blockIdx.x * 12 + 3] = t_issue;
@@ -1498,7 +1501,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     }
     auto launch = [&](auto kern) -> int {
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        kern<<<pl.grid, pl.L.dual ? kTcThreadsDual : kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
+        kern<<<pl.grid, (pl.L.dual || pl.L.fold) ? kTcThreadsDual : kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };
