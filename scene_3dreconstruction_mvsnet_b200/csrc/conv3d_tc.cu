@@ -1500,7 +1500,9 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         pl.L.wpacked = (const uint4 *)wp;
     }
     auto launch = [&](auto kern) -> int {
-        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
+        // per-layer one that a concurrent launch of another layer could lower between this call and the launch
+        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
         kern<<<pl.grid, (pl.L.dual || pl.L.fold) ? kTcThreadsDual : kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;

@@ -126,7 +126,7 @@ extern "C" int mvs_softmax_depth_conf(const float *logits, const float *depth_va
     if (smem <= 96 * 1024) {
         if (smem > 48 * 1024)
             MVS_CUDA(cudaFuncSetAttribute(softmax_depth_conf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
+                                          96 * 1024));  // one value for every caller (the attribute is per function, not per launch)
         softmax_depth_conf_kernel<true><<<grid, 32 * kSlices, smem, st>>>(logits, depth_values, depth, conf, prob, D, HW);
     } else {
         softmax_depth_conf_kernel<false><<<grid, 32 * kSlices, 0, st>>>(logits, depth_values, depth, conf, prob, D, HW);

@@ -321,3 +321,38 @@ def test_packed_weight_cache_follows_weight_changes(weights):
     assert not torch.equal(a, b), "changed weights must change the result"
     assert torch.equal(b, c), "in-place update must give the same result as a fresh model with those weights"
     assert torch.equal(a, d), "load_state_dict back to the original weights must restore the original result"
+
+
+def test_two_host_threads_two_streams_same_results(weights):
+    """nn.DataParallel calls forward from one host thread per replica (train.py:125): two threads, each with its own
+    model replica and CUDA stream on the same device, must reproduce the serial results bit for bit (thread-local
+    plans, per-stream workspaces, the shared packed-weight cache)."""
+    import threading
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    inputs = [tuple(t.to(DEV) for t in synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=s))
+              for s in (11, 12)]
+    models = [load_model(weights, precision="bf16") for _ in range(2)]
+    with torch.no_grad():
+        serial = [m(*inp)["depth"].clone() for m, inp in zip(models, inputs)]
+    torch.cuda.synchronize()
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream(DEV)
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(8):
+                    out = models[i](*inputs[i])["depth"]
+                results[i] = out.clone()
+            s.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert torch.equal(results[0], serial[0]) and torch.equal(results[1], serial[1])
