@@ -356,3 +356,36 @@ def test_two_host_threads_two_streams_same_results(weights):
         t.join()
     assert not errors, errors
     assert torch.equal(results[0], serial[0]) and torch.equal(results[1], serial[1])
+
+
+def test_two_devices_from_one_process(weights):
+    """nn.DataParallel-style use (train.py:125): replicas on two devices driven from two host threads of one process.
+    Needs two GPUs; skipped otherwise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import threading
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    imgs, proj, dv = synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=21)
+    with torch.no_grad():
+        ref = load_model(weights, precision="bf16")(imgs.to(DEV), proj.to(DEV), dv.to(DEV))["depth"].cpu()
+    results, errors = {}, []
+
+    def work(d):
+        try:
+            dev = "cuda:%d" % d
+            m = load_model(weights, precision="bf16").to(dev)
+            with torch.no_grad():
+                for _ in range(4):
+                    out = m(imgs.to(dev), proj.to(dev), dv.to(dev))["depth"]
+            results[d] = out.cpu()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert torch.equal(results[0], ref) and torch.equal(results[1], ref)
