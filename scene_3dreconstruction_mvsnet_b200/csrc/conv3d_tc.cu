@@ -72,6 +72,9 @@ struct TcLayer {
     int nsub, chunks, sub_bytes, sub_stride, slot_bytes, need, adv, nslot, pz0, zscale;
     int in_scale, sub_xoff[4], sub_yoff[4];
     int merged_x;  // 1: tensor map is 4-D with the 8 channels and x merged into one contiguous inner dimension
+    int in_split;  // 1 (stride-2 conv): the input is the (y,x)-parity-split copy [B][4][C/8][D][H/2][W/2][8] written by the
+                   //    previous layer (out2): each parity sub-plane is a unit-stride box -> fast merged-x TMA
+    void *out2;    // optional second output: the (y,x)-parity-split copy of `out` for a following stride-2 layer
     // gemm
     int nops, nacc, npad, wbytes_group;
     int acc_first[kMaxAcc + 1];  // op range of each accumulator group
@@ -238,6 +241,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     if (L.merged_x) {  // inner dimension = 16*P contiguous bytes per row (uint64 elements)
                         ptx::tma_load_4d(ring_base + slot * L.slot_bytes, &tmap, full_bar(slot), 2 * (x0 + L.sub_xoff[0]),
                                          y0 + L.sub_yoff[0], pz, b * L.chunks);
+                    } else if (L.in_split) {
+                        for (int s = 0; s < 4; ++s)  // s = ypar*2 + xpar: its own contiguous sub-volume
+                            ptx::tma_load_4d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot),
+                                             2 * (x0 + L.sub_xoff[s]), y0 + L.sub_yoff[s], pz, (b * 4 + s) * L.chunks);
                     } else {
                         for (int s = 0; s < L.nsub; ++s)
                             ptx::tma_load_5d(ring_base + slot * L.slot_bytes + s * L.sub_stride, &tmap, full_bar(slot), 0,
@@ -363,6 +370,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
             size_t base0 = 0, base1 = 0, base2 = 0, base3 = 0;
+            uint32_t sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;  // per-batch offsets into the parity-split second output (L.out2)
+            const size_t plane_sp = (size_t)L.Dout * (L.Hout / 2) * (L.Wout / 2);
             uint32_t vmask = 0;
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
@@ -370,6 +379,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     const int pos = mt * 128 + q * 32 + lane;
                     const int y = pos / L.P, x = pos - y * L.P;
                     const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
+                    if (L.out2 != nullptr) {
+                        const uint32_t sp = (uint32_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * (uint32_t)plane_sp +
+                                            (uint32_t)((y0 + y) >> 1) * (L.Wout / 2) + (uint32_t)((x0 + x) >> 1);
+                        if (mt == 0) sp0 = sp; else if (mt == 1) sp1 = sp; else if (mt == 2) sp2 = sp; else sp3 = sp;
+                    }
                     size_t bs = (size_t)(L.out_scale * (y0 + y)) * L.Wout + (size_t)L.out_scale * (x0 + x);
                     if (s2d)
                         bs = (size_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * plane +
@@ -498,6 +512,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                 pk.z = pack16x2<F16>(v[4], v[5]);
                                 pk.w = pack16x2<F16>(v[6], v[7]);
                                 op[(size_t)c8 * plane] = pk;
+                                if (L.out2 != nullptr)
+                                    reinterpret_cast<uint4 *>(L.out2)[((size_t)b * 4 * (L.cout_total >> 3) + chunk0 + c8) * plane_sp +
+                                                                      (mt == 0 ? sp0 : (mt == 1 ? sp1 : (mt == 2 ? sp2 : sp3))) +
+                                                                      (size_t)(zs + t) * ((size_t)(L.Hout / 2) * (L.Wout / 2))] = pk;
                             }
                         }
                     }
@@ -806,6 +824,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
             size_t base[4] = {0, 0, 0, 0};
+            uint32_t sp[4] = {0, 0, 0, 0};  // per-batch offsets into the parity-split second output (L.out2)
+            const size_t plane_sp = (size_t)L.Dout * (L.Hout / 2) * (L.Wout / 2), zstride_sp = (size_t)(L.Hout / 2) * (L.Wout / 2);
             uint32_t vmask = 0;
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
@@ -814,6 +834,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     const int y = pos / L.P, x = pos - y * L.P;
                     if ((y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt)) vmask |= 1u << mt;
                     base[mt] = (size_t)(y0 + y) * L.Wout + (size_t)(x0 + x);
+                    sp[mt] = (uint32_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * (uint32_t)plane_sp +
+                             (uint32_t)((y0 + y) >> 1) * (L.Wout / 2) + (uint32_t)((x0 + x) >> 1);
                 }
             }
             for (int e = 0; e < T; ++e, ++estep) {
@@ -952,6 +974,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                                     pk.z = pack_bf16x2(v[4], v[5]);
                                     pk.w = pack_bf16x2(v[6], v[7]);
                                     reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + c8) * plane + vox] = pk;
+                                    if (L.out2 != nullptr)
+                                        reinterpret_cast<uint4 *>(L.out2)[((size_t)b * 4 * (L.cout_total >> 3) + c8) * plane_sp + sp[mt] +
+                                                                          (size_t)(zs + e) * zstride_sp] = pk;
                                 }
                             }
                         }
@@ -1092,7 +1117,7 @@ static constexpr int kSmemLimit = 227 * 1024;
 
 // Builds the plan for one layer.  in: bf16 CP8 [B][cin/8][Din][Hin][Win][8].
 static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din, int Hin, int Win, const void *in_ptr,
-                     int num_sms, bool encode = true) {
+                     int num_sms, bool encode = true, bool in_split = false) {
     TcLayer &L = pl.L;
     memset(&pl, 0, sizeof(pl));
     MVS_REQUIRE(cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
@@ -1362,6 +1387,20 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     tmap_encode_fn enc = get_tmap_encode();
     MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     L.merged_x = (kind != TC_CONV_S2);
+    L.in_split = (kind == TC_CONV_S2 && in_split) ? 1 : 0;
+    if (L.in_split) {
+        // parity-split input [B][4 (ypar,xpar)][chunks][D][H/2][W/2][8]: every sub-plane box is unit-stride, rows contiguous
+        const int W2 = Win / 2, H2 = Hin / 2;
+        cuuint64_t gdim4[4] = {(cuuint64_t)2 * W2, (cuuint64_t)H2, (cuuint64_t)Din, (cuuint64_t)B * 4 * chunks};
+        cuuint64_t gstr4[3] = {(cuuint64_t)W2 * 16, (cuuint64_t)W2 * H2 * 16, (cuuint64_t)W2 * H2 * Din * 16};
+        cuuint32_t box4[4] = {(cuuint32_t)(2 * P), (cuuint32_t)rows, 1, (cuuint32_t)chunks};
+        cuuint32_t estr4[4] = {1, 1, 1, 1};
+        CUresult cr4 = enc(&pl.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(in_ptr), gdim4, gstr4, box4,
+                           estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr4 != CUDA_SUCCESS) return set_error(MVS_ERR_CUDA, "cuTensorMapEncodeTiled (parity-split) failed (%d)", (int)cr4);
+        return MVS_OK;
+    }
     if (L.merged_x) {
         // A TMA request per 16-byte inner row is ~10 cycles; merging (8ch, x) into one contiguous inner
         // dimension of uint64 elements makes every box row one 16*P-byte request.
@@ -1465,9 +1504,12 @@ int weight_cache_clear() {
 
 static int run_layer(TcKind kind, const void *in, const float *w_fp32, const float *shift, int relu, const void *skip,
                      void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
-                     int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false) {
+                     int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false, void *out2 = nullptr,
+                     bool in_split = false) {
     static thread_local TcPlan pl;  // ~3 KB; not kept across calls
-    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms)) return rc;
+    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split)) return rc;
+    MVS_REQUIRE(out2 == nullptr || (out_mode == 0 && !out_f32 && !f16 && (pl.L.fold || pl.L.nacc == 1) && skip == nullptr && Hin % 2 == 0 && Win % 2 == 0), "second output: plain conv layers only");
+    pl.L.out2 = out2;
     MVS_REQUIRE(!f16 || (kind == TC_CONV2D && pl.npad <= 32 && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
     MVS_REQUIRE(out_mode == 0 || (kind == TC_CONV2D && B == 1), "alternative output layouts: 2-D layers only");
     MVS_REQUIRE(out_mode != 1 || (Hin % 2 == 0 && Win % 2 == 0), "space-to-depth output needs even H, W");
@@ -1532,7 +1574,8 @@ static constexpr size_t kWScratch = 512 * 1024;
 
 size_t costreg_tc_workspace_bytes(int B, int D, int H, int W) {
     const size_t n0 = (size_t)B * D * H * W;
-    const size_t act = n0 * 64 + n0 * 16 + n0 * 4 + n0 * 4 + n0 + n0 + n0 / 4 + n0 / 4 + n0 + n0 * 4 + n0 * 16;
+    const size_t act = n0 * 64 + n0 * 16 + n0 * 4 + n0 * 4 + n0 + n0 + n0 / 4 + n0 / 4 + n0 + n0 * 4 + n0 * 16 +
+                       n0 * 16 + n0 * 4 + n0;  // + the parity-split copies of c0, c2, c4 read by the stride-2 layers
     return align_up(act, 1024) + 11 * kWScratch + 16 * 1024;
 }
 
@@ -1547,6 +1590,8 @@ int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_pa
     void *vol = take(volume_cp8 ? 0 : n0 * 64), *c0 = take(n0 * 16), *c1 = take(n0 * 4), *c2 = take(n0 * 4), *c3 = take(n0),
          *c4 = take(n0), *c5 = take(n0 / 4), *c6 = take(n0 / 4), *u7 = take(n0), *u9 = take(n0 * 4),
          *u11 = take(n0 * 16);
+    static const bool nosplit = getenv("MVS_TC_NOSPLIT") != nullptr;  // A/B knob
+    void *c0s = nosplit ? nullptr : take(n0 * 16), *c2s = nosplit ? nullptr : take(n0 * 4), *c4s = nosplit ? nullptr : take(n0);
     uint8_t *wsc = take(11 * kWScratch);
     const size_t N = (size_t)D * H * W;
     if (volume_cp8) {
@@ -1557,12 +1602,12 @@ int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_pa
     }
     int rc;
 #define RUN(expr) if ((rc = (expr)) != MVS_OK) return rc
-    RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st, 0, 0, true));
-    RUN(run_layer(TC_CONV_S2, c0, p->w[1], p->shift[1], 1, nullptr, c1, 0, wsc + 1 * kWScratch, B, 8, 16, D, H, W, num_sms, st, 0, 0, true));
-    RUN(run_layer(TC_CONV_S1, c1, p->w[2], p->shift[2], 1, nullptr, c2, 0, wsc + 2 * kWScratch, B, 16, 16, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true));
-    RUN(run_layer(TC_CONV_S2, c2, p->w[3], p->shift[3], 1, nullptr, c3, 0, wsc + 3 * kWScratch, B, 16, 32, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true));
-    RUN(run_layer(TC_CONV_S1, c3, p->w[4], p->shift[4], 1, nullptr, c4, 0, wsc + 4 * kWScratch, B, 32, 32, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
-    RUN(run_layer(TC_CONV_S2, c4, p->w[5], p->shift[5], 1, nullptr, c5, 0, wsc + 5 * kWScratch, B, 32, 64, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
+    RUN(run_layer(TC_CONV_S1, vol, p->w[0], p->shift[0], 1, nullptr, c0, 0, wsc + 0 * kWScratch, B, 32, 8, D, H, W, num_sms, st, 0, 0, true, c0s));
+    RUN(run_layer(TC_CONV_S2, c0s ? c0s : c0, p->w[1], p->shift[1], 1, nullptr, c1, 0, wsc + 1 * kWScratch, B, 8, 16, D, H, W, num_sms, st, 0, 0, true, nullptr, c0s != nullptr));
+    RUN(run_layer(TC_CONV_S1, c1, p->w[2], p->shift[2], 1, nullptr, c2, 0, wsc + 2 * kWScratch, B, 16, 16, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true, c2s));
+    RUN(run_layer(TC_CONV_S2, c2s ? c2s : c2, p->w[3], p->shift[3], 1, nullptr, c3, 0, wsc + 3 * kWScratch, B, 16, 32, D / 2, H / 2, W / 2, num_sms, st, 0, 0, true, nullptr, c2s != nullptr));
+    RUN(run_layer(TC_CONV_S1, c3, p->w[4], p->shift[4], 1, nullptr, c4, 0, wsc + 4 * kWScratch, B, 32, 32, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true, c4s));
+    RUN(run_layer(TC_CONV_S2, c4s ? c4s : c4, p->w[5], p->shift[5], 1, nullptr, c5, 0, wsc + 5 * kWScratch, B, 32, 64, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true, nullptr, c4s != nullptr));
     RUN(run_layer(TC_CONV_S1, c5, p->w[6], p->shift[6], 1, nullptr, c6, 0, wsc + 6 * kWScratch, B, 64, 64, D / 8, H / 8, W / 8, num_sms, st, 0, 0, true));
     RUN(run_layer(TC_CONVT, c6, p->w[7], p->shift[7], 1, c4, u7, 0, wsc + 7 * kWScratch, B, 64, 32, D / 8, H / 8, W / 8, num_sms, st, 0, 0, true));
     RUN(run_layer(TC_CONVT, u7, p->w[8], p->shift[8], 1, c2, u9, 0, wsc + 8 * kWScratch, B, 32, 16, D / 4, H / 4, W / 4, num_sms, st, 0, 0, true));
