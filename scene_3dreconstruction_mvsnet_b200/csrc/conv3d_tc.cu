@@ -50,6 +50,10 @@ constexpr int kMaxOps = 112;
 constexpr int kMaxAcc = 8;
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kTcThreadsDual = 352;  // + warp 10: second MMA issuer
+// depth-folded kernel: warp 0 producer, warp 1 issuer, NSETS epilogue sets of 4 warps (one per TMEM lane quadrant),
+// then the second issuer warp.  Measured (in the step): conv0 496 us with 2 sets, 437 us with 3; prob 237 / 313 us;
+// conv2 76 / 83 us -- so 3 sets for the 32-column (conv0) variant only.
+constexpr int fold_threads(int nsets) { return 32 * (3 + 4 * nsets); }
 
 struct TcOp {
     uint32_t a_off;     // byte offset of the A operand inside its ring plane (sub-plane + tap + chunk pair)
@@ -642,8 +646,8 @@ __device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab,
     }
 }
 
-template <int CW>
-__global__ void __launch_bounds__(kTcThreadsDual, 1)
+template <int CW, int NSETS>
+__global__ void __launch_bounds__(fold_threads(NSETS), 1)
 conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar_base = ptx::smem_u32(smem);
@@ -654,9 +658,12 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
     float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
-    float *s_edge = reinterpret_cast<float *>(smem + 1664);  // [2 epilogue sets][2 parities][16 groups of 32 positions][3] (fold_kw)
-    constexpr uint32_t kHdr = 2432;
-    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + 2 * 2 * 16 * 3 * 4 <= kHdr, "fold kernel header overflow");
+    // lane-shift edge values (fold_kw): CW = 16: [epilogue sets][2 parities][16 groups of 32 positions][3];
+    // CW = 32: [sets][2 parities][8 groups][24]
+    float *s_edge = reinterpret_cast<float *>(smem + 1664);
+    constexpr uint32_t kHdr = (CW == 32) ? 6400 : 2816;
+    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + NSETS * 2 * 16 * 3 * 4 <= 2816 &&
+                      1664 + NSETS * 2 * 8 * 24 * 4 <= 6400, "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
@@ -743,7 +750,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             }
             if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
         }
-    } else if (warp == 1 || warp == 10) {
+    } else if (warp == 1 || warp == 2 + 4 * NSETS) {
         // ================= MMA issuers =================
         // Two issuer warps split the M-TILES of every step (disjoint TMEM column regions, so no accumulator is shared between
         // them): the barrier waits and commits of one overlap the other's MMAs.  Both arrive on the plane's empty barrier
@@ -807,10 +814,11 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             L.dbg[blockIdx.x * 12 + 5] = g;
         }
     } else {
-        // ================= epilogue: 8 warps = 2 sets of 4 TMEM lane quadrants =================
-        // The two sets alternate over the OUTPUT PLANES: set e drains every other completed accumulator block, all M-tiles of
-        // its quadrant, so the fixed costs of a drain (barrier wait, tcgen05.ld / st round trips, release) are paid once per
-        // plane and quadrant and two planes are in the epilogue at any time.
+        // ================= epilogue: NSETS sets of 4 warps (one per TMEM lane quadrant) =================
+        // The sets take the OUTPUT PLANES in turn: set e drains every NSETS-th completed accumulator block, all M-tiles
+        // of its quadrant, so the fixed costs of a drain (barrier wait, tcgen05.ld / st round trips, release) are paid once
+        // per plane and quadrant and NSETS planes are in the epilogue at any time.  A drain is a long chain of dependent
+        // instructions in one warp (~7 cycles each), so its throughput scales with the number of sets, not with ILP.
         const int q = warp & 3;
         const int eset = (warp - 2) >> 2;
         const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
@@ -818,8 +826,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const int nchunk = (L.cout_group + 7) >> 3;
         const bool kwf = L.fold_kw != 0;
         uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
-        uint32_t estep = 0;              // output planes seen so far (parity: which set drains it)
-        long long epi_wait = 0, epi_work = 0;
+        uint32_t eturn = 0, ebuf = 0;    // whose turn the next output plane is; parity of this set's edge buffer
+        long long epi_wait = 0, epi_work = 0, ph_ld = 0, ph_st = 0, ph_bar = 0;
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
@@ -838,20 +846,114 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                              (uint32_t)((y0 + y) >> 1) * (L.Wout / 2) + (uint32_t)((x0 + x) >> 1);
                 }
             }
-            for (int e = 0; e < T; ++e, ++estep) {
+            for (int e = 0; e < T; ++e) {
                 const uint32_t myblk = blk;
                 if (++blk == (uint32_t)R) blk = 0;
-                if ((estep & 1u) != (uint32_t)eset) continue;  // the other set's plane
+                const uint32_t par = (fpar >> myblk) & 1u;
+                fpar ^= 1u << myblk;  // every completion of the block flips its phase, whichever set drains it
+                const bool mine = (eturn == (uint32_t)eset);
+                if (++eturn == (uint32_t)NSETS) eturn = 0;
+                if (!mine) continue;  // another set's plane
+                ebuf ^= 1u;
                 const long long c0 = clock64();
-                ptx::mbar_wait(tfull_bar(myblk), (fpar >> myblk) & 1u);
-                fpar ^= 1u << myblk;
+                ptx::mbar_wait(tfull_bar(myblk), par);
                 const long long c1 = clock64();
                 epi_wait += c1 - c0;
                 ptx::tcgen05_fence_after();
                 const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + myblk * CW;
                 const bool mirrored = myblk < 2;  // logical blocks 0 and 1 have a second part in physical blocks R, R+1
                 const size_t zoff = (size_t)(zs + e) * zstride;
-                if (kwf) {
+                if constexpr (CW == 32) {
+                    // conv0 (Cout = 8, kw folded into N, MT <= 2): column kw*8 + co of a block is
+                    // U_kw[p][co] = sum_{kh,ci} in[p + kh*P][ci] w[co][ci][kh][kw]; out[p] = U_0[p] + U_1[p+1] + U_2[p+2]
+                    // (columns 24..31 have zero weights).  Same lane shift + edge exchange as the prob layer below,
+                    // eight channels wide.
+                    uint32_t r[2][24];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        if (mt < MT) {
+#pragma unroll
+                            for (int c8 = 0; c8 < 3; ++c8) ptx::tmem_ld_x8(tb + mt * cols_mt + c8 * 8, &r[mt][c8 * 8]);
+                        }
+                    ptx::tmem_ld_wait();
+                    if (mirrored) {
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            if (mt < MT) {
+                                uint32_t r2[24];
+#pragma unroll
+                                for (int c8 = 0; c8 < 3; ++c8) ptx::tmem_ld_x8(tb + R * CW + mt * cols_mt + c8 * 8, &r2[c8 * 8]);
+                                ptx::tmem_ld_wait();
+#pragma unroll
+                                for (int k = 0; k < 24; ++k) r[mt][k] = __float_as_uint(__uint_as_float(r[mt][k]) + __uint_as_float(r2[k]));
+                            }
+                    }
+                    const long long p1 = clock64();
+                    ph_ld += p1 - c1;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        if (mt < MT) {
+                            ptx::tmem_st_zero_x16(tb + mt * cols_mt);
+                            ptx::tmem_st_zero_x16(tb + mt * cols_mt + 16);
+                            if (mirrored) {
+                                ptx::tmem_st_zero_x16(tb + R * CW + mt * cols_mt);
+                                ptx::tmem_st_zero_x16(tb + R * CW + mt * cols_mt + 16);
+                            }
+                        }
+                    ptx::tmem_st_wait();
+                    ptx::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
+                    const long long p2 = clock64();
+                    ph_st += p2 - p1;
+                    float *edge = s_edge + (eset * 2 + ebuf) * (8 * 24);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+                        if (mt < MT && lane < 2) {
+                            uint4 *eg = reinterpret_cast<uint4 *>(edge + (mt * 4 + q) * 24);
+                            if (lane == 0) {
+                                eg[0] = make_uint4(r[mt][8], r[mt][9], r[mt][10], r[mt][11]);
+                                eg[1] = make_uint4(r[mt][12], r[mt][13], r[mt][14], r[mt][15]);
+                            }
+                            eg[2 + lane * 2] = make_uint4(r[mt][16], r[mt][17], r[mt][18], r[mt][19]);
+                            eg[3 + lane * 2] = make_uint4(r[mt][20], r[mt][21], r[mt][22], r[mt][23]);
+                        }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+                    ph_bar += clock64() - p2;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        if (mt >= MT) continue;  // warp-uniform
+                        const int ng = mt * 4 + q + 1;  // next group of 32 positions (none after the tile's last one)
+                        const bool has = ng < MT * 4;
+                        // no divergence: every lane reads the next group's edge values (a broadcast for lanes < 30) and selects
+                        const uint4 *eg = reinterpret_cast<const uint4 *>(edge + (has ? ng : 0) * 24);
+                        const int l2 = lane == 31 ? 1 : 0;
+                        const uint4 a0 = eg[0], a1 = eg[1], b0 = eg[2 + l2 * 2], b1 = eg[3 + l2 * 2];
+                        const float e1[8] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z), __uint_as_float(a0.w),
+                                             __uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(a1.z), __uint_as_float(a1.w)};
+                        const float e2[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                             __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][8 + c]), 1);
+                            float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][16 + c]), 2);
+                            if (lane == 31) v1 = has ? e1[c] : 0.f;
+                            if (lane >= 30) v2 = has ? e2[c] : 0.f;
+                            v[c] = __uint_as_float(r[mt][c]) + v1 + v2 + s_shift[c];
+                            if (L.relu) v[c] = fmaxf(v[c], 0.f);
+                        }
+                        if (!((vmask >> mt) & 1u)) continue;
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[0], v[1]);
+                        pk.y = pack_bf16x2(v[2], v[3]);
+                        pk.z = pack_bf16x2(v[4], v[5]);
+                        pk.w = pack_bf16x2(v[6], v[7]);
+                        reinterpret_cast<uint4 *>(L.out)[(size_t)b * plane + base[mt] + zoff] = pk;
+                        if (L.out2 != nullptr)
+                            reinterpret_cast<uint4 *>(L.out2)[(size_t)b * 4 * plane_sp + sp[mt] + (size_t)(zs + e) * zstride_sp] = pk;
+                    }
+                } else if (kwf) {
                     // prob layer (Cout = 1, kw folded into N): only columns 0..2 of a block are ever non-zero
                     uint32_t r[4][4];
 #pragma unroll
@@ -869,6 +971,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 #pragma unroll
                             for (int k = 0; k < 3; ++k) r[mt][k] = __float_as_uint(__uint_as_float(r[mt][k]) + __uint_as_float(r2[mt][k]));
                     }
+                    const long long p1 = clock64();
+                    ph_ld += p1 - c1;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (mt < MT) {
@@ -883,7 +987,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     // p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the first two
                     // lanes of the next group (another warp of this set: TMEM lane quadrants are private), through shared
                     // memory and one named barrier of the set's 4 warps per plane.
-                    float *edge = s_edge + (eset * 2 + ((estep >> 1) & 1u)) * 48;  // double-buffered per set: one barrier per plane
+                    const long long p2 = clock64();
+                    ph_st += p2 - p1;
+                    float *edge = s_edge + (eset * 2 + ebuf) * 48;  // double-buffered per set: one barrier per plane
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (mt < MT && lane < 2) {
@@ -892,16 +998,19 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                             edge[grp * 3 + 1 + lane] = __uint_as_float(r[mt][2]);
                         }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+                    ph_bar += clock64() - p2;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
                         if (mt >= MT) continue;  // warp-uniform
                         const int ng = mt * 4 + q + 1;  // next group of 32 positions (none after the tile's last one)
                         float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][1]), 1);
                         float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][2]), 2);
-                        if (lane >= 30) {
+                        {   // no divergence: every lane reads the next group's edge values (a broadcast for lanes < 30) and selects
                             const bool has = ng < MT * 4;
-                            if (lane == 31) v1 = has ? edge[ng * 3 + 0] : 0.f;
-                            v2 = has ? edge[ng * 3 + 1 + (lane - 30)] : 0.f;
+                            const float *eg = edge + (has ? ng : 0) * 3;
+                            const float ea = eg[0], eb = eg[1 + (lane == 31 ? 1 : 0)];
+                            if (lane == 31) v1 = has ? ea : 0.f;
+                            if (lane >= 30) v2 = has ? eb : 0.f;
                         }
                         if (!((vmask >> mt) & 1u)) continue;
                         float v = __uint_as_float(r[mt][0]) + v1 + v2 + s_shift[0];
@@ -989,6 +1098,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         if (warp == 2 && lane == 0 && L.dbg) {
             L.dbg[blockIdx.x * 12 + 6] = epi_wait;
             L.dbg[blockIdx.x * 12 + 7] = epi_work;
+            L.dbg[blockIdx.x * 12 + 9] = ph_ld;    // kw-folded epilogues: accumulator loads (+ mirror) ...
+            L.dbg[blockIdx.x * 12 + 10] = ph_st;   // ... re-zeroing + release ...
+            L.dbg[blockIdx.x * 12 + 11] = ph_bar;  // ... edge exchange + set barrier; the rest of epi_work is shifts + stores
         }
     }
 
@@ -1047,6 +1159,7 @@ struct WPackParams {
     int nblocks, npad, cout_group, cout_total, cin_total, ngroups, transposed;
     int fold_cw;  // > 0: depth-folded layout, B row n = (kd = 2 - n / fold_cw, cout = n % fold_cw); src taps are kh*3+kw
     int fold_kw;  // 1: depth-folded layout with kw in N too: B row n = (kd = 2 - n / 16, kw = n % 16 < 3), Cout = 1; src taps are kh*3
+                  // 2: the same for Cout = 8 with 32-column blocks: B row n = (kd = 2 - n / 32, kw = (n % 32) / 8 < 3, cout = n % 8)
     int merged_t; // 1: class-merged transposed conv, B row n = (class n / cout, cout n % cout); src taps are dz*4+dy*2+dx
     int ntaps;    // taps per (cout, cin) pair in the source weights: 27 (3-D) or 9 (2-D, [Cout][Cin][3][3])
     int f16;      // 1: fp16 output, 0: bf16
@@ -1068,7 +1181,13 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     const int cin = p.src[blk].cin0[c] + e;
     int co = g * p.cout_group + n;
     int nn = n;
-    if (p.fold_cw > 0 && p.fold_kw) {
+    if (p.fold_cw > 0 && p.fold_kw == 2) {  // B row n = (kd = 2 - n / 32, kw = (n % 32) / 8 < 3, cout = n % 8)
+        const int kw = (n % p.fold_cw) >> 3;
+        nn = n & 7;
+        co = nn;
+        if (kw >= 3) tap = -1;
+        else if (tap >= 0) tap += (2 - n / p.fold_cw) * 9 + kw;
+    } else if (p.fold_cw > 0 && p.fold_kw) {
         const int kw = n % p.fold_cw;
         nn = 0;
         co = 0;
@@ -1133,6 +1252,11 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
     static const bool nofoldkw = getenv("MVS_TC_NOFOLDKW") != nullptr;  // A/B knob
     const bool fold_kw = fold && cin == 8 && cout == 1 && !nofoldkw;
+    // conv0 (32 -> 8): kw folded into N as well, 32-column blocks [kw][8 Cout] (24 used), N = 96: 6 MMAs of 56 cycles per
+    // plane and M-tile instead of 18 of 44 -- the layer was bound by the shared-memory operand path of its MMAs
+    static const bool nofoldkw8 = getenv("MVS_TC_NOFOLDKW8") != nullptr;  // A/B knob
+    const bool fold_kw8 = fold && cin >= 16 && cout == 8 && !nofoldkw8;
+    const int fold_cw = fold ? (fold_kw8 ? 32 : 16) : 0;
     const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
     // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
     static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
@@ -1140,6 +1264,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     int ntaps_ops;  // MMA instructions per step
     if (merged_t) ntaps_ops = 8 * kpairs_tap;
     else if (fold_kw) ntaps_ops = 2;
+    else if (fold_kw8) ntaps_ops = 3 * kpairs_tap;
     else if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
     else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
     else ntaps_ops = (kind == TC_CONVT) ? 27 : 15;  // cin == 8: taps are paired (conv) / not paired (convT, unused)
@@ -1148,13 +1273,13 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     int ngroups = 1;
     int cout_group = cout;
     while (!merged_t) {
-        const int npad_try = fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
+        const int npad_try = fold ? 3 * fold_cw : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
         if ((size_t)ntaps_ops * npad_try * 32 <= 112 * 1024 && cout_group <= 64) break;
         ngroups *= 2;
         cout_group = cout / ngroups;
         MVS_REQUIRE(cout_group >= 8 && cout % ngroups == 0, "tc conv: cannot split Cout=%d", cout);
     }
-    const int npad = merged_t ? 8 * cout : (fold ? 48 : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64)));
+    const int npad = merged_t ? 8 * cout : (fold ? 3 * fold_cw : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64)));
     const int nacc = (kind == TC_CONVT && !merged_t) ? 8 : 1;
     const int wbytes = ntaps_ops * npad * 32;
     // ring geometry
@@ -1167,7 +1292,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
     double best_score = -1;
     // MT limit: 2 buffers x nacc x MT x npad <= 512 columns; folded: MT regions of R blocks x 16 columns, R >= 8
-    const int tmem_budget = fold ? 4 : 256 / (nacc * npad);
+    const int tmem_budget = fold ? (fold_kw8 ? 2 : 4) : 256 / (nacc * npad);
     for (int nx = 1; nx <= 64; ++nx) {
         const int TXB = (Wt + nx - 1) / nx;
         if (TXB > max_cols) continue;
@@ -1179,7 +1304,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
-                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768;
+                const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
+                                     (fold ? (fold_kw8 ? 4096 : 512) : 0);
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -1245,16 +1371,16 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     WPackParams &W = pl.W;
     W.npad = npad; W.cout_group = cout_group; W.cout_total = cout; W.cin_total = cin; W.ngroups = ngroups;
     W.transposed = (kind == TC_CONVT);
-    W.fold_cw = fold ? 16 : 0;
-    W.fold_kw = fold_kw ? 1 : 0;
-    L.fold_kw = fold_kw ? 1 : 0;
+    W.fold_cw = fold_cw;
+    W.fold_kw = fold_kw ? 1 : (fold_kw8 ? 2 : 0);
+    L.fold_kw = W.fold_kw;
     W.ntaps = is2d ? 9 : 27;
     W.merged_t = merged_t ? 1 : 0;
     L.merged_t = merged_t ? 1 : 0;
     L.fold = fold ? 1 : 0;
     static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
     L.dual = (!fold && !nodual) ? 1 : 0;
-    L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * 16)) : 0;
+    L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * fold_cw)) : 0;
     const int chunk_stride = rows * P * 16;
     int nops = 0;
     auto tap_off = [&](int kh, int kw) -> int {  // byte offset of a conv tap inside its plane (chunk 0)
@@ -1267,7 +1393,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         for (int kd = 0; kd < ((fold || is2d) ? 1 : 3); ++kd) {  // folded: kd lives in the rows of the packed B block; 2-D: no kd
             if (cin >= 16) {
                 for (int kh = 0; kh < 3; ++kh)
-                    for (int kw = 0; kw < 3; ++kw)
+                    for (int kw = 0; kw < (fold_kw8 ? 1 : 3); ++kw)  // fold_kw8: kw lives in the rows of the packed B block
                         for (int kc = 0; kc < cin / 16; ++kc) {
                             TcOp &op = L.ops[nops];
                             op.a_off = tap_off(kh, kw) + 2 * kc * chunk_stride;
@@ -1378,7 +1504,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     }
     pl.npad = npad;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
-    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768;
+    pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
+                    (fold ? (fold_kw8 ? 4096 : 512) : 0);
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
@@ -1545,11 +1672,12 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
         // per-layer one that a concurrent launch of another layer could lower between this call and the launch
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        kern<<<pl.grid, (pl.L.dual || pl.L.fold) ? kTcThreadsDual : kTcThreads, pl.smem_bytes, st>>>(pl.tmap, pl.L);
+        kern<<<pl.grid, pl.L.fold ? fold_threads(pl.L.fold_kw == 2 ? 3 : 2) : (pl.L.dual ? kTcThreadsDual : kTcThreads), pl.smem_bytes, st>>>(
+            pl.tmap, pl.L);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };
-    if (pl.L.fold) return launch(conv3d_tc_fold_kernel<16>);
+    if (pl.L.fold) return pl.L.fold_kw == 2 ? launch(conv3d_tc_fold_kernel<32, 3>) : launch(conv3d_tc_fold_kernel<16, 2>);
     // lean epilogue when there is one accumulator per M-tile, no skip connection and a 16-bit output
     const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32 && !pl.L.merged_t;
     if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true, 1>) : launch(conv3d_tc_kernel<32, true, 1>);
