@@ -51,8 +51,9 @@ constexpr int kMaxAcc = 8;
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kTcThreadsDual = 352;  // + warp 10: second MMA issuer
 // depth-folded kernel: warp 0 producer, warp 1 issuer, NSETS epilogue sets of 4 warps (one per TMEM lane quadrant),
-// then the second issuer warp.  Measured (in the step): conv0 496 us with 2 sets, 437 us with 3; prob 237 / 313 us;
-// conv2 76 / 83 us -- so 3 sets for the 32-column (conv0) variant only.
+// then the second issuer warp.  Measured (in the step): conv0 496 us with 2 sets, 437 us with 3; prob 210 / 160 us.
+// 3 sets cap the kernel at 128 registers: fine for the kw-folded variants (119 / 128), not for the plain one (161:
+// spills in the drain loop cost more than the third set gives), which keeps 2 sets.
 constexpr int fold_threads(int nsets) { return 32 * (3 + 4 * nsets); }
 
 struct TcOp {
@@ -103,6 +104,7 @@ struct TcLayer {
     int dual;        // 1: two MMA issuer warps alternate over the steps
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
+    int fold_sets;   // depth-folded kernel: number of epilogue sets (2 or 3)
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
                      //    the three partial sums of x, x+1, x+2 (lane shifts)
     TcOp ops[kMaxOps];
@@ -646,7 +648,7 @@ __device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab,
     }
 }
 
-template <int CW, int NSETS>
+template <int CW, int NSETS, bool KWF>  // KWF: kw folded into N too (CW = 16: prob, Cout = 1; CW = 32: conv0, Cout = 8)
 __global__ void __launch_bounds__(fold_threads(NSETS), 1)
 conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -824,10 +826,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const size_t plane = (size_t)L.Dout * L.Hout * L.Wout;
         const size_t zstride = (size_t)L.Hout * L.Wout;
         const int nchunk = (L.cout_group + 7) >> 3;
-        const bool kwf = L.fold_kw != 0;
         uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
         uint32_t eturn = 0, ebuf = 0;    // whose turn the next output plane is; parity of this set's edge buffer
-        long long epi_wait = 0, epi_work = 0, ph_ld = 0, ph_st = 0, ph_bar = 0;
+        long long epi_wait = 0, epi_work = 0;
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
@@ -888,8 +889,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                                 for (int k = 0; k < 24; ++k) r[mt][k] = __float_as_uint(__uint_as_float(r[mt][k]) + __uint_as_float(r2[k]));
                             }
                     }
-                    const long long p1 = clock64();
-                    ph_ld += p1 - c1;
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt)
                         if (mt < MT) {
@@ -904,8 +903,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     ptx::tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
-                    const long long p2 = clock64();
-                    ph_st += p2 - p1;
                     float *edge = s_edge + (eset * 2 + ebuf) * (8 * 24);
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt)
@@ -919,7 +916,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                             eg[3 + lane * 2] = make_uint4(r[mt][20], r[mt][21], r[mt][22], r[mt][23]);
                         }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
-                    ph_bar += clock64() - p2;
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         if (mt >= MT) continue;  // warp-uniform
@@ -953,7 +949,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                         if (L.out2 != nullptr)
                             reinterpret_cast<uint4 *>(L.out2)[(size_t)b * 4 * plane_sp + sp[mt] + (size_t)(zs + e) * zstride_sp] = pk;
                     }
-                } else if (kwf) {
+                } else if constexpr (KWF) {
                     // prob layer (Cout = 1, kw folded into N): only columns 0..2 of a block are ever non-zero
                     uint32_t r[4][4];
 #pragma unroll
@@ -971,8 +967,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 #pragma unroll
                             for (int k = 0; k < 3; ++k) r[mt][k] = __float_as_uint(__uint_as_float(r[mt][k]) + __uint_as_float(r2[mt][k]));
                     }
-                    const long long p1 = clock64();
-                    ph_ld += p1 - c1;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (mt < MT) {
@@ -987,8 +981,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     // p+1, p+2 are the next lanes; the last two lanes of a 32-position group take them from the first two
                     // lanes of the next group (another warp of this set: TMEM lane quadrants are private), through shared
                     // memory and one named barrier of the set's 4 warps per plane.
-                    const long long p2 = clock64();
-                    ph_st += p2 - p1;
                     float *edge = s_edge + (eset * 2 + ebuf) * 48;  // double-buffered per set: one barrier per plane
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
@@ -998,7 +990,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                             edge[grp * 3 + 1 + lane] = __uint_as_float(r[mt][2]);
                         }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
-                    ph_bar += clock64() - p2;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
                         if (mt >= MT) continue;  // warp-uniform
@@ -1098,9 +1089,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         if (warp == 2 && lane == 0 && L.dbg) {
             L.dbg[blockIdx.x * 12 + 6] = epi_wait;
             L.dbg[blockIdx.x * 12 + 7] = epi_work;
-            L.dbg[blockIdx.x * 12 + 9] = ph_ld;    // kw-folded epilogues: accumulator loads (+ mirror) ...
-            L.dbg[blockIdx.x * 12 + 10] = ph_st;   // ... re-zeroing + release ...
-            L.dbg[blockIdx.x * 12 + 11] = ph_bar;  // ... edge exchange + set barrier; the rest of epi_work is shifts + stores
         }
     }
 
@@ -1381,6 +1369,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
     L.dual = (!fold && !nodual) ? 1 : 0;
     L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * fold_cw)) : 0;
+    L.fold_sets = fold ? ((fold_kw8 || fold_kw) ? 3 : 2) : 0;  // the plain variant needs > 128 registers: 2 sets
     const int chunk_stride = rows * P * 16;
     int nops = 0;
     auto tap_off = [&](int kh, int kw) -> int {  // byte offset of a conv tap inside its plane (chunk 0)
@@ -1672,12 +1661,16 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
         // per-layer one that a concurrent launch of another layer could lower between this call and the launch
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        kern<<<pl.grid, pl.L.fold ? fold_threads(pl.L.fold_kw == 2 ? 3 : 2) : (pl.L.dual ? kTcThreadsDual : kTcThreads), pl.smem_bytes, st>>>(
+        kern<<<pl.grid, pl.L.fold ? fold_threads(pl.L.fold_sets) : (pl.L.dual ? kTcThreadsDual : kTcThreads), pl.smem_bytes, st>>>(
             pl.tmap, pl.L);
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };
-    if (pl.L.fold) return pl.L.fold_kw == 2 ? launch(conv3d_tc_fold_kernel<32, 3>) : launch(conv3d_tc_fold_kernel<16, 2>);
+    if (pl.L.fold) {
+        if (pl.L.fold_kw == 2) return launch(conv3d_tc_fold_kernel<32, 3, true>);
+        if (pl.L.fold_kw) return launch(conv3d_tc_fold_kernel<16, 3, true>);
+        return launch(conv3d_tc_fold_kernel<16, 2, false>);
+    }
     // lean epilogue when there is one accumulator per M-tile, no skip connection and a 16-bit output
     const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32 && !pl.L.merged_t;
     if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true, 1>) : launch(conv3d_tc_kernel<32, true, 1>);

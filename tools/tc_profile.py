@@ -26,5 +26,5 @@ for name, kind, ci, co, d, h, w in layers:
     t = t[t[:, 5] > 0]
     steps = t[:, 5].mean().item()
     m = t.mean(0) / steps
-    print("%-7s steps/CTA %6.1f | per step cycles: total %7.0f  mma: wait_full %6.0f wait_tmem %6.0f issue %6.0f | epi: wait %6.0f work %6.0f | producer wait_empty %6.0f | release %5.0f | epi phases ld %5.0f st %5.0f bar %5.0f"
-          % (name, steps, m[4], m[1], m[2], m[3], m[6], m[7], m[0], m[8], m[9], m[10], m[11]))
+    print("%-7s steps/CTA %6.1f | per step cycles: total %7.0f  mma: wait_full %6.0f wait_tmem %6.0f issue %6.0f | epi: wait %6.0f work %6.0f | producer wait_empty %6.0f | release %5.0f"
+          % (name, steps, m[4], m[1], m[2], m[3], m[6], m[7], m[0], m[8]))
