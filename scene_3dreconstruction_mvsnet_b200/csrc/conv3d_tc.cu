@@ -105,6 +105,8 @@ struct TcLayer {
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     int fold_sets;   // depth-folded kernel: number of epilogue sets (2 or 3)
+    int mma_n;       // > 0: N of the tcgen05.mma (kw-folded 2-D layers: 3*Cout rounded up to 16) -- the TMEM column stride
+                     //      per M-tile stays the template's NPAD
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
                      //    the three partial sums of x, x+1, x+2 (lane shifts)
     TcOp ops[kMaxOps];
@@ -271,7 +273,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // warp's MMAs instead of leaving the tensor pipe idle.
         const uint32_t me = (warp == 10) ? 1u : 0u;
         const bool leader = ptx::elect_one();
-        const uint32_t idesc = F16 ? ptx::make_idesc_f16_m128(NPAD) : ptx::make_idesc_bf16_m128(NPAD);
+        const uint32_t mma_n = L.mma_n > 0 ? (uint32_t)L.mma_n : (uint32_t)NPAD;
+        const uint32_t idesc = F16 ? ptx::make_idesc_f16_m128(mma_n) : ptx::make_idesc_bf16_m128(mma_n);
         uint32_t st = 0;
         uint32_t s0 = 0;    // ring slot of the oldest plane of the current step
         uint32_t par = 0;   // bit s: parity of the fill of slot s that is current (toggles when the slot is released)
@@ -372,9 +375,23 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const float relu_lo = L.relu ? 0.f : -3.0e38f;
         uint32_t st = 0;
         long long epi_wait = 0, epi_work = 0;
+        // (row, col) of this thread's position in each M-tile: the same for every item (the division is hoisted out of the
+        // item loop -- 2-D layers have items of one to five steps)
+        uint32_t yx0 = 0, yx1 = 0, yx2 = 0, yx3 = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int pos = mt * 128 + q * 32 + lane;
+            const int y = pos / L.P, x = pos - y * L.P;
+            const uint32_t yx = ((uint32_t)y << 16) | (uint32_t)x;
+            if (mt == 0) yx0 = yx; else if (mt == 1) yx1 = yx; else if (mt == 2) yx2 = yx; else yx3 = yx;
+        }
         for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
+            if (STEPWISE && T == 1 && (st & 1u) != (uint32_t)eset) {  // a one-step item that the other warp set drains
+                ++st;
+                continue;
+            }
             size_t base0 = 0, base1 = 0, base2 = 0, base3 = 0;
             uint32_t sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;  // per-batch offsets into the parity-split second output (L.out2)
             const size_t plane_sp = (size_t)L.Dout * (L.Hout / 2) * (L.Wout / 2);
@@ -382,8 +399,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
                 if (mt < L.MT) {
-                    const int pos = mt * 128 + q * 32 + lane;
-                    const int y = pos / L.P, x = pos - y * L.P;
+                    const uint32_t yx = mt == 0 ? yx0 : (mt == 1 ? yx1 : (mt == 2 ? yx2 : yx3));
+                    const int y = (int)(yx >> 16), x = (int)(yx & 0xffffu);
                     const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
                     if (L.out2 != nullptr) {
                         const uint32_t sp = (uint32_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * (uint32_t)plane_sp +
@@ -413,7 +430,53 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 ptx::tcgen05_fence_after();
                 const size_t zoff = (size_t)(zs + t) * zstride;
                 const uint32_t tbuf = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ncols_buf;
-                if constexpr (EPI == 2) {
+                if constexpr (EPI == 3) {
+                    // kw-folded 2-D layer (FeatureNet): column kw*COUT + co of an M-tile is
+                    // U_kw[p][co] = sum_{kh,ci} in[p + kh*P][ci] w[co][ci][kh][kw]; out[p] = U_0[p] + U_1[p+1] + U_2[p+2].
+                    // The row pitch is P = 32 positions = one 32-lane group, and the last two positions of a row are halo
+                    // (never an output), so the shift never leaves the warp: two shuffles per channel, no edge exchange.
+                    constexpr int COUT = (NPAD == 32) ? 8 : (NPAD == 64 ? 16 : 32);
+                    constexpr int MB = (COUT == 8) ? 2 : 1;  // M-tiles per batch
+                    uint4 *oz = reinterpret_cast<uint4 *>(L.out) + zoff;
+                    for (int m0 = 0; m0 < L.MT; m0 += MB) {
+                        uint32_t r[MB][3 * COUT];
+#pragma unroll
+                        for (int i = 0; i < MB; ++i)
+                            if (m0 + i < L.MT) {
+#pragma unroll
+                                for (int c8 = 0; c8 < 3 * COUT / 8; ++c8) ptx::tmem_ld_x8(tbuf + (m0 + i) * NPAD + c8 * 8, &r[i][c8 * 8]);
+                            }
+                        ptx::tmem_ld_wait();
+                        if (m0 + MB >= L.MT) {  // everything this warp needs from the buffer is in registers
+                            ptx::tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+                        }
+#pragma unroll
+                        for (int i = 0; i < MB; ++i) {
+                            const int mt = m0 + i;
+                            if (mt >= L.MT) continue;  // warp-uniform
+                            uint32_t pk[COUT / 2];
+#pragma unroll
+                            for (int c = 0; c < COUT; c += 2) {
+                                float v[2];
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][COUT + c + h]), 1);
+                                    const float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2 * COUT + c + h]), 2);
+                                    v[h] = fmaxf(__uint_as_float(r[i][c + h]) + v1 + v2 + s_shift[c + h], relu_lo);
+                                }
+                                pk[c / 2] = pack16x2<F16>(v[0], v[1]);
+                            }
+                            if (!((vmask >> mt) & 1u)) continue;
+                            uint4 *op = oz + (mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3)));
+#pragma unroll
+                            for (int c8 = 0; c8 < COUT / 8; ++c8)
+                                op[(size_t)c8 * plane] = make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+                        }
+                    }
+                    epi_work += clock64() - c1;
+                } else if constexpr (EPI == 2) {
                     // Class-merged transposed conv: the M-tile's NPAD columns are [class (pz,py,px)][Cout].  A "pair" is
                     // the two x-parity classes of one (pz, py, channel chunk): their output chunks are adjacent in
                     // memory (voxels 2x and 2x+1), so each thread moves 32 contiguous bytes with one 256-bit load /
@@ -1151,6 +1214,7 @@ struct WPackParams {
     int merged_t; // 1: class-merged transposed conv, B row n = (class n / cout, cout n % cout); src taps are dz*4+dy*2+dx
     int ntaps;    // taps per (cout, cin) pair in the source weights: 27 (3-D) or 9 (2-D, [Cout][Cin][3][3])
     int f16;      // 1: fp16 output, 0: bf16
+    int kw2d;     // 1: 2-D layer with kw folded into N: B row n = (kw = n / cout < 3, cout = n % cout); src taps are kh*3
     WSrc src[kMaxOps];
 };
 
@@ -1169,7 +1233,13 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     const int cin = p.src[blk].cin0[c] + e;
     int co = g * p.cout_group + n;
     int nn = n;
-    if (p.fold_cw > 0 && p.fold_kw == 2) {  // B row n = (kd = 2 - n / 32, kw = (n % 32) / 8 < 3, cout = n % 8)
+    if (p.kw2d) {
+        const int kw = n / p.cout_total;
+        nn = n % p.cout_total;
+        co = nn;
+        if (kw >= 3) tap = -1;
+        else if (tap >= 0) tap += kw;
+    } else if (p.fold_cw > 0 && p.fold_kw == 2) {  // B row n = (kd = 2 - n / 32, kw = (n % 32) / 8 < 3, cout = n % 8)
         const int kw = (n % p.fold_cw) >> 3;
         nn = n & 7;
         co = nn;
@@ -1215,6 +1285,7 @@ struct TcPlan {
     WPackParams W;
     CUtensorMap tmap;
     int npad;
+    bool kw2d;
     size_t smem_bytes;
     size_t wpacked_bytes;
     int grid;
@@ -1224,7 +1295,7 @@ static constexpr int kSmemLimit = 227 * 1024;
 
 // Builds the plan for one layer.  in: bf16 CP8 [B][cin/8][Din][Hin][Win][8].
 static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din, int Hin, int Win, const void *in_ptr,
-                     int num_sms, bool encode = true, bool in_split = false) {
+                     int num_sms, bool encode = true, bool in_split = false, bool allow_kw2d = false) {
     TcLayer &L = pl.L;
     memset(&pl, 0, sizeof(pl));
     MVS_REQUIRE(cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
@@ -1249,9 +1320,19 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
     static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
     const bool merged_t = (kind == TC_CONVT) && cin >= 16 && 8 * cout <= 128 && !nomerge;
+    // 2-D layers with fp16 operands (FeatureNet): kw folded into N (N = 3*Cout), row pitch fixed at 32 positions so that the
+    // epilogue's lane shifts stay inside a warp
+    static const bool nokw2d = getenv("MVS_TC_NOKW2D") != nullptr;  // A/B knob
+    // Measured per FeatureNet layer (tools/featurenet_tc_profile.py, kw-folded / plain, ms): 8->8 k3 0.119 / 0.099 (the
+    // plain form has only 5 MMAs per M-tile: the fold's 3x larger accumulator read dominates), 32(s2d)->16 0.044 / 0.065,
+    // 16->16 0.038 / 0.040, 64(s2d)->32 0.032 / 0.037, 32->32 0.027 / 0.021 -- so: folded when the plain form has >= 9
+    // MMAs per M-tile and Cout <= 16, or >= 36 with Cout = 32.
+    const bool kw2d = is2d && allow_kw2d && !nokw2d && Win >= 30 &&
+                      (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64));
     int ntaps_ops;  // MMA instructions per step
     if (merged_t) ntaps_ops = 8 * kpairs_tap;
     else if (fold_kw) ntaps_ops = 2;
+    else if (kw2d) ntaps_ops = (cin >= 16) ? 3 * kpairs_tap : 2;
     else if (fold_kw8) ntaps_ops = 3 * kpairs_tap;
     else if (fold || is2d) ntaps_ops = (cin >= 16) ? 9 * kpairs_tap : 5;
     else if (cin >= 16) ntaps_ops = 27 * kpairs_tap;
@@ -1260,14 +1341,14 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     MVS_REQUIRE(ntaps_ops <= kMaxOps, "tc conv: too many ops");
     int ngroups = 1;
     int cout_group = cout;
-    while (!merged_t) {
+    while (!merged_t && !kw2d) {
         const int npad_try = fold ? 3 * fold_cw : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64));
         if ((size_t)ntaps_ops * npad_try * 32 <= 112 * 1024 && cout_group <= 64) break;
         ngroups *= 2;
         cout_group = cout / ngroups;
         MVS_REQUIRE(cout_group >= 8 && cout % ngroups == 0, "tc conv: cannot split Cout=%d", cout);
     }
-    const int npad = merged_t ? 8 * cout : (fold ? 3 * fold_cw : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64)));
+    const int npad = kw2d ? std::max(32, 3 * cout) : merged_t ? 8 * cout : (fold ? 3 * fold_cw : (cout_group <= 16 ? 16 : (cout_group <= 32 ? 32 : 64)));
     const int nacc = (kind == TC_CONVT && !merged_t) ? 8 : 1;
     const int wbytes = ntaps_ops * npad * 32;
     // ring geometry
@@ -1280,9 +1361,11 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
     double best_score = -1;
     // MT limit: 2 buffers x nacc x MT x npad <= 512 columns; folded: MT regions of R blocks x 16 columns, R >= 8
-    const int tmem_budget = fold ? (fold_kw8 ? 2 : 4) : 256 / (nacc * npad);
+    const int npad_cols = kw2d ? (cout == 8 ? 32 : (cout == 16 ? 64 : 128)) : npad;  // TMEM columns per M-tile (the template's NPAD)
+    const int tmem_budget = fold ? (fold_kw8 ? 2 : 4) : 256 / (nacc * npad_cols);
     for (int nx = 1; nx <= 64; ++nx) {
-        const int TXB = (Wt + nx - 1) / nx;
+        const int TXB = kw2d ? 30 : (Wt + nx - 1) / nx;
+        if (kw2d && nx > 1) break;
         if (TXB > max_cols) continue;
         const int P = TXB + halo;
         for (int MT = 1; MT <= 4 && MT <= tmem_budget; ++MT) {
@@ -1297,7 +1380,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
-                const double xeff = (double)Wt / (nx * TXB);
+                const double xeff = kw2d ? (double)Wt / (((Wt + TXB - 1) / TXB) * TXB) : (double)Wt / (nx * TXB);
                 const double yeff = (double)Ht / (((Ht + TY - 1) / TY) * TY);
                 const double pipe = (nslot >= need + 2 * adv) ? 1.0 : (nslot >= need + adv ? 0.9 : 0.6);
                 const double score = useful * xeff * yeff * pipe * (0.9 + 0.1 * (double)TY / rows);
@@ -1343,7 +1426,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const long long items = (long long)cols * nseg;
             const double wave = (double)items / ((double)((items + num_sms - 1) / num_sms) * num_sms);
             const double haloeff = fold ? (double)len / (len + 2) : (double)(adv * len) / (adv * (len - 1) + need);
-            const double sc = wave * haloeff;
+            const double sc = wave * haloeff * (is2d ? (double)len / (len + 0.05) : 1.0);  // 2-D: per-item setup
+
             if (sc > best + 1e-9) { best = sc; zsegs = zs; }
         }
     }
@@ -1363,6 +1447,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.fold_kw = fold_kw ? 1 : (fold_kw8 ? 2 : 0);
     L.fold_kw = W.fold_kw;
     W.ntaps = is2d ? 9 : 27;
+    W.kw2d = kw2d ? 1 : 0;
+    L.mma_n = kw2d ? npad : 0;
     W.merged_t = merged_t ? 1 : 0;
     L.merged_t = merged_t ? 1 : 0;
     L.fold = fold ? 1 : 0;
@@ -1382,7 +1468,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         for (int kd = 0; kd < ((fold || is2d) ? 1 : 3); ++kd) {  // folded: kd lives in the rows of the packed B block; 2-D: no kd
             if (cin >= 16) {
                 for (int kh = 0; kh < 3; ++kh)
-                    for (int kw = 0; kw < (fold_kw8 ? 1 : 3); ++kw)  // fold_kw8: kw lives in the rows of the packed B block
+                    for (int kw = 0; kw < ((fold_kw8 || kw2d) ? 1 : 3); ++kw)  // kw folds: kw lives in the rows of the packed B block
                         for (int kc = 0; kc < cin / 16; ++kc) {
                             TcOp &op = L.ops[nops];
                             op.a_off = tap_off(kh, kw) + 2 * kc * chunk_stride;
@@ -1392,7 +1478,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
                             W.src[nops] = WSrc{{(int16_t)tap, (int16_t)tap}, {(int16_t)(16 * kc), (int16_t)(16 * kc + 8)}};
                             ++nops;
                         }
-            } else if (fold_kw) {  // K = (kh, 8 channels): kh = 0,1 in one instruction, kh = 2 (+ a zero chunk) in the other
+            } else if (fold_kw || kw2d) {  // K = (kh, 8 channels): kh = 0,1 in one instruction, kh = 2 (+ a zero chunk) in the other
                 for (int i = 0; i < 2; ++i) {
                     TcOp &op = L.ops[nops];
                     op.a_off = tap_off(2 * i, 0);
@@ -1491,7 +1577,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
         op.a_lo = ((op.a_off >> 4) & 0x3FFFu) | ((op.lbo >> 4) << 16);
         op.b_lo = (((uint32_t)op.widx * npad * 32) >> 4) | (((uint32_t)npad * 16 >> 4) << 16);
     }
-    pl.npad = npad;
+    pl.npad = npad_cols;
+    pl.kw2d = kw2d;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
     pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
                     (fold ? (fold_kw8 ? 4096 : 512) : 0);
@@ -1623,10 +1710,10 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
                      int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false, void *out2 = nullptr,
                      bool in_split = false) {
     static thread_local TcPlan pl;  // ~3 KB; not kept across calls
-    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split)) return rc;
+    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split, f16 != 0 && skip == nullptr && !out_f32)) return rc;
     MVS_REQUIRE(out2 == nullptr || (out_mode == 0 && !out_f32 && !f16 && (pl.L.fold || pl.L.nacc == 1) && skip == nullptr && Hin % 2 == 0 && Win % 2 == 0), "second output: plain conv layers only");
     pl.L.out2 = out2;
-    MVS_REQUIRE(!f16 || (kind == TC_CONV2D && pl.npad <= 32 && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
+    MVS_REQUIRE(!f16 || (kind == TC_CONV2D && (pl.npad <= 32 || pl.kw2d) && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
     MVS_REQUIRE(out_mode == 0 || (kind == TC_CONV2D && B == 1), "alternative output layouts: 2-D layers only");
     MVS_REQUIRE(out_mode != 1 || (Hin % 2 == 0 && Win % 2 == 0), "space-to-depth output needs even H, W");
     pl.L.f16 = f16;
@@ -1673,6 +1760,10 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     }
     // lean epilogue when there is one accumulator per M-tile, no skip connection and a 16-bit output
     const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32 && !pl.L.merged_t;
+    if (pl.kw2d) {
+        if (pl.npad == 32) return launch(conv3d_tc_kernel<32, true, 3>);
+        return pl.npad == 64 ? launch(conv3d_tc_kernel<64, true, 3>) : launch(conv3d_tc_kernel<128, true, 3>);
+    }
     if (f16) return pl.npad == 16 ? launch(conv3d_tc_kernel<16, true, 1>) : launch(conv3d_tc_kernel<32, true, 1>);
     if (pl.L.merged_t) return pl.npad == 64 ? launch(conv3d_tc_kernel<64, false, 2>) : launch(conv3d_tc_kernel<128, false, 2>);
     if (simple) {
