@@ -105,6 +105,7 @@ struct TcLayer {
     int fold;        // 1: depth-folded variant (conv3d_tc_fold_kernel): the three kd taps are folded into N
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     int fold_sets;   // depth-folded kernel: number of epilogue sets (2 or 3)
+    unsigned long long rcp_zsegs, rcp_tiles_x, rcp_tiles_y;  // ceil(2^40 / d) for the item decode
     int mma_n;       // > 0: N of the tcgen05.mma (kw-folded 2-D layers: 3*Cout rounded up to 16) -- the TMEM column stride
                      //      per M-tile stays the template's NPAD
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
@@ -116,13 +117,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
-__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
-    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t *>(&v);
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {  // saturating (finite) conversion: one F2FP instead of 4 FMNMX + F2FP
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
     return F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+}
+
+// floor(n / d) for n < 2^20 with rcp = ceil(2^40 / d)
+__device__ __forceinline__ uint32_t fast_div40(uint32_t n, unsigned long long rcp) {
+    return (uint32_t)(((unsigned long long)n * rcp) >> 40);
 }
 
 // One elected lane issues every tcgen05.mma of one z-step.  Per op: one 8-byte shared-memory load of the two
@@ -218,11 +225,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const int ctas_per_group = (gridDim.x - group + L.ngroups - 1) / L.ngroups;
 
     auto decode = [&](int it, int &b, int &x0, int &y0, int &zs, int &T) {
-        int r = it;
-        const int zseg = r % L.zsegs; r /= L.zsegs;
-        const int tx = r % L.tiles_x; r /= L.tiles_x;
-        const int ty = r % L.tiles_y; r /= L.tiles_y;
-        b = r;
+        // divisions by the per-layer constants through 2^40 reciprocals (exact for it < 2^20): ~4 instructions each; an
+        // item of a 2-D layer is one to five steps, and six integer divisions per item were a visible share of them
+        uint32_t r = (uint32_t)it;
+        uint32_t qd = fast_div40(r, L.rcp_zsegs);
+        const int zseg = (int)(r - qd * (uint32_t)L.zsegs); r = qd;
+        qd = fast_div40(r, L.rcp_tiles_x);
+        const int tx = (int)(r - qd * (uint32_t)L.tiles_x); r = qd;
+        qd = fast_div40(r, L.rcp_tiles_y);
+        const int ty = (int)(r - qd * (uint32_t)L.tiles_y); r = qd;
+        b = (int)r;
         x0 = tx * L.TXB;
         y0 = ty * L.TY;
         zs = zseg * L.zseg_len;
@@ -783,11 +795,16 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     ptx::tcgen05_fence_after();
 
     auto decode = [&](int it, int &b, int &x0, int &y0, int &zs, int &T) {
-        int r = it;
-        const int zseg = r % L.zsegs; r /= L.zsegs;
-        const int tx = r % L.tiles_x; r /= L.tiles_x;
-        const int ty = r % L.tiles_y; r /= L.tiles_y;
-        b = r;
+        // divisions by the per-layer constants through 2^40 reciprocals (exact for it < 2^20): ~4 instructions each; an
+        // item of a 2-D layer is one to five steps, and six integer divisions per item were a visible share of them
+        uint32_t r = (uint32_t)it;
+        uint32_t qd = fast_div40(r, L.rcp_zsegs);
+        const int zseg = (int)(r - qd * (uint32_t)L.zsegs); r = qd;
+        qd = fast_div40(r, L.rcp_tiles_x);
+        const int tx = (int)(r - qd * (uint32_t)L.tiles_x); r = qd;
+        qd = fast_div40(r, L.rcp_tiles_y);
+        const int ty = (int)(r - qd * (uint32_t)L.tiles_y); r = qd;
+        b = (int)r;
         x0 = tx * L.TXB;
         y0 = ty * L.TY;
         zs = zseg * L.zseg_len;
@@ -1434,6 +1451,9 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     L.zseg_len = (Dt + zsegs - 1) / zsegs;
     L.zsegs = (Dt + L.zseg_len - 1) / L.zseg_len;
     L.n_items = cols * L.zsegs;
+    MVS_REQUIRE(L.n_items < (1 << 20), "tc conv: too many work items (%d)", L.n_items);
+    auto rcp40 = [](int d) { return (unsigned long long)(((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d); };
+    L.rcp_zsegs = rcp40(L.zsegs); L.rcp_tiles_x = rcp40(L.tiles_x); L.rcp_tiles_y = rcp40(L.tiles_y);
     L.nacc = nacc; L.npad = npad; L.wbytes_group = wbytes;
     L.cout_group = cout_group; L.cout_total = cout;
     L.out_scale = (kind == TC_CONVT) ? 2 : 1;
