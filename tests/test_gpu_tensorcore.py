@@ -41,6 +41,11 @@ CONV_CASES = [
     (8, 16, 2, (8, 12, 40)),     # stride 2 with paired taps across parity sub-planes
     (16, 32, 2, (6, 10, 44)),
     (32, 64, 2, (4, 8, 12)),
+    # several items per CTA with odd segment lengths: the three epilogue warp sets of the kw-folded fold kernels take the
+    # output planes in turn across item boundaries (accumulator-ring phases tracked for every block by every set)
+    (32, 8, 1, (11, 96, 330)),
+    (8, 1, 1, (11, 96, 330)),
+    (16, 16, 1, (7, 64, 200)),
 ]
 
 
@@ -186,7 +191,10 @@ def check16(y, ref, what):
 
 @pytest.mark.parametrize("cin,cout,k,hw,N", [(3, 8, 3, (20, 44), 2), (8, 8, 3, (37, 130), 1), (16, 16, 3, (24, 40), 3),
                                              (32, 32, 3, (9, 13), 2), (8, 16, 5, (24, 52), 2), (16, 32, 5, (20, 36), 1),
-                                             (8, 16, 5, (6, 260), 1)])
+                                             (8, 16, 5, (6, 260), 1),
+                                             # kw-folded variants (EPI=3: row pitch 32, N = 3*Cout), ragged widths / heights
+                                             (16, 16, 3, (50, 95), 1), (16, 32, 5, (40, 136), 2), (8, 16, 5, (34, 180), 1),
+                                             (16, 8, 3, (19, 61), 2)])
 def test_tc_conv2d(cin, cout, k, hw, N):
     g = torch.Generator().manual_seed(cin * 31 + cout + hw[1])
     x = f16_round(torch.randn(N, cin, *hw, generator=g))
