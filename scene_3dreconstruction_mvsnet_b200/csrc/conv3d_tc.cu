@@ -106,6 +106,11 @@ struct TcLayer {
     int fold_R;      // accumulator blocks per M-tile in TMEM (ring along z)
     int fold_sets;   // depth-folded kernel: number of epilogue sets (2 or 3)
     unsigned long long rcp_zsegs, rcp_tiles_x, rcp_tiles_y;  // ceil(2^40 / d) for the item decode
+    // class-merged transposed conv: the skip tile of a step ([CPC][2 planes][2*TY rows][2*TXB voxels][8]) is brought to
+    // shared memory by TMA one step ahead (two buffers, one per epilogue warp set) instead of being loaded by the
+    // epilogue threads when they need it
+    int skip_tma, skip_buf_bytes, skip_tx_bytes, skip_off;  // skip_off: offset of buffer 0 from the end of the plane ring
+    alignas(64) CUtensorMap skip_map;
     int mma_n;       // > 0: N of the tcgen05.mma (kw-folded 2-D layers: 3*Cout rounded up to 16) -- the TMEM column stride
                      //      per M-tile stays the template's NPAD
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
@@ -172,6 +177,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
+    auto sfull_bar = [&](int b) { return bar_base + 8u * (22 + b); };   // skip tile of buffer b has landed
+    auto sempty_bar = [&](int b) { return bar_base + 8u * (24 + b); };  // ... has been read by the 4 warps of set b
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 256);  // [kMaxOps] {A desc lo (no slot base), B desc lo}
     float *s_shift = reinterpret_cast<float *>(smem + 256 + kMaxOps * 8);  // [64] folded shifts of this channel group
     constexpr uint32_t kHdr = 256 + kMaxOps * 8 + 256;
@@ -180,6 +187,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // descriptor high word: SBO = 128 B (8 rows x 16 B), version 1 (Blackwell), no swizzle
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
     const uint32_t ring_base = (w_base + L.wbytes_group + 127u) & ~127u;
+    const uint32_t skip_base = (ring_base + L.nslot * L.slot_bytes + (uint32_t)L.skip_off + 1023u) & ~1023u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncols_buf = L.nacc * L.MT * NPAD;
@@ -208,9 +216,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             ptx::mbar_init(tfull_bar(b), 1);
             // lean epilogue: the 4 quadrant warps of the set that owns this buffer; general: all 8 epilogue warps
             ptx::mbar_init(tempty_bar(b), STEPWISE ? 4 : 8);
+            ptx::mbar_init(sfull_bar(b), 1);
+            ptx::mbar_init(sempty_bar(b), 4);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmap);
+        if (L.skip_tma) ptx::prefetch_tensormap(&L.skip_map);
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
     ptx::fence_proxy_async_smem();  // weights were written with generic stores, read by the MMA (async proxy)
@@ -274,6 +285,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 }
             }
             if (L.dbg) L.dbg[blockIdx.x * 12 + 0] = prod_wait;
+        } else if (lane == 1 && L.skip_tma) {
+            // second producer thread: the skip tile of every step, into the buffer of the epilogue set that drains it
+            uint32_t sst = 0;
+            const int cpc = L.cout_total >> 3;
+            for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
+                int b, x0, y0, zs, T;
+                decode(it, b, x0, y0, zs, T);
+                for (int t = 0; t < T; ++t, ++sst) {
+                    const uint32_t sb = sst & 1u;
+                    ptx::mbar_wait(sempty_bar(sb), ((sst >> 1) & 1u) ^ 1u);
+                    ptx::mbar_arrive_expect_tx(sfull_bar(sb), (uint32_t)L.skip_tx_bytes);
+                    ptx::tma_load_4d(skip_base + sb * L.skip_buf_bytes, &L.skip_map, sfull_bar(sb), 4 * x0, 2 * y0, 2 * (zs + t), b * cpc);
+                }
+            }
         }
     } else if (warp == 1 || warp == 10) {
         // ================= MMA issuer(s) =================
@@ -414,7 +439,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     const uint32_t yx = mt == 0 ? yx0 : (mt == 1 ? yx1 : (mt == 2 ? yx2 : yx3));
                     const int y = (int)(yx >> 16), x = (int)(yx & 0xffffu);
                     const bool valid = (y < L.TY) && (x < L.TXB) && (y0 + y < L.Ht) && (x0 + x < L.Wt);
-                    if (L.out2 != nullptr) {
+                    if (L.skip_tma) {  // byte offset of voxel (2y, 2x) inside a plane of the skip tile in shared memory
+                        const uint32_t sp = ((uint32_t)(2 * y) * 2u * (uint32_t)L.TXB + (uint32_t)(2 * x)) * 16u;
+                        if (mt == 0) sp0 = sp; else if (mt == 1) sp1 = sp; else if (mt == 2) sp2 = sp; else sp3 = sp;
+                    } else if (L.out2 != nullptr) {
                         const uint32_t sp = (uint32_t)((((y0 + y) & 1) * 2 + ((x0 + x) & 1)) * (L.cout_total >> 3)) * (uint32_t)plane_sp +
                                             (uint32_t)((y0 + y) >> 1) * (L.Wout / 2) + (uint32_t)((x0 + x) >> 1);
                         if (mt == 0) sp0 = sp; else if (mt == 1) sp1 = sp; else if (mt == 2) sp2 = sp; else sp3 = sp;
@@ -499,18 +527,36 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     constexpr int COUT = NPAD / 8, CPC = COUT / 8;
                     const uint4 *skp = skip ? skip + zoff : nullptr;
                     uint4 *outp = reinterpret_cast<uint4 *>(L.out) + zoff;
+                    // skip tile in shared memory (L.skip_tma): voxel (pz, 2y+py, 2x+px) of chunk cc at
+                    // (((cc*2 + pz) * 2TY + 2y+py) * 2TXB + 2x+px) * 16 bytes; sp* hold the thread's (2y, 2x) part
+                    const uint32_t s_row = 2u * (uint32_t)L.TXB * 16u, s_plane = 2u * (uint32_t)L.TY * s_row;
+                    const uint32_t s_buf = skip_base + buf * (uint32_t)L.skip_buf_bytes;
+                    if (L.skip_tma) ptx::mbar_wait(sfull_bar(buf), (st >> 1) & 1);
                     for (int mt = 0; mt < L.MT; ++mt) {
                         const bool ok = (vmask >> mt) & 1u;
                         const size_t mb = mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3));
+                        const uint32_t s_thr = s_buf + (mt == 0 ? sp0 : (mt == 1 ? sp1 : (mt == 2 ? sp2 : sp3)));
 #pragma unroll
                         for (int pz = 0; pz < 2; ++pz) {
                             uint32_t sk[2 * CPC][8];
                             if (skp != nullptr && ok) {
+                                if (L.skip_tma) {
 #pragma unroll
-                                for (int py = 0; py < 2; ++py)
+                                    for (int py = 0; py < 2; ++py)
 #pragma unroll
-                                    for (int cc = 0; cc < CPC; ++cc)
-                                        ptx::ldg256(skp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], sk[py * CPC + cc]);
+                                        for (int cc = 0; cc < CPC; ++cc) {
+                                            const uint32_t a = s_thr + (uint32_t)(cc * 2 + pz) * s_plane + (uint32_t)py * s_row;
+                                            uint32_t *d = sk[py * CPC + cc];
+                                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a));
+                                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]) : "r"(a + 16u));
+                                        }
+                                } else {
+#pragma unroll
+                                    for (int py = 0; py < 2; ++py)
+#pragma unroll
+                                        for (int cc = 0; cc < CPC; ++cc)
+                                            ptx::ldg256(skp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], sk[py * CPC + cc]);
+                                }
                             }
                             uint32_t r[2 * CPC][16];
 #pragma unroll
@@ -554,6 +600,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                     ptx::stg256(outp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], pk);
                                 }
                         }
+                    }
+                    if (L.skip_tma) {  // every skip value of this step is in registers or stored: the buffer can be refilled
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(sempty_bar(buf));
                     }
                     epi_work += clock64() - c1;
                 } else if constexpr (SIMPLE) {
@@ -1312,7 +1362,8 @@ static constexpr int kSmemLimit = 227 * 1024;
 
 // Builds the plan for one layer.  in: bf16 CP8 [B][cin/8][Din][Hin][Win][8].
 static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din, int Hin, int Win, const void *in_ptr,
-                     int num_sms, bool encode = true, bool in_split = false, bool allow_kw2d = false) {
+                     int num_sms, bool encode = true, bool in_split = false, bool allow_kw2d = false,
+                     const void *skip_ptr = nullptr) {
     TcLayer &L = pl.L;
     memset(&pl, 0, sizeof(pl));
     MVS_REQUIRE(cin % 8 == 0, "tc conv: Cin must be a multiple of 8");
@@ -1346,6 +1397,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // MMAs per M-tile and Cout <= 16, or >= 36 with Cout = 32.
     const bool kw2d = is2d && allow_kw2d && !nokw2d && Win >= 30 &&
                       (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64));
+    static const bool noskiptma = getenv("MVS_TC_NOSKIPTMA") != nullptr;  // A/B knob
+    const bool skip_tma = merged_t && skip_ptr != nullptr && !noskiptma;
     int ntaps_ops;  // MMA instructions per step
     if (merged_t) ntaps_ops = 8 * kpairs_tap;
     else if (fold_kw) ntaps_ops = 2;
@@ -1374,7 +1427,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int nsub = (kind == TC_CONV_S2) ? 4 : 1;
     const int halo = (kind == TC_CONV_S1 || is2d) ? 2 : 1;  // extra rows / cols in a (sub-)plane box
     // choose the tile: TXB columns, TY rows, MT M-tiles of 128 flattened positions
-    const int max_cols = 128 - halo;  // boxDim[x] <= 256: 2 uint64 per voxel (merged inner dim) or elementStrides = 2
+    // boxDim[x] <= 256: 2 uint64 per voxel (merged inner dim) or elementStrides = 2; the skip tile box is 4*TXB uint64 wide
+    const int max_cols = skip_tma ? 64 : 128 - halo;
     int best_TXB = 0, best_TY = 0, best_MT = 0, best_nslot = 0;
     double best_score = -1;
     // MT limit: 2 buffers x nacc x MT x npad <= 512 columns; folded: MT regions of R blocks x 16 columns, R >= 8
@@ -1392,8 +1446,9 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             const size_t sub_bytes = (size_t)chunks * rows * P * 16;
             const size_t slot_bytes = nsub * ((sub_bytes + 127) & ~(size_t)127);
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
+                const size_t skip_smem = skip_tma ? 2 * (((size_t)128 * TXB * TY * (cout / 8) + 1023) & ~(size_t)1023) + 1024 : 0;
                 const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
-                                     (fold ? (fold_kw8 ? 4096 : 512) : 0);
+                                     (fold ? (fold_kw8 ? 4096 : 512) : 0) + skip_smem;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -1600,8 +1655,12 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     pl.npad = npad_cols;
     pl.kw2d = kw2d;
     pl.wpacked_bytes = (size_t)ngroups * wbytes;
+    L.skip_tma = skip_tma ? 1 : 0;
+    L.skip_tx_bytes = 128 * TXB * TY * (cout / 8);
+    L.skip_buf_bytes = (L.skip_tx_bytes + 1023) & ~1023;
+    L.skip_off = (128 + 2 * P + 8) * 16;  // past the A-operand overrun guard that follows the ring
     pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
-                    (fold ? (fold_kw8 ? 4096 : 512) : 0);
+                    (fold ? (fold_kw8 ? 4096 : 512) : 0) + (skip_tma ? 2 * (size_t)L.skip_buf_bytes + 1024 : 0);
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
@@ -1609,6 +1668,17 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // ---- tensor map over the input: dims (8ch, x, y, z, B*chunks)
     tmap_encode_fn enc = get_tmap_encode();
     MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    if (skip_tma) {  // skip tensor = bf16 CP8 [B][Cout/8][Dout][Hout][Wout][8], merged (8ch, x) inner dimension
+        const int cpc = cout / 8;
+        cuuint64_t gd[4] = {(cuuint64_t)2 * L.Wout, (cuuint64_t)L.Hout, (cuuint64_t)L.Dout, (cuuint64_t)B * cpc};
+        cuuint64_t gs[3] = {(cuuint64_t)L.Wout * 16, (cuuint64_t)L.Wout * L.Hout * 16, (cuuint64_t)L.Wout * L.Hout * L.Dout * 16};
+        cuuint32_t bx[4] = {(cuuint32_t)(4 * TXB), (cuuint32_t)(2 * TY), 2, (cuuint32_t)cpc};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult cs = enc(&L.skip_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(skip_ptr), gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cs != CUDA_SUCCESS) return set_error(MVS_ERR_CUDA, "cuTensorMapEncodeTiled (skip tile) failed (%d)", (int)cs);
+    }
     L.merged_x = (kind != TC_CONV_S2);
     L.in_split = (kind == TC_CONV_S2 && in_split) ? 1 : 0;
     if (L.in_split) {
@@ -1730,7 +1800,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
                      int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false, void *out2 = nullptr,
                      bool in_split = false) {
     static thread_local TcPlan pl;  // ~3 KB; not kept across calls
-    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split, f16 != 0 && skip == nullptr && !out_f32)) return rc;
+    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split, f16 != 0 && skip == nullptr && !out_f32, skip)) return rc;
     MVS_REQUIRE(out2 == nullptr || (out_mode == 0 && !out_f32 && !f16 && (pl.L.fold || pl.L.nacc == 1) && skip == nullptr && Hin % 2 == 0 && Win % 2 == 0), "second output: plain conv layers only");
     pl.L.out2 = out2;
     MVS_REQUIRE(!f16 || (kind == TC_CONV2D && (pl.npad <= 32 || pl.kw2d) && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
