@@ -38,7 +38,7 @@ softmax_depth_conf_kernel(const float *__restrict__ logits, const float *__restr
 
     // pass 1: max over depth
     float m = -FLT_MAX;
-#pragma unroll 8
+#pragma unroll 24  // D = 192 with 8 slices: a thread's 24 loads all in flight at once
     for (int d = d0; d < d1; ++d) {
         const float l = live ? __ldcs(lp + (size_t)d * HW) : 0.f;
         if (CACHE) s_tile[d * 32 + lane] = l;
