@@ -179,6 +179,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
     auto sfull_bar = [&](int b) { return bar_base + 8u * (22 + b); };   // skip tile of buffer b has landed
     auto sempty_bar = [&](int b) { return bar_base + 8u * (24 + b); };  // ... has been read by the 4 warps of set b
+    const uint32_t w_bar = bar_base + 8u * 26;                           // packed weights have landed
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 256);  // [kMaxOps] {A desc lo (no slot base), B desc lo}
     float *s_shift = reinterpret_cast<float *>(smem + 256 + kMaxOps * 8);  // [64] folded shifts of this channel group
     constexpr uint32_t kHdr = 256 + kMaxOps * 8 + 256;
@@ -197,16 +198,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // ---- one-time setup
     // Items are ordered so that a CTA keeps the same n-group for all of its items: group = blockIdx.x % ngroups.
     const int group = blockIdx.x % L.ngroups;
-    {
-        const uint4 *src = L.wpacked + (size_t)group * (L.wbytes_group / 16);
-        uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
-        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
+    // The packed weights (up to 110 KB) come by one bulk copy that completes on w_bar; only the MMA issuers wait for it, so
+    // it overlaps the rest of the set-up and the first plane loads.  (A per-thread copy loop here was a chain of L2
+    // latencies: ~2-7 us per launch depending on how far the compiler happened to unroll it.)
+    (void)w_smem;
     for (int o = threadIdx.x; o < L.nops; o += blockDim.x)
         optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
     if (threadIdx.x < 64)
         s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + group * L.cout_group + threadIdx.x) : 0.f;
     if (threadIdx.x == 0) {
+        ptx::mbar_init(w_bar, 1);
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             // dual issuers: a plane is free when BOTH issuer warps' MMAs that read it have completed
@@ -220,6 +221,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             ptx::mbar_init(sempty_bar(b), 4);
         }
         ptx::fence_barrier_init();
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked + (size_t)group * (L.wbytes_group / 16), (uint32_t)L.wbytes_group, w_bar);
         ptx::prefetch_tensormap(&tmap);
         if (L.skip_tma) ptx::prefetch_tensormap(&L.skip_map);
     }
@@ -319,6 +322,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const long long t_start = clock64();
         const uint32_t nslot = L.nslot, need = L.need, adv = L.adv;
         auto wrap = [&](uint32_t s) { return s >= nslot ? s - nslot : s; };
+        if (leader) ptx::mbar_wait(w_bar, 0);
         // one lane runs the whole loop: no warp-level re-convergence points between a step's waits and its MMAs
         if (leader)
         for (int it = cta_in_group; it < items_per_group; it += ctas_per_group) {
@@ -808,15 +812,13 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)MT * cols_mt) tmem_cols <<= 1;
 
-    {
-        const uint4 *src = L.wpacked;
-        uint4 *dst = reinterpret_cast<uint4 *>(w_smem);
-        for (int i = threadIdx.x; i < L.wbytes_group / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
+    (void)w_smem;  // packed weights: one bulk copy completing on w_bar, awaited by the issuers only (see conv3d_tc_kernel)
+    const uint32_t w_bar = bar_base + 392u;
     for (int o = threadIdx.x; o < L.nops; o += blockDim.x)
         optab[o] = make_uint2(L.ops[o].a_lo, L.ops[o].b_lo + (w_base >> 4));
     if (threadIdx.x < 64) s_shift[threadIdx.x] = (threadIdx.x < L.cout_group) ? __ldg(L.shift + threadIdx.x) : 0.f;
     if (threadIdx.x == 0) {
+        ptx::mbar_init(w_bar, 1);
         for (int s = 0; s < L.nslot; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 2);  // both issuer warps release a plane
@@ -826,6 +828,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             ptx::mbar_init(tempty_bar(b), 4);  // the 4 quadrant warps of the epilogue set that drains the block
         }
         ptx::fence_barrier_init();
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked, (uint32_t)L.wbytes_group, w_bar);
         ptx::prefetch_tensormap(&tmap);
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
@@ -899,6 +903,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const int nops = L.nops;
         const uint32_t nslot = L.nslot, uR = (uint32_t)R;
         auto wrapR = [&](uint32_t v) { return v >= uR ? v - uR : v; };
+        if (leader) ptx::mbar_wait(w_bar, 0);
         // one lane runs the whole loop: no warp-level re-convergence points between a step's waits and its MMAs
         if (leader)
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
