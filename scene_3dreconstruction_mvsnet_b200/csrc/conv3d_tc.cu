@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(kTcThreadsDual, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
     constexpr bool SIMPLE = (EPI == 1);
     constexpr bool STEPWISE = (EPI != 0);  // epilogue warp sets alternate over steps (one TMEM buffer each)
+    // Programmatic dependent launch: the next layer's CTAs may start on SMs this grid has left; everything up to
+    // pdl_wait() below (barriers, TMEM, descriptor table) touches nothing another kernel writes.
+    ptx::pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem[];
     // [0,256): mbarriers + tmem address; then packed weights; then the plane ring (128-byte aligned)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -221,8 +224,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             ptx::mbar_init(sempty_bar(b), 4);
         }
         ptx::fence_barrier_init();
-        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
-        ptx::bulk_copy_g2s(w_base, L.wpacked + (size_t)group * (L.wbytes_group / 16), (uint32_t)L.wbytes_group, w_bar);
         ptx::prefetch_tensormap(&tmap);
         if (L.skip_tma) ptx::prefetch_tensormap(&L.skip_map);
     }
@@ -233,6 +234,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     ptx::tcgen05_fence_after();
     // warp-uniform copy of the TMEM base (shuffle from lane 0 lets the compiler keep it in a uniform register)
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    ptx::pdl_wait();  // from here on: the previous kernel's outputs (activations, freshly packed weights) are read
+    if (threadIdx.x == 0) {
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked + (size_t)group * (L.wbytes_group / 16), (uint32_t)L.wbytes_group, w_bar);
+    }
 
     const int items_per_group = L.n_items / L.ngroups;
     const int cta_in_group = blockIdx.x / L.ngroups;
@@ -780,6 +786,7 @@ __device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab,
 template <int CW, int NSETS, bool KWF>  // KWF: kw folded into N too (CW = 16: prob, Cout = 1; CW = 32: conv0, Cout = 8)
 __global__ void __launch_bounds__(fold_threads(NSETS), 1)
 conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcLayer L) {
+    ptx::pdl_launch_dependents();  // see conv3d_tc_kernel
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar_base = ptx::smem_u32(smem);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -828,8 +835,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
             ptx::mbar_init(tempty_bar(b), 4);  // the 4 quadrant warps of the epilogue set that drains the block
         }
         ptx::fence_barrier_init();
-        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
-        ptx::bulk_copy_g2s(w_base, L.wpacked, (uint32_t)L.wbytes_group, w_bar);
         ptx::prefetch_tensormap(&tmap);
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), tmem_cols);
@@ -847,6 +852,12 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     ptx::tcgen05_fence_before();
     __syncthreads();
     ptx::tcgen05_fence_after();
+
+    ptx::pdl_wait();  // the previous kernel's outputs are read from here on
+    if (threadIdx.x == 0) {
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked, (uint32_t)L.wbytes_group, w_bar);
+    }
 
     auto decode = [&](int it, int &b, int &x0, int &y0, int &zs, int &T) {
         // divisions by the per-layer constants through 2^40 reciprocals (exact for it < 2^20): ~4 instructions each; an
@@ -1843,8 +1854,18 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
         // per-layer one that a concurrent launch of another layer could lower between this call and the launch
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        kern<<<pl.grid, pl.L.fold ? fold_threads(pl.L.fold_sets) : (pl.L.dual ? kTcThreadsDual : kTcThreads), pl.smem_bytes, st>>>(
-            pl.tmap, pl.L);
+        static const bool nopdl = getenv("MVS_TC_NOPDL") != nullptr;  // A/B knob
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pl.grid);
+        cfg.blockDim = dim3((unsigned)(pl.L.fold ? fold_threads(pl.L.fold_sets) : (pl.L.dual ? kTcThreadsDual : kTcThreads)));
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = nopdl ? 0 : 1;
+        MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.tmap, pl.L));
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
     };

@@ -90,6 +90,13 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src
                  : "memory");
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// launch_dependents: the next kernel of the stream (if it was launched with programmatic stream serialization) may start
+// its CTAs as SMs become free; grid_dependency_wait: blocks until every prerequisite grid has completed and its memory
+// is visible (a no-op for a normally launched kernel).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- tcgen05 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -153,6 +153,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                          const float *__restrict__ depth_values,         // [B,D]
                          uint4 *__restrict__ out,                        // bf16 CP8 [B,4,D,H,W,8]
                          int V, int nsrc, int nwin, int D, int H, int W, int dchunk, int WY) {
+    // the next kernel (conv0, launched with programmatic stream serialization) may start its set-up on SMs this grid has left
+    ptx::pdl_launch_dependents();
     constexpr int TW = 32 * TWW;
     constexpr int ROWQ = 4 * WX;     // uint4 per window row
     constexpr int ROWB = ROWQ * 16;  // bytes per window row
