@@ -111,6 +111,8 @@ struct TcLayer {
     // epilogue threads when they need it
     int skip_tma, skip_buf_bytes, skip_tx_bytes, skip_off;  // skip_off: offset of buffer 0 from the end of the plane ring
     alignas(64) CUtensorMap skip_map;
+    int w_early;     // 1: the packed weights were written long before this launch (cache hit): their copy to shared memory
+                     //    may start before the grid dependency wait
     int mma_n;       // > 0: N of the tcgen05.mma (kw-folded 2-D layers: 3*Cout rounded up to 16) -- the TMEM column stride
                      //      per M-tile stays the template's NPAD
     int fold_kw;     // 1: (Cin = 8, Cout = 1: the prob layer) the kw taps are folded into N as well; the epilogue adds
@@ -234,8 +236,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     ptx::tcgen05_fence_after();
     // warp-uniform copy of the TMEM base (shuffle from lane 0 lets the compiler keep it in a uniform register)
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    if (threadIdx.x == 0 && L.w_early) {
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked + (size_t)group * (L.wbytes_group / 16), (uint32_t)L.wbytes_group, w_bar);
+    }
     ptx::pdl_wait();  // from here on: the previous kernel's outputs (activations, freshly packed weights) are read
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !L.w_early) {
         ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
         ptx::bulk_copy_g2s(w_base, L.wpacked + (size_t)group * (L.wbytes_group / 16), (uint32_t)L.wbytes_group, w_bar);
     }
@@ -853,8 +859,12 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     __syncthreads();
     ptx::tcgen05_fence_after();
 
+    if (threadIdx.x == 0 && L.w_early) {
+        ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
+        ptx::bulk_copy_g2s(w_base, L.wpacked, (uint32_t)L.wbytes_group, w_bar);
+    }
     ptx::pdl_wait();  // the previous kernel's outputs are read from here on
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !L.w_early) {
         ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)L.wbytes_group);
         ptx::bulk_copy_g2s(w_base, L.wpacked, (uint32_t)L.wbytes_group, w_bar);
     }
@@ -1757,6 +1767,7 @@ struct WCacheKey {
 struct WCacheEntry {
     void *ptr;
     cudaEvent_t ready;
+    bool done;  // the fill has been observed complete: no event wait needed any more
 };
 static std::mutex g_wcache_mu;
 static std::map<WCacheKey, WCacheEntry> g_wcache;
@@ -1769,17 +1780,25 @@ static uint64_t fnv1a(const void *data, size_t n, uint64_t h = 14695981039346656
 
 // Returns the cached device buffer for `key`, creating it with fill(dst) (which must enqueue work on st) on a miss.
 template <typename F>
-static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void **out, F fill) {
+static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void **out, F fill, bool *settled = nullptr) {
     std::lock_guard<std::mutex> lock(g_wcache_mu);
     auto it = g_wcache.find(key);
+    if (settled) *settled = false;
     if (it == g_wcache.end()) {
         WCacheEntry e;
+        e.done = false;
         MVS_CUDA(cudaMalloc(&e.ptr, bytes));
         MVS_CUDA(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
         if (int rc = fill(e.ptr)) { cudaFree(e.ptr); cudaEventDestroy(e.ready); return rc; }
         MVS_CUDA(cudaEventRecord(e.ready, st));
         it = g_wcache.emplace(key, e).first;
+    } else if (it->second.done) {
+        if (settled) *settled = true;
+    } else if (cudaEventQuery(it->second.ready) == cudaSuccess) {
+        it->second.done = true;  // filled long ago: nothing to order against (and no stream op between two conv launches)
+        if (settled) *settled = true;
     } else {
+        (void)cudaGetLastError();  // cudaErrorNotReady is not sticky, but leave no stale status behind
         MVS_CUDA(cudaStreamWaitEvent(st, it->second.ready, 0));
     }
     *out = it->second.ptr;
@@ -1841,14 +1860,16 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         MVS_CUDA(cudaGetDevice(&dev));
         const int nw = (int)(pl.wpacked_bytes / 2);
         void *wp = nullptr;
+        bool settled = false;
         const WCacheKey key{dev, w_fp32, fnv1a(&pl.W, sizeof(pl.W))};
         if (int rc = wcache_get(key, pl.wpacked_bytes, st, &wp, [&](void *dst) -> int {
                 pack_weights_kernel<<<cdiv(nw, 256), 256, 0, st>>>(w_fp32, (__nv_bfloat16 *)dst, pl.W);
                 MVS_LAUNCH_CHECK(1);
                 return MVS_OK;
-            }))
+            }, &settled))
             return rc;
         pl.L.wpacked = (const uint4 *)wp;
+        pl.L.w_early = settled ? 1 : 0;
     }
     auto launch = [&](auto kern) -> int {
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
