@@ -2046,6 +2046,7 @@ __global__ void nchw_to_cp8n_f16_kernel(const T *__restrict__ in, uint4 *__restr
 // Four consecutive pixels per thread: one 16-byte (fp32) or 4-byte (uint8) load per colour plane, 64 contiguous bytes out.
 template <typename T>
 __global__ void images_to_cp8_kernel(const T *__restrict__ in, uint4 *__restrict__ out, size_t HW, long long quads) {
+    ptx::pdl_launch_dependents();  // the first FeatureNet layer may set up while this grid drains
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= quads) return;
     const size_t px = (size_t)i * 4;  // first pixel (n*HW + y*W + x); W % 4 == 0 keeps the four in one row

@@ -25,6 +25,8 @@ softmax_depth_conf_kernel(const float *__restrict__ logits, const float *__restr
                           float *__restrict__ depth, float *__restrict__ conf, float *__restrict__ prob, int D,
                           int HW) {
     extern __shared__ float s_tile[];  // CACHE: [D][32] logits
+    // launched with programmatic stream serialization: CTAs may start while the producer of `logits` drains
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __shared__ float s_red[4][kSlices][32];
 
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -127,7 +129,17 @@ extern "C" int mvs_softmax_depth_conf(const float *logits, const float *depth_va
         if (smem > 48 * 1024)
             MVS_CUDA(cudaFuncSetAttribute(softmax_depth_conf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           96 * 1024));  // one value for every caller (the attribute is per function, not per launch)
-        softmax_depth_conf_kernel<true><<<grid, 32 * kSlices, smem, st>>>(logits, depth_values, depth, conf, prob, D, HW);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(32 * kSlices);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MVS_CUDA(cudaLaunchKernelEx(&cfg, softmax_depth_conf_kernel<true>, logits, depth_values, depth, conf, prob, D, HW));
     } else {
         softmax_depth_conf_kernel<false><<<grid, 32 * kSlices, 0, st>>>(logits, depth_values, depth, conf, prob, D, HW);
     }

@@ -90,6 +90,10 @@ __device__ void compose_one(const float *src_proj, const float *ref_proj, float 
 }
 
 __global__ void compose_views_kernel(const float *__restrict__ proj, float *__restrict__ rt, int B, int V) {
+    // programmatic dependent launch: the warp kernel behind may be scheduled early; nothing is read or written before
+    // every earlier kernel of the stream has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= B * (V - 1)) return;
     int b = n / (V - 1), v = n % (V - 1) + 1;
@@ -105,7 +109,16 @@ __global__ void compose_pairs_kernel(const float *__restrict__ src_proj, const f
 
 int compose_homographies(const float *proj, float *rt, int B, int V, cudaStream_t st) {
     int n = B * (V - 1);
-    compose_views_kernel<<<cdiv(n, 64), 64, 0, st>>>(proj, rt, B, V);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(n, 64));
+    cfg.blockDim = dim3(64);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MVS_CUDA(cudaLaunchKernelEx(&cfg, compose_views_kernel, proj, (float *)rt, B, V));
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }

@@ -155,6 +155,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                          int V, int nsrc, int nwin, int D, int H, int W, int dchunk, int WY) {
     // the next kernel (conv0, launched with programmatic stream serialization) may start its set-up on SMs this grid has left
     ptx::pdl_launch_dependents();
+    ptx::pdl_wait();  // launched with programmatic stream serialization: homographies and features are read below
     constexpr int TW = 32 * TWW;
     constexpr int ROWQ = 4 * WX;     // uint4 per window row
     constexpr int ROWB = ROWQ * 16;  // bytes per window row
@@ -428,8 +429,18 @@ int launch_win(const void *tex16, const float *rt, const float *depth_values, vo
         configured_dev = dev;
     }
     dim3 grid(cdiv(W, 32 * TWW), cdiv(H, TH), B * cdiv(D, dchunk));
-    kern<<<grid, 32 * TWW * TH, p.smem, st>>>(tmap, (const uint4 *)tex16, rt, depth_values, (uint4 *)vol_cp8, V, nsrc, p.nwin,
-                                             D, H, W, dchunk, p.wy);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(32 * TWW * TH);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, (const uint4 *)tex16, (const float *)rt, (const float *)depth_values, (uint4 *)vol_cp8, V,
+                                nsrc, p.nwin, D, H, W, dchunk, p.wy));
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }
