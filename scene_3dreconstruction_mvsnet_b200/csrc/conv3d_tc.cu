@@ -805,9 +805,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     // lane-shift edge values (fold_kw): CW = 16: [epilogue sets][2 parities][16 groups of 32 positions][3];
     // CW = 32: [sets][2 parities][8 groups][24]
     float *s_edge = reinterpret_cast<float *>(smem + 1664);
-    constexpr uint32_t kHdr = (CW == 32) ? 6400 : 2816;
-    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + NSETS * 2 * 16 * 3 * 4 <= 2816 &&
-                      1664 + NSETS * 2 * 8 * 24 * 4 <= 6400, "fold kernel header overflow");
+    constexpr uint32_t kHdr = (CW == 32 && KWF) ? 6400 : 2816;  // edge buffers only in the kw-folded variants
+    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + (KWF ? NSETS * 2 * (CW == 32 ? 8 * 24 : 16 * 3) * 4 : 0) <= kHdr,
+                  "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
@@ -1020,7 +1020,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + myblk * CW;
                 const bool mirrored = myblk < 2;  // logical blocks 0 and 1 have a second part in physical blocks R, R+1
                 const size_t zoff = (size_t)(zs + e) * zstride;
-                if constexpr (CW == 32) {
+                if constexpr (CW == 32 && KWF) {
                     // conv0 (Cout = 8, kw folded into N, MT <= 2): column kw*8 + co of a block is
                     // U_kw[p][co] = sum_{kh,ci} in[p + kh*P][ci] w[co][ci][kh][kw]; out[p] = U_0[p] + U_1[p+1] + U_2[p+2]
                     // (columns 24..31 have zero weights).  Same lane shift + edge exchange as the prob layer below,
@@ -1165,13 +1165,14 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                         reinterpret_cast<float *>(L.out)[(size_t)b * plane + base[mt] + zoff] = v;
                     }
                 } else {
-                    // M-tiles in pairs: 2 x CW accumulator registers at a time
+                    // MB M-tiles at a time: 32 accumulator registers (+ 32 for a mirror block)
+                    constexpr int MB = (CW == 32) ? 1 : 2;
 #pragma unroll
-                    for (int m0 = 0; m0 < 4; m0 += 2) {
+                    for (int m0 = 0; m0 < 4; m0 += MB) {
                         if (m0 >= MT) break;  // warp-uniform
-                        uint32_t r[2][CW];
+                        uint32_t r[MB][CW];
 #pragma unroll
-                        for (int i = 0; i < 2; ++i)
+                        for (int i = 0; i < MB; ++i)
                             if (m0 + i < MT) {
 #pragma unroll
                                 for (int c8 = 0; c8 < CW / 8; ++c8)
@@ -1179,9 +1180,9 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                             }
                         ptx::tmem_ld_wait();
                         if (mirrored) {
-                            uint32_t r2[2][CW];
+                            uint32_t r2[MB][CW];
 #pragma unroll
-                            for (int i = 0; i < 2; ++i)
+                            for (int i = 0; i < MB; ++i)
                                 if (m0 + i < MT) {
 #pragma unroll
                                     for (int c8 = 0; c8 < CW / 8; ++c8)
@@ -1189,26 +1190,29 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                                 }
                             ptx::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 2; ++i)
+                            for (int i = 0; i < MB; ++i)
 #pragma unroll
                                 for (int k = 0; k < CW; ++k)
                                     if (k < 8 * nchunk) r[i][k] = __float_as_uint(__uint_as_float(r[i][k]) + __uint_as_float(r2[i][k]));
                         }
                         // values are in registers: zero the block (and its mirror) for its next use
 #pragma unroll
-                        for (int i = 0; i < 2; ++i)
+                        for (int i = 0; i < MB; ++i)
                             if (m0 + i < MT) {
-                                ptx::tmem_st_zero_x16(tb + (m0 + i) * cols_mt);
-                                if (mirrored) ptx::tmem_st_zero_x16(tb + R * CW + (m0 + i) * cols_mt);
+#pragma unroll
+                                for (int c16 = 0; c16 < CW; c16 += 16) {
+                                    ptx::tmem_st_zero_x16(tb + (m0 + i) * cols_mt + c16);
+                                    if (mirrored) ptx::tmem_st_zero_x16(tb + R * CW + (m0 + i) * cols_mt + c16);
+                                }
                             }
-                        if (m0 + 2 >= MT) {  // last pair: hand the block back
+                        if (m0 + MB >= MT) {  // last batch: hand the block back
                             ptx::tmem_st_wait();
                             ptx::tcgen05_fence_before();
                             __syncwarp();
                             if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
                         }
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
+                        for (int i = 0; i < MB; ++i) {
                             const int mt = m0 + i;
                             if (mt >= MT || !((vmask >> mt) & 1u)) continue;
                             const size_t vox = base[mt] + zoff;
@@ -1402,14 +1406,16 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int kpairs_tap = (cin >= 16) ? cin / 16 : 1;
     // depth-folded variant (conv3d_tc_fold_kernel): stride-1 layers whose Cout fits one 16-column block
     static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
-    const bool fold = (kind == TC_CONV_S1) && cout <= 16 && !nofold;
+    // ... and Cout = 32 (conv4, 32 -> 32): 32-column blocks, N = 96: 18 MMAs of 56 cycles per plane and M-tile instead of 54 of 40
+    static const bool nofold32 = getenv("MVS_TC_NOFOLD32") != nullptr;  // A/B knob
+    const bool fold = (kind == TC_CONV_S1) && (cout <= 16 || (cout == 32 && cin >= 16 && !nofold32)) && !nofold;
     static const bool nofoldkw = getenv("MVS_TC_NOFOLDKW") != nullptr;  // A/B knob
     const bool fold_kw = fold && cin == 8 && cout == 1 && !nofoldkw;
     // conv0 (32 -> 8): kw folded into N as well, 32-column blocks [kw][8 Cout] (24 used), N = 96: 6 MMAs of 56 cycles per
     // plane and M-tile instead of 18 of 44 -- the layer was bound by the shared-memory operand path of its MMAs
     static const bool nofoldkw8 = getenv("MVS_TC_NOFOLDKW8") != nullptr;  // A/B knob
     const bool fold_kw8 = fold && cin >= 16 && cout == 8 && !nofoldkw8;
-    const int fold_cw = fold ? (fold_kw8 ? 32 : 16) : 0;
+    const int fold_cw = fold ? ((fold_kw8 || cout == 32) ? 32 : 16) : 0;
     const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
     // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
     static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
@@ -1421,8 +1427,9 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // plain form has only 5 MMAs per M-tile: the fold's 3x larger accumulator read dominates), 32(s2d)->16 0.044 / 0.065,
     // 16->16 0.038 / 0.040, 64(s2d)->32 0.032 / 0.037, 32->32 0.027 / 0.021 -- so: folded when the plain form has >= 9
     // MMAs per M-tile and Cout <= 16, or >= 36 with Cout = 32.
+    static const bool kw2d_all = getenv("MVS_TC_KW2D_ALL") != nullptr;  // A/B knob: fold every eligible 2-D layer
     const bool kw2d = is2d && allow_kw2d && !nokw2d && Win >= 30 &&
-                      (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64));
+                      (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64) || (kw2d_all && (cout == 8 || cout == 16 || cout == 32)));
     static const bool noskiptma = getenv("MVS_TC_NOSKIPTMA") != nullptr;  // A/B knob
     const bool skip_tma = merged_t && skip_ptr != nullptr && !noskiptma;
     int ntaps_ops;  // MMA instructions per step
@@ -1459,7 +1466,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     double best_score = -1;
     // MT limit: 2 buffers x nacc x MT x npad <= 512 columns; folded: MT regions of R blocks x 16 columns, R >= 8
     const int npad_cols = kw2d ? (cout == 8 ? 32 : (cout == 16 ? 64 : 128)) : npad;  // TMEM columns per M-tile (the template's NPAD)
-    const int tmem_budget = fold ? (fold_kw8 ? 2 : 4) : 256 / (nacc * npad_cols);
+    const int tmem_budget = fold ? (fold_cw == 32 ? 2 : 4) : 256 / (nacc * npad_cols);
     for (int nx = 1; nx <= 64; ++nx) {
         const int TXB = kw2d ? 30 : (Wt + nx - 1) / nx;
         if (kw2d && nx > 1) break;
@@ -1893,7 +1900,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     if (pl.L.fold) {
         if (pl.L.fold_kw == 2) return launch(conv3d_tc_fold_kernel<32, 3, true>);
         if (pl.L.fold_kw) return launch(conv3d_tc_fold_kernel<16, 3, true>);
-        return launch(conv3d_tc_fold_kernel<16, 2, false>);
+        return pl.W.fold_cw == 32 ? launch(conv3d_tc_fold_kernel<32, 2, false>) : launch(conv3d_tc_fold_kernel<16, 2, false>);
     }
     // lean epilogue when there is one accumulator per M-tile, no skip connection and a 16-bit output
     const bool simple = (pl.L.nacc == 1) && (skip == nullptr) && !out_f32 && !pl.L.merged_t;
