@@ -74,14 +74,17 @@ __device__ __forceinline__ void accumulate_chunk(const uint4 a, const uint4 b, c
                                                  float2 *Q) {
     const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
     const uint32_t wc[4] = {c.x, c.y, c.z, c.w}, wd[4] = {d.x, d.y, d.z, d.w};
-    const float2 one2 = make_float2(1.f, 1.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const __half2 vh =
             __hfma2(as_half2(wd[j]), h11, __hfma2(as_half2(wc[j]), h10, __hfma2(as_half2(wb[j]), h01, __hmul2(as_half2(wa[j]), h00))));
-        const float2 val = __half22float2(vh);
-        S[j] = __ffma2_rn(val, one2, S[j]);
-        Q[j] = __ffma2_rn(val, val, Q[j]);
+        // mixed-precision accumulate (FHADD / FHFMA: fp32 += f16, fp32 += f16 * f16, the half taken from either half of the
+        // register): no conversion instructions, same results as convert + fp32 add / fma (f16 -> f32 is exact)
+        const unsigned short lo = __half_as_ushort(__low2half(vh)), hi = __half_as_ushort(__high2half(vh));
+        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(S[j].x) : "h"(lo));
+        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(S[j].y) : "h"(hi));
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(Q[j].x) : "h"(lo));
+        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(Q[j].y) : "h"(hi));
     }
 }
 
