@@ -802,12 +802,8 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 384);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 400);
     float *s_shift = reinterpret_cast<float *>(smem + 400 + kMaxOps * 8);  // [64]
-    // lane-shift edge values (fold_kw): CW = 16: [epilogue sets][2 parities][16 groups of 32 positions][3];
-    // CW = 32: [sets][2 parities][8 groups][24]
-    float *s_edge = reinterpret_cast<float *>(smem + 1664);
-    constexpr uint32_t kHdr = (CW == 32 && KWF) ? 6400 : 2816;  // edge buffers only in the kw-folded variants
-    static_assert(400 + kMaxOps * 8 + 256 <= 1664 && 1664 + (KWF ? NSETS * 2 * (CW == 32 ? 8 * 24 : 16 * 3) * 4 : 0) <= kHdr,
-                  "fold kernel header overflow");
+    constexpr uint32_t kHdr = 1664;
+    static_assert(400 + kMaxOps * 8 + 256 <= kHdr, "fold kernel header overflow");
     uint8_t *w_smem = smem + kHdr;
     const uint32_t w_base = bar_base + kHdr;
     constexpr uint64_t kDescHi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
@@ -983,7 +979,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
         const size_t zstride = (size_t)L.Hout * L.Wout;
         const int nchunk = (L.cout_group + 7) >> 3;
         uint32_t blk = 2 % R, fpar = 0;  // ring position of the next block to drain (block 2 of the first item)
-        uint32_t eturn = 0, ebuf = 0;    // whose turn the next output plane is; parity of this set's edge buffer
+        uint32_t eturn = 0;              // whose turn the next output plane is
         long long epi_wait = 0, epi_work = 0;
         for (int it = blockIdx.x; it < L.n_items; it += gridDim.x) {
             int b, x0, y0, zs, T;
@@ -1011,7 +1007,6 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 const bool mine = (eturn == (uint32_t)eset);
                 if (++eturn == (uint32_t)NSETS) eturn = 0;
                 if (!mine) continue;  // another set's plane
-                ebuf ^= 1u;
                 const long long c0 = clock64();
                 ptx::mbar_wait(tfull_bar(myblk), par);
                 const long long c1 = clock64();
@@ -1023,8 +1018,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                 if constexpr (CW == 32 && KWF) {
                     // conv0 (Cout = 8, kw folded into N, MT <= 2): column kw*8 + co of a block is
                     // U_kw[p][co] = sum_{kh,ci} in[p + kh*P][ci] w[co][ci][kh][kw]; out[p] = U_0[p] + U_1[p+1] + U_2[p+2]
-                    // (columns 24..31 have zero weights).  Same lane shift + edge exchange as the prob layer below,
-                    // eight channels wide.
+                    // (columns 24..31 have zero weights).  Same lane shifts as the prob layer below, eight channels wide.
                     uint32_t r[2][24];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt)
@@ -1059,39 +1053,15 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     ptx::tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(tempty_bar(myblk));
-                    float *edge = s_edge + (eset * 2 + ebuf) * (8 * 24);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt)
-                        if (mt < MT && lane < 2) {
-                            uint4 *eg = reinterpret_cast<uint4 *>(edge + (mt * 4 + q) * 24);
-                            if (lane == 0) {
-                                eg[0] = make_uint4(r[mt][8], r[mt][9], r[mt][10], r[mt][11]);
-                                eg[1] = make_uint4(r[mt][12], r[mt][13], r[mt][14], r[mt][15]);
-                            }
-                            eg[2 + lane * 2] = make_uint4(r[mt][16], r[mt][17], r[mt][18], r[mt][19]);
-                            eg[3 + lane * 2] = make_uint4(r[mt][20], r[mt][21], r[mt][22], r[mt][23]);
-                        }
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+                    // row pitch fixed at P = 32 positions: the lane shifts never leave the warp (see the prob layer below)
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         if (mt >= MT) continue;  // warp-uniform
-                        const int ng = mt * 4 + q + 1;  // next group of 32 positions (none after the tile's last one)
-                        const bool has = ng < MT * 4;
-                        // no divergence: every lane reads the next group's edge values (a broadcast for lanes < 30) and selects
-                        const uint4 *eg = reinterpret_cast<const uint4 *>(edge + (has ? ng : 0) * 24);
-                        const int l2 = lane == 31 ? 1 : 0;
-                        const uint4 a0 = eg[0], a1 = eg[1], b0 = eg[2 + l2 * 2], b1 = eg[3 + l2 * 2];
-                        const float e1[8] = {__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z), __uint_as_float(a0.w),
-                                             __uint_as_float(a1.x), __uint_as_float(a1.y), __uint_as_float(a1.z), __uint_as_float(a1.w)};
-                        const float e2[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
-                                             __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
                         float v[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][8 + c]), 1);
-                            float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][16 + c]), 2);
-                            if (lane == 31) v1 = has ? e1[c] : 0.f;
-                            if (lane >= 30) v2 = has ? e2[c] : 0.f;
+                            const float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][8 + c]), 1);
+                            const float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[mt][16 + c]), 2);
                             v[c] = __uint_as_float(r[mt][c]) + v1 + v2 + s_shift[c];
                             if (L.relu) v[c] = fmaxf(v[c], 0.f);
                         }
@@ -1452,7 +1422,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     const int npad_cols = kw2d ? (cout == 8 ? 32 : (cout == 16 ? 64 : 128)) : npad;  // TMEM columns per M-tile (the template's NPAD)
     const int tmem_budget = fold ? (fold_cw == 32 ? 2 : 4) : 256 / (nacc * npad_cols);
     for (int nx = 1; nx <= 64; ++nx) {
-        const bool pitch32 = kw2d || fold_kw;  // lane shifts of the kw-folded epilogues stay inside a warp
+        const bool pitch32 = kw2d || fold_kw || fold_kw8;  // lane shifts of the kw-folded epilogues stay inside a warp
         const int TXB = pitch32 ? 30 : (Wt + nx - 1) / nx;
         if (pitch32 && nx > 1) break;
         if (TXB > max_cols) continue;
@@ -1466,7 +1436,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
             for (int nslot = 8; nslot >= need; --nslot) {  // deeper ring = more TMA prefetch distance
                 const size_t skip_smem = skip_tma ? 2 * (((size_t)128 * TXB * TY * (cout / 8) + 1023) & ~(size_t)1023) + 1024 : 0;
                 const size_t total = 256 + kMaxOps * 8 + 256 + wbytes + 128 + nslot * slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
-                                     (fold ? (fold_kw8 ? 4096 : 512) : 0) + skip_smem;
+                                     (fold ? 512 : 0) + skip_smem;
                 if (total > (size_t)kSmemLimit) continue;
                 // useful fraction of the MMA rows, x- and y-tile padding, halo re-read
                 const double useful = (double)(TY * TXB) / (MT * 128.0);
@@ -1678,7 +1648,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     L.skip_buf_bytes = (L.skip_tx_bytes + 1023) & ~1023;
     L.skip_off = (128 + 2 * P + 8) * 16;  // past the A-operand overrun guard that follows the ring
     pl.smem_bytes = 256 + kMaxOps * 8 + 256 + wbytes + 128 + (size_t)L.nslot * L.slot_bytes + (128 + 2 * P + 8) * 16 + 1024 + 768 +
-                    (fold ? (fold_kw8 ? 4096 : 512) : 0) + (skip_tma ? 2 * (size_t)L.skip_buf_bytes + 1024 : 0);
+                    (fold ? 512 : 0) + (skip_tma ? 2 * (size_t)L.skip_buf_bytes + 1024 : 0);
     pl.grid = std::min(L.n_items, num_sms);
     pl.grid = std::max(ngroups, pl.grid / ngroups * ngroups);  // every group gets the same number of CTAs
 
