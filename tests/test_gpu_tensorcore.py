@@ -47,6 +47,7 @@ CONV_CASES = [
     (8, 1, 1, (11, 96, 330)),
     (16, 16, 1, (7, 64, 200)),
     (8, 1, 1, (5, 12, 20)),      # prob layer narrower than its fixed 30-column tile
+    (32, 8, 1, (5, 9, 22)),      # conv0 likewise
     (32, 32, 1, (9, 40, 150)),   # conv4-like: depth fold with 32-column blocks, several tiles and segments
 ]
 
