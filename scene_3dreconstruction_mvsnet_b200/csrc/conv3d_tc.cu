@@ -111,6 +111,7 @@ struct TcLayer {
     // epilogue threads when they need it
     int skip_tma, skip_buf_bytes, skip_tx_bytes, skip_off;  // skip_off: offset of buffer 0 from the end of the plane ring
     alignas(64) CUtensorMap skip_map;
+    int tmem_bufs_log2;  // 1 or 2: two or four accumulator buffers in TMEM
     int w_early;     // 1: the packed weights were written long before this launch (cache hit): their copy to shared memory
                      //    may start before the grid dependency wait
     int mma_n;       // > 0: N of the tcgen05.mma (kw-folded 2-D layers: 3*Cout rounded up to 16) -- the TMEM column stride
@@ -179,12 +180,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t bar_base = ptx::smem_u32(smem);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 20);
-    auto sfull_bar = [&](int b) { return bar_base + 8u * (22 + b); };   // skip tile of buffer b has landed
-    auto sempty_bar = [&](int b) { return bar_base + 8u * (24 + b); };  // ... has been read by the 4 warps of set b
-    const uint32_t w_bar = bar_base + 8u * 26;                           // packed weights have landed
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };   // [4] accumulator buffer b is complete
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (20 + b); };  // [4] ... has been drained
+    auto sfull_bar = [&](int b) { return bar_base + 8u * (24 + b); };   // [2] skip tile of buffer b has landed
+    auto sempty_bar = [&](int b) { return bar_base + 8u * (26 + b); };  // [2] ... has been read by the 4 warps of set b
+    const uint32_t w_bar = bar_base + 8u * 28;                           // packed weights have landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 8 * 29);
     uint2 *optab = reinterpret_cast<uint2 *>(smem + 256);  // [kMaxOps] {A desc lo (no slot base), B desc lo}
     float *s_shift = reinterpret_cast<float *>(smem + 256 + kMaxOps * 8);  // [64] folded shifts of this channel group
     constexpr uint32_t kHdr = 256 + kMaxOps * 8 + 256;
@@ -197,8 +198,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncols_buf = L.nacc * L.MT * NPAD;
+    // 2 or 4 accumulator buffers (4 when they fit the 512 columns): steps alternate between the two issuer warps and between
+    // the two epilogue warp sets by parity, so with 4 buffers each of them has two in flight and the hand-offs
+    // (commit -> drain -> release -> next MMAs) of one buffer overlap the work on the other
+    const uint32_t nbs = L.tmem_bufs_log2;  // log2(buffers)
+    const uint32_t nbm = (1u << nbs) - 1u;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2u * ncols_buf) tmem_cols <<= 1;
+    while (tmem_cols < ((uint32_t)ncols_buf << nbs)) tmem_cols <<= 1;
 
     // ---- one-time setup
     // Items are ordered so that a CTA keeps the same n-group for all of its items: group = blockIdx.x % ngroups.
@@ -218,10 +224,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             // dual issuers: a plane is free when BOTH issuer warps' MMAs that read it have completed
             ptx::mbar_init(empty_bar(s), L.dual ? 2 : 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             ptx::mbar_init(tfull_bar(b), 1);
             // lean epilogue: the 4 quadrant warps of the set that owns this buffer; general: all 8 epilogue warps
             ptx::mbar_init(tempty_bar(b), STEPWISE ? 4 : 8);
+        }
+        for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(sfull_bar(b), 1);
             ptx::mbar_init(sempty_bar(b), 4);
         }
@@ -341,8 +349,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             int b, x0, y0, zs, T;
             decode(it, b, x0, y0, zs, T);
             for (int t = 0; t < T; ++t, ++st) {
-                const uint32_t buf = st & 1;
-                const bool mine = !L.dual || buf == me;  // dual mode: the other warp's steps only advance the ring state
+                const uint32_t buf = st & nbm;
+                const bool mine = !L.dual || (st & 1u) == me;  // dual mode: the other warp's steps only advance the ring state
                 const uint32_t sl0 = s0, sl1 = wrap(s0 + 1), sl2 = wrap(s0 + 2);
                 if (leader && mine) {  // only one lane spins; the warp re-converges below so the issue loop stays uniform
                     const long long c0 = clock64();
@@ -353,7 +361,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                         ptx::mbar_wait(full_bar(sl), (par >> sl) & 1u);
                     }
                     const long long c1 = clock64();
-                    ptx::mbar_wait(tempty_bar(buf), ((st >> 1) & 1) ^ 1);
+                    ptx::mbar_wait(tempty_bar(buf), ((st >> nbs) & 1) ^ 1);
                     w_full += c1 - c0;
                     w_tempty += clock64() - c1;
                 }
@@ -477,10 +485,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 // so each warp has two step times for one drain and the per-step fixed costs (barrier wait,
                 // tcgen05.wait::ld round trip, release) are paid once per step.  General path (skip loads in the loop):
                 // both warps work on every step and split its (M-tile, accumulator) pairs -- measured faster there.
-                const uint32_t buf = st & 1;
-                if (STEPWISE && buf != (uint32_t)eset) continue;
+                const uint32_t buf = st & nbm;
+                const uint32_t sbuf = st & 1u;  // skip-tile buffer (two of them, one per warp set)
+                if (STEPWISE && sbuf != (uint32_t)eset) continue;
                 const long long c0 = clock64();
-                ptx::mbar_wait(tfull_bar(buf), (st >> 1) & 1);
+                ptx::mbar_wait(tfull_bar(buf), (st >> nbs) & 1);
                 const long long c1 = clock64();
                 epi_wait += c1 - c0;
                 ptx::tcgen05_fence_after();
@@ -546,8 +555,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     // skip tile in shared memory (L.skip_tma): voxel (pz, 2y+py, 2x+px) of chunk cc at
                     // (((cc*2 + pz) * 2TY + 2y+py) * 2TXB + 2x+px) * 16 bytes; sp* hold the thread's (2y, 2x) part
                     const uint32_t s_row = 2u * (uint32_t)L.TXB * 16u, s_plane = 2u * (uint32_t)L.TY * s_row;
-                    const uint32_t s_buf = skip_base + buf * (uint32_t)L.skip_buf_bytes;
-                    if (L.skip_tma) ptx::mbar_wait(sfull_bar(buf), (st >> 1) & 1);
+                    const uint32_t s_buf = skip_base + sbuf * (uint32_t)L.skip_buf_bytes;
+                    if (L.skip_tma) ptx::mbar_wait(sfull_bar(sbuf), (st >> 1) & 1);
                     for (int mt = 0; mt < L.MT; ++mt) {
                         const bool ok = (vmask >> mt) & 1u;
                         const size_t mb = mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3));
@@ -619,7 +628,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     }
                     if (L.skip_tma) {  // every skip value of this step is in registers or stored: the buffer can be refilled
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(sempty_bar(buf));
+                        if (lane == 0) ptx::mbar_arrive(sempty_bar(sbuf));
                     }
                     epi_work += clock64() - c1;
                 } else if constexpr (SIMPLE) {
@@ -1498,6 +1507,8 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     auto rcp40 = [](int d) { return (unsigned long long)(((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d); };
     L.rcp_zsegs = rcp40(L.zsegs); L.rcp_tiles_x = rcp40(L.tiles_x); L.rcp_tiles_y = rcp40(L.tiles_y);
     L.nacc = nacc; L.npad = npad; L.wbytes_group = wbytes;
+    static const bool nobuf4 = getenv("MVS_TC_NOBUF4") != nullptr;  // A/B knob
+    L.tmem_bufs_log2 = (!fold && !nobuf4 && 4 * nacc * MT * npad_cols <= 512) ? 2 : 1;
     L.cout_group = cout_group; L.cout_total = cout;
     L.out_scale = (kind == TC_CONVT) ? 2 : 1;
     L.Dout = L.out_scale * Dt; L.Hout = L.out_scale * Ht; L.Wout = L.out_scale * Wt;
