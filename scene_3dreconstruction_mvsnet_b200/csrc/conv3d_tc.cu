@@ -134,6 +134,18 @@ template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
     return F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
 }
+// ReLU on a packed pair after rounding: max(round(x), 0) == round(max(x, 0)) (rounding is monotonic, 0 is exact) -- one
+// instruction for two channels instead of two fp32 max
+template <bool F16>
+__device__ __forceinline__ uint32_t relu16x2(uint32_t v) {
+    if constexpr (F16) {
+        const __half2 r = __hmax2(*reinterpret_cast<const __half2 *>(&v), __float2half2_rn(0.f));
+        return *reinterpret_cast<const uint32_t *>(&r);
+    } else {
+        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&v), __float2bfloat162_rn(0.f));
+        return *reinterpret_cast<const uint32_t *>(&r);
+    }
+}
 
 // floor(n / d) for n < 2^20 with rcp = ceil(2^40 / d)
 __device__ __forceinline__ uint32_t fast_div40(uint32_t n, unsigned long long rcp) {
@@ -523,15 +535,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                             if (mt >= L.MT) continue;  // warp-uniform
                             uint32_t pk[COUT / 2];
 #pragma unroll
-                            for (int c = 0; c < COUT; c += 2) {
-                                float v[2];
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][COUT + c + h]), 1);
-                                    const float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2 * COUT + c + h]), 2);
-                                    v[h] = fmaxf(__uint_as_float(r[i][c + h]) + v1 + v2 + s_shift[c + h], relu_lo);
-                                }
-                                pk[c / 2] = pack16x2<F16>(v[0], v[1]);
+                            for (int c = 0; c < COUT; c += 2) {  // two channels at a time: packed fp32 adds, same order as before
+                                const float2 a = make_float2(__uint_as_float(r[i][c]), __uint_as_float(r[i][c + 1]));
+                                const float2 u1 = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(r[i][COUT + c]), 1),
+                                                              __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][COUT + c + 1]), 1));
+                                const float2 u2 = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2 * COUT + c]), 2),
+                                                              __shfl_down_sync(0xffffffffu, __uint_as_float(r[i][2 * COUT + c + 1]), 2));
+                                const float2 v = __fadd2_rn(__fadd2_rn(__fadd2_rn(a, u1), u2), make_float2(s_shift[c], s_shift[c + 1]));
+                                const uint32_t p = pack16x2<F16>(v.x, v.y);
+                                pk[c / 2] = L.relu ? relu16x2<F16>(p) : p;
                             }
                             if (!((vmask >> mt) & 1u)) continue;
                             uint4 *op = oz + (mt == 0 ? base0 : (mt == 1 ? base1 : (mt == 2 ? base2 : base3)));
@@ -657,16 +669,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
                             for (int c8 = 0; c8 < NPAD / 8; ++c8) {
                                 if (c8 >= nchunk) break;
-                                float v[8];
+                                uint32_t pw[4];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    v[e] = fmaxf(__uint_as_float(r[i][c8 * 8 + e]) + (NPAD <= 32 ? shr[(c8 * 8 + e) % kShr] : s_shift[c8 * 8 + e]),
-                                                 relu_lo);
-                                uint4 pk;
-                                pk.x = pack16x2<F16>(v[0], v[1]);
-                                pk.y = pack16x2<F16>(v[2], v[3]);
-                                pk.z = pack16x2<F16>(v[4], v[5]);
-                                pk.w = pack16x2<F16>(v[6], v[7]);
+                                for (int e = 0; e < 8; e += 2) {  // packed fp32 add of the shift, ReLU on the packed 16-bit pair
+                                    const float2 sh = NPAD <= 32 ? make_float2(shr[(c8 * 8 + e) % kShr], shr[(c8 * 8 + e + 1) % kShr])
+                                                                 : make_float2(s_shift[c8 * 8 + e], s_shift[c8 * 8 + e + 1]);
+                                    const float2 v = __fadd2_rn(make_float2(__uint_as_float(r[i][c8 * 8 + e]), __uint_as_float(r[i][c8 * 8 + e + 1])), sh);
+                                    const uint32_t p = pack16x2<F16>(v.x, v.y);
+                                    pw[e / 2] = L.relu ? relu16x2<F16>(p) : p;
+                                }
+                                const uint4 pk = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                                 op[(size_t)c8 * plane] = pk;
                                 if (L.out2 != nullptr)
                                     reinterpret_cast<uint4 *>(L.out2)[((size_t)b * 4 * (L.cout_total >> 3) + chunk0 + c8) * plane_sp +
