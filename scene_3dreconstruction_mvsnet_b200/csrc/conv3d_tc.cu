@@ -618,21 +618,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                     const int u = py * CPC + cc;
                                     uint32_t pk[8];
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) {  // h = x parity
-                                        float v[8];
+                                    for (int h = 0; h < 2; ++h) {  // h = x parity; two channels at a time (packed fp32 adds)
 #pragma unroll
-                                        for (int e = 0; e < 8; ++e)
-                                            v[e] = fmaxf(__uint_as_float(r[u][h * 8 + e]) + s_shift[cc * 8 + e], relu_lo);
-                                        if (skp != nullptr) {
-#pragma unroll
-                                            for (int e = 0; e < 4; ++e) {
-                                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&sk[u][h * 4 + e]));
-                                                v[2 * e] += f.x;
-                                                v[2 * e + 1] += f.y;
-                                            }
+                                        for (int e = 0; e < 4; ++e) {
+                                            float2 a = __fadd2_rn(make_float2(__uint_as_float(r[u][h * 8 + 2 * e]), __uint_as_float(r[u][h * 8 + 2 * e + 1])),
+                                                                  make_float2(s_shift[cc * 8 + 2 * e], s_shift[cc * 8 + 2 * e + 1]));
+                                            a.x = fmaxf(a.x, relu_lo);
+                                            a.y = fmaxf(a.y, relu_lo);
+                                            if (skp != nullptr)
+                                                a = __fadd2_rn(a, __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&sk[u][h * 4 + e])));
+                                            pk[h * 4 + e] = pack_bf16x2(a.x, a.y);
                                         }
-#pragma unroll
-                                        for (int e = 0; e < 4; ++e) pk[h * 4 + e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
                                     }
                                     ptx::stg256(outp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], pk);
                                 }
