@@ -800,11 +800,10 @@ constexpr int kFoldMaxR = 16;
 template <int MT>
 __device__ __forceinline__ void issue_fold_pass(const uint2 *__restrict__ optab, int nops, uint32_t d, uint32_t cols_mt,
                                                 uint32_t sb, uint32_t brow, uint32_t idesc, uint64_t desc_hi) {
-    uint2 en = optab[0];  // next op's table entry, loaded one op ahead (see issue_step)
+    // (loading the table entry one op ahead as in issue_step was measured here too: conv0 442 -> 477 us -- not kept)
 #pragma unroll 2
     for (int o = 0; o < nops; ++o) {
-        const uint2 e = en;
-        en = optab[o + 1 < nops ? o + 1 : o];
+        const uint2 e = optab[o];
         const uint32_t alo = e.x + sb;
         const uint64_t bd = desc_hi | (uint64_t)(e.y + brow);
 #pragma unroll
