@@ -6,7 +6,8 @@ independently in C, this file issues the SAME PyTorch library calls the referenc
 torch.gather), written as stateless functions over a state_dict instead of nn.Modules.
 It is what bench.py times as the CPU baseline (`--impl reference`, `cpu_baseline.kind="port"`):
 the reference's CPU path *is* these ATen/oneDNN calls on the host cores, and /root/reference
-itself does not exist on the GPU box.
+itself does not exist on the GPU box.  bench.py also runs it with CUDA tensors as the
+`cuda_eager_baseline` (the reference's stock eager-GPU path: the same calls dispatch to cuDNN / ATen CUDA).
 
 Pinned against the unmodified reference in tests/test_oracle_golden.py (golden vectors made by
 tests/make_golden.py, which imports /root/reference/models in the build container).
@@ -41,9 +42,10 @@ def plane_sweep_grid(src_proj, ref_proj, depth_values, h, w):
     B, D = depth_values.shape
     P = src_proj @ torch.inverse(ref_proj)
     R, t = P[:, :3, :3], P[:, :3, 3:4]
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
-                            indexing="ij")
-    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)))  # [3, hw]
+    dev = src_proj.device  # CPU for the oracle; bench.py also runs this port on the GPU as the eager-CUDA baseline
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=dev),
+                            torch.arange(w, dtype=torch.float32, device=dev), indexing="ij")
+    pix = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, device=dev)))  # [3, hw]
     q = (R @ pix.unsqueeze(0).expand(B, -1, -1)).unsqueeze(2) * depth_values.view(B, 1, D, 1) + t.view(B, 3, 1, 1)
     xy = q[:, :2] / q[:, 2:3]
     gx = xy[:, 0] / ((w - 1) / 2) - 1
@@ -98,7 +100,7 @@ def depth_tail(logits, depth_values):
     p = F.softmax(logits, dim=1)
     depth = torch.sum(p * depth_values.view(B, D, 1, 1), 1)
     sum4 = 4 * F.avg_pool3d(F.pad(p.unsqueeze(1), (0, 0, 0, 0, 1, 2)), (4, 1, 1), stride=1, padding=0).squeeze(1)
-    idx = torch.sum(p * torch.arange(D, dtype=torch.float32).view(1, D, 1, 1), 1).long()
+    idx = torch.sum(p * torch.arange(D, dtype=torch.float32, device=p.device).view(1, D, 1, 1), 1).long()
     conf = torch.gather(sum4, 1, idx.unsqueeze(1)).squeeze(1)
     return depth, conf, p
 

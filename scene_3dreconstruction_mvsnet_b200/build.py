@@ -43,7 +43,7 @@ def _compile(nvcc, src, verbose):
     return obj, r.stderr
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, report=False):
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     todo = []
@@ -64,6 +64,9 @@ def build_library(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if report:
+        print("libmvsnet_b200.so: compiled %s; reused up-to-date objects of %s" % (
+            ", ".join(todo) or "nothing", ", ".join(s for s in SOURCES if s not in todo) or "nothing"))
     if verbose:
         for src, log in logs.items():
             print("==== %s\n%s" % (src, log))

@@ -186,6 +186,13 @@ extern "C" int mvs_depth_from_features_host(const float *fea_host, const float *
 
     const size_t HW = (size_t)H * W, n0 = (size_t)D * HW;
     const size_t fea_b = (size_t)B * V * 32 * HW * 4, proj_b = (size_t)B * V * 64, dv_b = (size_t)B * D * 4;
+    // the weights live in device memory owned by this call: packed copies keyed by those pointers must not outlive it, on
+    // any exit path (a later cudaMalloc may return the same addresses).  Declared first = destroyed last, after `wts`... the
+    // clear only drops cache entries, it does not touch the buffers, so the order against ~DevBuf does not matter.
+    struct CacheGuard {
+        bool on;
+        ~CacheGuard() { if (on) mvs_weight_cache_clear(); }
+    } cache_guard{precision == MVS_PRECISION_BF16};
     DevBuf fea, proj, dv, var, ws1, ws2, logits, depth, conf, wts;
     MVS_CUDA(fea.alloc(fea_b));
     MVS_CUDA(proj.alloc(proj_b));
@@ -228,7 +235,5 @@ extern "C" int mvs_depth_from_features_host(const float *fea_host, const float *
     MVS_CUDA(cudaMemcpyAsync(depth_host, depth.p, (size_t)B * HW * 4, cudaMemcpyDeviceToHost, st));
     MVS_CUDA(cudaMemcpyAsync(conf_host, conf.p, (size_t)B * HW * 4, cudaMemcpyDeviceToHost, st));
     MVS_CUDA(cudaStreamSynchronize(st));
-    // the weights lived in device memory owned by this call: packed copies keyed by those pointers must not outlive it
-    if (precision == MVS_PRECISION_BF16) mvs_weight_cache_clear();
     return MVS_OK;
 }

@@ -130,15 +130,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {  // saturatin
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// pack / unpack in the 16-bit storage format of the tensor-core path (kActF16, tc_common.cuh)
+__device__ __forceinline__ uint32_t pack_act(float a, float b) { return kActF16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
+__device__ __forceinline__ float2 unpack_act(uint32_t u) {
+    if constexpr (kActF16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+    else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u));
+}
 template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
-    return F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+    return (F16 || kActF16) ? pack_f16x2(a, b) : pack_bf16x2(a, b);
 }
 // ReLU on a packed pair after rounding: max(round(x), 0) == round(max(x, 0)) (rounding is monotonic, 0 is exact) -- one
 // instruction for two channels instead of two fp32 max
 template <bool F16>
 __device__ __forceinline__ uint32_t relu16x2(uint32_t v) {
-    if constexpr (F16) {
+    if constexpr (F16 || kActF16) {
         const __half2 r = __hmax2(*reinterpret_cast<const __half2 *>(&v), __float2half2_rn(0.f));
         return *reinterpret_cast<const uint32_t *>(&r);
     } else {
@@ -351,7 +357,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const uint32_t me = (warp == 10) ? 1u : 0u;
         const bool leader = ptx::elect_one();
         const uint32_t mma_n = L.mma_n > 0 ? (uint32_t)L.mma_n : (uint32_t)NPAD;
-        const uint32_t idesc = F16 ? ptx::make_idesc_f16_m128(mma_n) : ptx::make_idesc_bf16_m128(mma_n);
+        const uint32_t idesc = (F16 || kActF16) ? ptx::make_idesc_f16_m128(mma_n) : ptx::make_idesc_bf16_m128(mma_n);
         uint32_t st = 0;
         uint32_t s0 = 0;    // ring slot of the oldest plane of the current step
         uint32_t par = 0;   // bit s: parity of the fill of slot s that is current (toggles when the slot is released)
@@ -631,8 +637,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                             a.x = fmaxf(a.x, relu_lo);
                                             a.y = fmaxf(a.y, relu_lo);
                                             if (skp != nullptr)
-                                                a = __fadd2_rn(a, __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&sk[u][h * 4 + e])));
-                                            pk[h * 4 + e] = pack_bf16x2(a.x, a.y);
+                                                a = __fadd2_rn(a, unpack_act(sk[u][h * 4 + e]));
+                                            pk[h * 4 + e] = pack_act(a.x, a.y);
                                         }
                                     }
                                     ptx::stg256(outp + ((size_t)b * CPC + cc) * plane + mb + mvoff[pz * 2 + py], pk);
@@ -736,10 +742,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                                 reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox[j]] = v[0];
                             } else {
                                 if (skip != nullptr) {  // skip + relu(bn(convT))  (mvsnet.py:69-71)
-                                    const __nv_bfloat162 *sp = reinterpret_cast<const __nv_bfloat162 *>(&sk[j][c8]);
+                                    const uint32_t *sp = reinterpret_cast<const uint32_t *>(&sk[j][c8]);
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
-                                        const float2 f = __bfloat1622float2(sp[e]);
+                                        const float2 f = unpack_act(sp[e]);
                                         v[2 * e] += f.x;
                                         v[2 * e + 1] += f.y;
                                     }
@@ -971,7 +977,7 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                     const uint32_t sb = (ring_base + slot * L.slot_bytes) >> 4;
                     const uint32_t d = tmem_base + (pj + k0) * CW + mt_lo * cols_mt;  // window start: never wraps (mirror blocks)
                     const uint32_t brow = k0 * CW;
-                    const uint32_t idesc = ptx::make_idesc_bf16_m128(cnt * CW);
+                    const uint32_t idesc = kActF16 ? ptx::make_idesc_f16_m128(cnt * CW) : ptx::make_idesc_bf16_m128(cnt * CW);
                     const uint32_t sbm = sb + mt_lo * 128;  // this warp's first M-tile
                     if (mt_n == 2) issue_fold_pass<2>(optab, nops, d, cols_mt, sbm, brow, idesc, kDescHi);
                     else if (mt_n == 1) issue_fold_pass<1>(optab, nops, d, cols_mt, sbm, brow, idesc, kDescHi);
@@ -1090,10 +1096,10 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                         }
                         if (!((vmask >> mt) & 1u)) continue;
                         uint4 pk;
-                        pk.x = pack_bf16x2(v[0], v[1]);
-                        pk.y = pack_bf16x2(v[2], v[3]);
-                        pk.z = pack_bf16x2(v[4], v[5]);
-                        pk.w = pack_bf16x2(v[6], v[7]);
+                        pk.x = pack_act(v[0], v[1]);
+                        pk.y = pack_act(v[2], v[3]);
+                        pk.z = pack_act(v[4], v[5]);
+                        pk.w = pack_act(v[6], v[7]);
                         reinterpret_cast<uint4 *>(L.out)[(size_t)b * plane + base[mt] + zoff] = pk;
                         if (L.out2 != nullptr)
                             reinterpret_cast<uint4 *>(L.out2)[(size_t)b * 4 * plane_sp + sp[mt] + (size_t)(zs + e) * zstride_sp] = pk;
@@ -1206,10 +1212,10 @@ conv3d_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
                                     reinterpret_cast<float *>(L.out)[(size_t)b * plane + vox] = v[0];
                                 } else {
                                     uint4 pk;
-                                    pk.x = pack_bf16x2(v[0], v[1]);
-                                    pk.y = pack_bf16x2(v[2], v[3]);
-                                    pk.z = pack_bf16x2(v[4], v[5]);
-                                    pk.w = pack_bf16x2(v[6], v[7]);
+                                    pk.x = pack_act(v[0], v[1]);
+                                    pk.y = pack_act(v[2], v[3]);
+                                    pk.z = pack_act(v[4], v[5]);
+                                    pk.w = pack_act(v[6], v[7]);
                                     reinterpret_cast<uint4 *>(L.out)[((size_t)b * (L.cout_total / 8) + c8) * plane + vox] = pk;
                                     if (L.out2 != nullptr)
                                         reinterpret_cast<uint4 *>(L.out2)[((size_t)b * 4 * (L.cout_total >> 3) + c8) * plane_sp + sp[mt] +
@@ -1251,10 +1257,10 @@ __global__ void ncdhw_to_cp8_kernel(const float *__restrict__ in, uint4 *__restr
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = __ldcs(src + (size_t)e * N);
     uint4 pk;
-    pk.x = pack_bf16x2(f[0], f[1]);
-    pk.y = pack_bf16x2(f[2], f[3]);
-    pk.z = pack_bf16x2(f[4], f[5]);
-    pk.w = pack_bf16x2(f[6], f[7]);
+    pk.x = pack_act(f[0], f[1]);
+    pk.y = pack_act(f[2], f[3]);
+    pk.z = pack_act(f[4], f[5]);
+    pk.w = pack_act(f[6], f[7]);
     out[(size_t)bc * N + v] = pk;
 }
 
@@ -1265,11 +1271,11 @@ __global__ void cp8_to_ncdhw_kernel(const uint4 *__restrict__ in, float *__restr
     if (v >= N) return;
     const int b = bc / (C / 8), chunk = bc % (C / 8);
     const uint4 pk = __ldg(in + (size_t)bc * N + v);
-    const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(&pk);
     float *dst = out + ((size_t)b * C + chunk * 8) * N + v;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(p[e]);
+        const float2 f = unpack_act(p[e]);
         dst[(size_t)(2 * e) * N] = f.x;
         dst[(size_t)(2 * e + 1) * N] = f.y;
     }
@@ -1345,7 +1351,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, __nv_bfloat16 *
     float v = 0.f;
     if (tap >= 0 && nn < p.cout_group && co < p.cout_total && cin < p.cin_total)
         v = p.transposed ? w[((size_t)cin * p.cout_total + co) * 27 + tap] : w[((size_t)co * p.cin_total + cin) * p.ntaps + tap];
-    if (p.f16) reinterpret_cast<__half *>(out)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    if (p.f16 || kActF16) reinterpret_cast<__half *>(out)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     else out[idx] = __float2bfloat16_rn(v);
 }
 
@@ -1382,33 +1388,25 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     // N (padded cout) per CTA: keep resident weights <= ~112 KB
     const int kpairs_tap = (cin >= 16) ? cin / 16 : 1;
     // depth-folded variant (conv3d_tc_fold_kernel): stride-1 layers whose Cout fits one 16-column block
-    static const bool nofold = getenv("MVS_TC_NOFOLD") != nullptr;  // A/B knob
     // ... and Cout = 32 (conv4, 32 -> 32): 32-column blocks, N = 96: 18 MMAs of 56 cycles per plane and M-tile instead of 54 of 40
-    static const bool nofold32 = getenv("MVS_TC_NOFOLD32") != nullptr;  // A/B knob
-    const bool fold = (kind == TC_CONV_S1) && (cout <= 16 || (cout == 32 && cin >= 16 && !nofold32)) && !nofold;
-    static const bool nofoldkw = getenv("MVS_TC_NOFOLDKW") != nullptr;  // A/B knob
-    const bool fold_kw = fold && cin == 8 && cout == 1 && !nofoldkw;
+    const bool fold = (kind == TC_CONV_S1) && (cout <= 16 || (cout == 32 && cin >= 16));
+    const bool fold_kw = fold && cin == 8 && cout == 1;
     // conv0 (32 -> 8): kw folded into N as well, 32-column blocks [kw][8 Cout] (24 used), N = 96: 6 MMAs of 56 cycles per
     // plane and M-tile instead of 18 of 44 -- the layer was bound by the shared-memory operand path of its MMAs
-    static const bool nofoldkw8 = getenv("MVS_TC_NOFOLDKW8") != nullptr;  // A/B knob
-    const bool fold_kw8 = fold && cin >= 16 && cout == 8 && !nofoldkw8;
+    const bool fold_kw8 = fold && cin >= 16 && cout == 8;
     const int fold_cw = fold ? ((fold_kw8 || cout == 32) ? 32 : 16) : 0;
     const bool is2d = (kind == TC_CONV2D);  // planes are independent images: only the (kh, kw) taps of one plane
     // class-merged transposed conv: one MMA per input offset (dz,dy,dx) and K-chunk with N = 8 classes x Cout
-    static const bool nomerge = getenv("MVS_TC_NOMERGE") != nullptr;  // A/B knob
-    const bool merged_t = (kind == TC_CONVT) && cin >= 16 && 8 * cout <= 128 && !nomerge;
+    const bool merged_t = (kind == TC_CONVT) && cin >= 16 && 8 * cout <= 128;
     // 2-D layers with fp16 operands (FeatureNet): kw folded into N (N = 3*Cout), row pitch fixed at 32 positions so that the
     // epilogue's lane shifts stay inside a warp
-    static const bool nokw2d = getenv("MVS_TC_NOKW2D") != nullptr;  // A/B knob
     // Measured per FeatureNet layer (tools/featurenet_tc_profile.py, kw-folded / plain, ms): 8->8 k3 0.119 / 0.099 (the
     // plain form has only 5 MMAs per M-tile: the fold's 3x larger accumulator read dominates), 32(s2d)->16 0.044 / 0.065,
     // 16->16 0.038 / 0.040, 64(s2d)->32 0.032 / 0.037, 32->32 0.027 / 0.021 -- so: folded when the plain form has >= 9
     // MMAs per M-tile and Cout <= 16, or >= 36 with Cout = 32.
-    static const bool kw2d_all = getenv("MVS_TC_KW2D_ALL") != nullptr;  // A/B knob: fold every eligible 2-D layer
-    const bool kw2d = is2d && allow_kw2d && !nokw2d && Win >= 30 &&
-                      (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64) || (kw2d_all && (cout == 8 || cout == 16 || cout == 32)));
-    static const bool noskiptma = getenv("MVS_TC_NOSKIPTMA") != nullptr;  // A/B knob
-    const bool skip_tma = merged_t && skip_ptr != nullptr && !noskiptma;
+    const bool kw2d = is2d && allow_kw2d  && Win >= 30 &&
+                      (((cout == 8 || cout == 16) && cin >= 16) || (cout == 32 && cin >= 64));
+    const bool skip_tma = merged_t && skip_ptr != nullptr;
     int ntaps_ops;  // MMA instructions per step
     if (merged_t) ntaps_ops = 8 * kpairs_tap;
     else if (fold_kw) ntaps_ops = 2;
@@ -1521,8 +1519,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     auto rcp40 = [](int d) { return (unsigned long long)(((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d); };
     L.rcp_zsegs = rcp40(L.zsegs); L.rcp_tiles_x = rcp40(L.tiles_x); L.rcp_tiles_y = rcp40(L.tiles_y);
     L.nacc = nacc; L.npad = npad; L.wbytes_group = wbytes;
-    static const bool nobuf4 = getenv("MVS_TC_NOBUF4") != nullptr;  // A/B knob
-    L.tmem_bufs_log2 = (!fold && !nobuf4 && 4 * nacc * MT * npad_cols <= 512) ? 2 : 1;
+    L.tmem_bufs_log2 = (!fold && 4 * nacc * MT * npad_cols <= 512) ? 2 : 1;
     L.cout_group = cout_group; L.cout_total = cout;
     L.out_scale = (kind == TC_CONVT) ? 2 : 1;
     L.Dout = L.out_scale * Dt; L.Hout = L.out_scale * Ht; L.Wout = L.out_scale * Wt;
@@ -1540,8 +1537,7 @@ static int make_plan(TcPlan &pl, TcKind kind, int B, int cin, int cout, int Din,
     W.merged_t = merged_t ? 1 : 0;
     L.merged_t = merged_t ? 1 : 0;
     L.fold = fold ? 1 : 0;
-    static const bool nodual = getenv("MVS_TC_NODUAL") != nullptr;  // A/B knob
-    L.dual = (!fold && !nodual) ? 1 : 0;
+    L.dual = (!fold) ? 1 : 0;
     L.fold_R = fold ? std::min(kFoldMaxR, 512 / (MT * fold_cw)) : 0;
     L.fold_sets = fold ? ((fold_kw8 || fold_kw) ? 3 : 2) : 0;  // the plain variant needs > 128 registers: 2 sets
     const int chunk_stride = rows * P * 16;
@@ -1862,7 +1858,6 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
         // per-layer one that a concurrent launch of another layer could lower between this call and the launch
         MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-        static const bool nopdl = getenv("MVS_TC_NOPDL") != nullptr;  // A/B knob
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)pl.grid);
         cfg.blockDim = dim3((unsigned)(pl.L.fold ? fold_threads(pl.L.fold_sets) : (pl.L.dual ? kTcThreadsDual : kTcThreads)));
@@ -1872,7 +1867,7 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = nopdl ? 0 : 1;
+        cfg.numAttrs = 1;
         MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, pl.tmap, pl.L));
         MVS_LAUNCH_CHECK(1);
         return MVS_OK;
@@ -1926,8 +1921,7 @@ int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_pa
     void *vol = take(volume_cp8 ? 0 : n0 * 64), *c0 = take(n0 * 16), *c1 = take(n0 * 4), *c2 = take(n0 * 4), *c3 = take(n0),
          *c4 = take(n0), *c5 = take(n0 / 4), *c6 = take(n0 / 4), *u7 = take(n0), *u9 = take(n0 * 4),
          *u11 = take(n0 * 16);
-    static const bool nosplit = getenv("MVS_TC_NOSPLIT") != nullptr;  // A/B knob
-    void *c0s = nosplit ? nullptr : take(n0 * 16), *c2s = nosplit ? nullptr : take(n0 * 4), *c4s = nosplit ? nullptr : take(n0);
+    void *c0s = take(n0 * 16), *c2s = take(n0 * 4), *c4s = take(n0);
     uint8_t *wsc = take(11 * kWScratch);
     const size_t N = (size_t)D * H * W;
     if (volume_cp8) {
@@ -2120,7 +2114,10 @@ int featurenet_tc(const void *imgs, int imgs_u8, const mvs_featurenet_params *p,
         const long long total = (long long)px;
         const long long quads = total / 4;  // W % 4 == 0
         const bool aligned = ((uintptr_t)imgs & 15) == 0;
-        if (imgs_u8) images_to_cp8_kernel<uint8_t><<<cdiv(quads, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, (size_t)H * W, quads);
+        // the vectorised kernels read 4 pixels per load: uchar4 needs a 4-byte aligned base (a uint8 view with an odd
+        // storage offset is legal for the caller), float4 a 16-byte aligned one; otherwise the scalar kernel
+        if (imgs_u8 && ((uintptr_t)imgs & 3) != 0) nchw_to_cp8n_f16_kernel<uint8_t><<<cdiv(total, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
+        else if (imgs_u8) images_to_cp8_kernel<uint8_t><<<cdiv(quads, 256), 256, 0, st>>>((const uint8_t *)imgs, (uint4 *)in0, (size_t)H * W, quads);
         else if (aligned) images_to_cp8_kernel<float><<<cdiv(quads, 256), 256, 0, st>>>((const float *)imgs, (uint4 *)in0, (size_t)H * W, quads);
         else nchw_to_cp8n_f16_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float *)imgs, (uint4 *)in0, N, 3, H, W, 0, total);
         MVS_LAUNCH_CHECK(1);

@@ -8,6 +8,13 @@
 #include <stdint.h>
 
 namespace mvs {
+
+// 16-bit storage format of the tensor-core path (CostRegNet activations, cost volume, packed weights): fp16 since
+// round 2 -- kind::f16 runs fp16 and bf16 at the same rate, the activations are O(1) after BN + ReLU, and fp16's 3 extra
+// mantissa bits cut the depth-map error of the whole path several times (profiles/r02_precision.md).  Values are
+// converted with saturation (|x| <= 65504).  kActF16 = false restores bf16 everywhere.
+constexpr bool kActF16 = true;
+
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

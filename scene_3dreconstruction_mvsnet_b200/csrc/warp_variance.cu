@@ -709,7 +709,6 @@ static int pick_dchunk(int B, int D, int H, int W) {
     const long long tiles = (long long)cdiv(W, 32) * cdiv(H, kWarps) * B;
     int dchunk = 16;
     while (dchunk > 2 && tiles * cdiv(D, dchunk) < 148LL * 2 * 4) dchunk >>= 1;
-    if (const char *e = getenv("MVS_WARP_DCHUNK")) dchunk = std::max(1, atoi(e));  // tuning knob (tools/warp_tune.py)
     while ((long long)B * cdiv(D, dchunk) > 65535) dchunk <<= 1;  // gridDim.z limit
     return dchunk;
 }

@@ -362,8 +362,12 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                         const float2 qv = HACC ? __half22float2(Qh[HACC ? 4 * c + j : 0]) : Q[HACC ? 0 : 4 * c + j];
                         const float2 m = __fmul2_rn(sv, invV2);
                         const float2 r = __ffma2_rn(qv, invV2, __fmul2_rn(m, make_float2(-m.x, -m.y)));
-                        const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
-                        pk[j] = *reinterpret_cast<const uint32_t *>(&o);
+                        if constexpr (kActF16) {  // saturating: a variance above 65504 (|feature| > 250) stays finite
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(r.y), "f"(r.x));
+                        } else {
+                            const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
+                            pk[j] = *reinterpret_cast<const uint32_t *>(&o);
+                        }
                     }
                     __stcs(out + ((((size_t)b * 4 + c) * D + d) * H + y) * W + x, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 }

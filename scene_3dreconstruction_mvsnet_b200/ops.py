@@ -56,6 +56,20 @@ def weights_changed():
         _lib.load().mvs_weight_cache_clear()
 
 
+def compose_like_reference(proj):
+    """proj [B,V,4,4] -> [B,V,4,4] whose view 0 is the identity and whose view v is `src_proj @ inverse(ref_proj)`
+    computed by the reference's own torch calls (models/module.py:107, fp32, on the tensors' device).  The library then
+    composes H_v * inverse(I) = H_v exactly, so the strict-fp32 path samples at the reference's homographies bit for
+    bit instead of the library's own (more accurate) float64 composition: the two differ by ~1.5e-5 px at the DTU
+    shape, 100x the fp32 rounding of everything else on the path."""
+    ref_inv = torch.inverse(proj[:, 0])
+    out = torch.empty_like(proj)
+    out[:, 0] = torch.eye(4, dtype=proj.dtype, device=proj.device)
+    for v in range(1, proj.shape[1]):
+        out[:, v] = torch.matmul(proj[:, v], ref_inv)
+    return out
+
+
 def release_workspaces():
     """Drop every cached scratch buffer (they are re-created on demand)."""
     _WS_CACHE.clear()
@@ -111,6 +125,10 @@ class _HomoWarping(torch.autograd.Function):
 
 
 def homo_warping(src_fea, src_proj, ref_proj, depth_values):
+    if isinstance(src_proj, torch.Tensor) and src_proj.is_cuda and src_proj.dtype == torch.float32:
+        # module.py:107 with the reference's own calls (see compose_like_reference)
+        src_proj = torch.matmul(src_proj, torch.inverse(ref_proj))
+        ref_proj = torch.eye(4, dtype=src_proj.dtype, device=src_proj.device).expand_as(src_proj).contiguous()
     if torch.is_grad_enabled() and src_fea.requires_grad:
         return _HomoWarping.apply(src_fea, src_proj, ref_proj, depth_values)
     return homo_warping_fwd(src_fea, src_proj, ref_proj, depth_values)
@@ -169,6 +187,8 @@ class _WarpVariance(torch.autograd.Function):
 
 def warp_variance(fea, proj, depth_values):
     """fea [B,V,32,h,w] (view 0 = reference view) -> variance cost volume [B,32,D,h,w]."""
+    if isinstance(proj, torch.Tensor) and proj.is_cuda and proj.dtype == torch.float32 and proj.dim() == 4:
+        proj = compose_like_reference(proj)
     if torch.is_grad_enabled() and fea.requires_grad:
         return _WarpVariance.apply(fea, proj, depth_values)
     return warp_variance_fwd(fea, proj, depth_values)
@@ -330,7 +350,7 @@ def featurenet_tc(imgs, folded):
 
 
 def warp_variance_cp8(fea, proj, depth_values, half_sums=False):
-    """Fused warp+variance with the bf16 chunk-planar output: returns a bf16 tensor [B, 4, D, h, w, 8]
+    """Fused warp+variance with the 16-bit chunk-planar output: returns an fp16 tensor [B, 4, D, h, w, 8]
     (channel = chunk*8 + last index).  fea: fp32 [B,V,32,h,w] (exact fp32 arithmetic) or fp16 channels-last
     [B,V,h,w,32] (fp16 texels).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
     lib = _lib.load()
@@ -350,7 +370,7 @@ def warp_variance_cp8(fea, proj, depth_values, half_sums=False):
     proj = _prep(proj, "proj_matrices", 4)
     depth_values = _prep(depth_values, "depth_values", 2)
     D = depth_values.shape[1]
-    vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.bfloat16, device=fea.device)
+    vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.float16, device=fea.device)
     ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
     with torch.cuda.device(fea.device):
         extra = (int(half_sums),) if rcp8 else ()

@@ -16,6 +16,11 @@ Fixtures:
   case_b.npz  B=2 V=4 32x64  D=8,  per-sample depth ranges, grayscale imgs -> same stages
   case_bwd.npz  grads of the train-branch variance volume w.r.t. every view's features
   case_default_init.npz  default (uncalibrated) weights at case_a's inputs: depth == mean(depth_values)
+  config_c1.npz / config_c3.npz / config_c2.npz   (python tests/make_golden.py --config-sized)
+              the BASELINE.json shapes C1 (3 views 512x640), C3 (4 views gray 512x640) and C2 (5 views 1152x1600),
+              D=192, inputs = synth.make_named(name, seed=0), calibrated weights: depth, conf, index_f of the
+              unmodified reference's MVSNet.forward, plus the variance volume and the logits at 16 / 256 sampled
+              pixels (all planes) so that the fused kernels are pinned to the reference at full size too.
 """
 import os
 import sys
@@ -80,8 +85,46 @@ def run_stages(ref_mvsnet, ref_module, m, imgs, proj, dv):
     return {k: v.numpy() for k, v in out.items()}
 
 
+def config_sized(names=("c1_3view_512x640", "c3_bin_4view_512x640", "c2_dtu_5view_1152x1600")):
+    """Outputs of the unmodified reference at the BASELINE shapes (CPU; C2 takes ~1 min and ~15 GB)."""
+    import hashlib
+    from scene_3dreconstruction_mvsnet_b200 import synth
+
+    ref_mvsnet, ref_module = import_reference()
+    gold = os.path.join(HERE, "golden")
+    with np.load(os.path.join(gold, "weights_calibrated.npz")) as z:
+        sd = {k: torch.from_numpy(z[k]) for k in z.files}
+    m = ref_mvsnet.MVSNet(refine=False)
+    m.load_state_dict(sd)
+    m.eval()
+    torch.set_num_threads(os.cpu_count())
+    for name in names:
+        imgs, proj, dv = synth.make_named(name, B=1, seed=0)
+        st = run_stages(ref_mvsnet, ref_module, m, imgs, proj, dv)
+        h, w = st["depth"].shape[1:]
+        g = np.random.default_rng(17)
+        pix = np.sort(g.choice(h * w, 256, replace=False))
+        py, px = pix // w, pix % w
+        tag = name.split("_")[0]
+        np.savez_compressed(
+            os.path.join(gold, "config_%s.npz" % tag), name=np.array(name),
+            imgs_sha1=np.array(hashlib.sha1(imgs.numpy().tobytes()).hexdigest()),
+            depth=st["depth"], conf=st["conf"], index_f=st["index_f"],
+            sample_yx=np.stack([py, px], 1).astype(np.int32),
+            logits_samples=st["logits"][0][:, py, px].astype(np.float32),          # [D, 256]
+            variance_samples=st["variance"][0][:, :, py[:16], px[:16]].astype(np.float32),  # [32, D, 16]
+            features_samples=st["features"][0][:, :, py, px].astype(np.float32))   # [V, 32, 256]
+        print("%s: depth [%.1f, %.1f] conf [%.3f, %.3f] logits std %.3g" % (
+            tag, st["depth"].min(), st["depth"].max(), st["conf"].min(), st["conf"].max(), st["logits"].std()),
+            flush=True)
+        del st
+
+
 def main():
     from scene_3dreconstruction_mvsnet_b200 import synth
+
+    if "--config-sized" in sys.argv:
+        return config_sized()
 
     ref_mvsnet, ref_module = import_reference()
     gold = os.path.join(HERE, "golden")

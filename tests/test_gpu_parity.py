@@ -27,6 +27,14 @@ def maxabs(a, b):
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))))
 
 
+def composed(proj):
+    """[B,V,4,4] (numpy or tensor) -> numpy [B,V,4,4]: view 0 = I, view v = proj_v @ inverse(proj_0) by the reference's own
+    torch calls on the device (ops.compose_like_reference).  Idempotent, so feeding it to the CUDA path AND to the
+    oracle (whose float64 composition of H @ inverse(I) is exact) compares both at the same homographies."""
+    t = cu(proj) if not isinstance(proj, torch.Tensor) else proj.to(DEV)
+    return ops.compose_like_reference(t.float()).cpu().numpy()
+
+
 def load_model(weights, precision="fp32"):
     m = MVSNet(refine=False, precision=precision)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
@@ -39,8 +47,9 @@ def test_homo_warping_golden(case, request):
     c = request.getfixturevalue(case)
     out = ops.homo_warping(cu(c["features"][:, 1]), cu(c["proj"][:, 1]), cu(c["proj"][:, 0]), cu(c["dv"]))
     assert out.shape == c["warped_v1"].shape
-    assert maxabs(out, c["warped_v1"]) < 2e-4        # reference (fp32 LAPACK inverse) vs ours (fp64 inverse)
-    ref = orc.homo_warping(c["features"][:, 1], c["proj"][:, 1], c["proj"][:, 0], c["dv"])
+    assert maxabs(out, c["warped_v1"]) < 2e-5        # reference on the CPU (LAPACK inverse) vs ours (torch.inverse on CUDA)
+    pc = composed(c["proj"])
+    ref = orc.homo_warping(c["features"][:, 1], pc[:, 1], pc[:, 0], c["dv"])
     assert maxabs(out, ref) < 2e-6                   # same homography, same op order: fp32 FMA noise only
 
 
@@ -51,7 +60,8 @@ def test_homo_warping_shapes(C, H, W):
     fea = torch.randn(2, C, H, W, generator=g)
     _, proj, dv = synth.make_inputs(B=2, V=2, H=4 * H, W=4 * W, D=6, focal=25.0, interval_scale=30.0, yaw=0.2, seed=W)
     out = ops.homo_warping(fea.to(DEV), proj[:, 1].to(DEV), proj[:, 0].to(DEV), dv.to(DEV))
-    ref = orc.homo_warping(fea.numpy(), proj[:, 1].numpy(), proj[:, 0].numpy(), dv.numpy())
+    pc = composed(proj)
+    ref = orc.homo_warping(fea.numpy(), pc[:, 1], pc[:, 0], dv.numpy())
     assert maxabs(out, ref) < 5e-6
     assert (ref == 0).mean() > 0.02
 
@@ -74,8 +84,8 @@ def test_homo_warping_behind_camera_is_zero():
 def test_warp_variance_golden(case, request):
     c = request.getfixturevalue(case)
     var = ops.warp_variance(cu(c["features"]), cu(c["proj"]), cu(c["dv"]))
-    assert maxabs(var, c["variance"]) < 2e-4
-    assert maxabs(var, orc.warp_variance(c["features"], c["proj"], c["dv"])) < 5e-6
+    assert maxabs(var, c["variance"]) < 2e-5
+    assert maxabs(var, orc.warp_variance(c["features"], composed(c["proj"]), c["dv"])) < 5e-6
 
 
 @pytest.mark.parametrize("B,V,h,w,D", [(1, 5, 24, 40, 16), (2, 2, 9, 33, 5), (1, 1, 8, 32, 4), (1, 3, 40, 100, 24)])
@@ -83,7 +93,7 @@ def test_warp_variance_oracle(B, V, h, w, D):
     fea = synth.make_features(B, V, 32, h, w, seed=V)
     _, proj, dv = synth.make_inputs(B=B, V=V, H=4 * h, W=4 * w, D=D, focal=0.9 * w, interval_scale=8.0, yaw=0.04, seed=D)
     var = ops.warp_variance(fea.to(DEV), proj.to(DEV), dv.to(DEV))
-    ref = orc.warp_variance(fea.numpy(), proj.numpy(), dv.numpy())
+    ref = orc.warp_variance(fea.numpy(), composed(proj), dv.numpy())
     assert maxabs(var, ref) < 2e-5
     if V == 1:
         assert float(var.abs().max()) < 1e-6  # variance of a single view
@@ -114,11 +124,11 @@ def test_warp_variance_backward_golden(case_bwd):
     c = case_bwd
     fea = cu(c["fea"]).requires_grad_(True)
     var = ops.warp_variance(fea, cu(c["proj"]), cu(c["dv"]))
-    assert maxabs(var, c["variance"]) < 2e-4
+    assert maxabs(var, c["variance"]) < 2e-5
     var.backward(cu(c["grad_var"]))
     scale = float(np.abs(c["grad_fea"]).max())
-    assert maxabs(fea.grad, c["grad_fea"]) < 2e-4 * scale        # vs autograd through the reference
-    ref = orc.warp_variance_bwd(c["grad_var"], c["fea"], c["proj"], c["dv"])
+    assert maxabs(fea.grad, c["grad_fea"]) < 2e-5 * scale        # vs autograd through the reference
+    ref = orc.warp_variance_bwd(c["grad_var"], c["fea"], composed(c["proj"]), c["dv"])
     assert maxabs(fea.grad, ref) < 2e-5 * scale                  # vs the oracle (atomics: order noise only)
 
 
@@ -351,5 +361,5 @@ def test_c3_four_view_grayscale_full_size(weights):
         b = load_model(weights, "bf16")(imgs, proj, dv)
     rng = float(dv.max() - dv.min())
     assert a["depth"].shape == (1, 128, 160)
-    assert maxabs(a["depth"], b["depth"]) < 2e-2 * rng
-    assert float((a["depth"] - b["depth"]).abs().mean()) < 2e-3 * rng
+    assert maxabs(a["depth"], b["depth"]) < 5e-3 * rng             # the one tolerance stated for the tensor-core mode
+    assert float((a["depth"] - b["depth"]).abs().mean()) < 5e-4 * rng

@@ -1,10 +1,11 @@
-"""GPU parity of the tcgen05 (bf16 operand) CostRegNet path against the oracle.
+"""GPU parity of the tcgen05 CostRegNet / FeatureNet path against the oracle.
 
-Tolerance (stated separately from the fp32 path, as north_star allows): operands are rounded to bf16
-(8-bit mantissa), accumulation is fp32.  Per layer the oracle is evaluated on the SAME bf16-rounded inputs
-and weights, so the remaining difference is accumulation order plus the bf16 rounding of the stored output:
-|y - ref| <= 2^-8 |ref| + 2e-3.  End to end (11 layers) logits are compared at 3e-2 absolute on logits of
-std ~0.5, and the depth map at 5e-3 x depth range."""
+Tolerance (stated separately from the fp32 path, as north_star allows): operands are rounded to fp16
+(11-bit significand; bf16 until round 2), accumulation is fp32.  Per layer the oracle is evaluated on the SAME
+fp16-rounded inputs and weights, so the remaining difference is accumulation order plus the fp16 rounding of the
+stored output: |y - ref| <= 2^-10 |ref| + 2.5e-4.  End to end (11 layers) logits are compared at LOGITS_TOL absolute
+on logits of std ~0.5, and the depth map at 5e-3 x depth range (tests/test_gpu_config_goldens.py holds the same bar
+at the BASELINE shapes, confidence included)."""
 import numpy as np
 import pytest
 import torch
@@ -16,14 +17,18 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+LOGITS_TOL = 1e-2
+
+
 def bf16_round(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+    """Rounds to the 16-bit storage format of the tensor-core path (fp16 since round 2; the name is historical)."""
+    return t.to(torch.float16).to(torch.float32)
 
 
 def check(y, ref, what):
     y = y.cpu().numpy().astype(np.float64)
     err = np.abs(y - ref)
-    tol = np.abs(ref) * 2.0 ** -8 + 2e-3
+    tol = np.abs(ref) * 2.0 ** -10 + 2.5e-4
     bad = err > tol
     assert not bad.any(), "%s: %d/%d outside tolerance, max err %.4g at %s (ref %.4g got %.4g)" % (
         what, bad.sum(), bad.size, err.max(), np.unravel_index(err.argmax(), err.shape), ref.flat[err.argmax()],
@@ -170,7 +175,7 @@ def test_tc_costreg_and_depth_golden(case, precision, request, weights):
     c = request.getfixturevalue(case)
     m = load_model(weights, precision=precision)
     logits = m.cost_regularization.infer(cu(c["variance"]), "bf16")
-    assert maxabs(logits, c["logits"]) < 3e-2
+    assert maxabs(logits, c["logits"]) < LOGITS_TOL
     with torch.no_grad():
         out = m(cu(c["imgs"]), cu(c["proj"]), cu(c["dv"]))
     rng = float(c["dv"].max() - c["dv"].min())
@@ -305,8 +310,8 @@ def test_full_size_c2_forward_properties(weights):
     c = a["photometric_confidence"]
     assert float(c.min()) >= 0 and float(c.max()) <= 1 + 1e-5
     rng = float(dv.max() - dv.min())
-    assert float((a["depth"] - s["depth"]).abs().mean()) < 2e-3 * rng
-    assert float((a["depth"] - s["depth"]).abs().max()) < 2e-2 * rng
+    assert float((a["depth"] - s["depth"]).abs().mean()) < 5e-4 * rng
+    assert float((a["depth"] - s["depth"]).abs().max()) < 5e-3 * rng   # the one tolerance stated for this mode
 
 
 def test_packed_weight_cache_follows_weight_changes(weights):

@@ -22,13 +22,24 @@ for case in ("case_a.npz", "case_b.npz"):
         e = np.abs(o["depth"].cpu().numpy() - c["depth"])
         ce = np.abs(o["photometric_confidence"].cpu().numpy() - c["conf"])
         print("%s %-5s depth err / range: max %.2e mean %.2e | conf abs err: max %.2e mean %.2e" % (case[:6], p, e.max() / rng, e.mean() / rng, ce.max(), ce.mean()))
+del ms["fast"]
 imgs, proj, dv = synth.make_named("c1_3view_512x640")
 imgs, proj, dv = imgs.cuda(), proj.cuda(), dv.cuda()
 rng = float(dv.max() - dv.min())
 with torch.no_grad():
     ref = ms["fp32"](imgs, proj, dv)
-    for p in ("bf16", "fast"):
+    for p in ("bf16",):
         o = ms[p](imgs, proj, dv)
         e = (o["depth"] - ref["depth"]).abs()
         ce = (o["photometric_confidence"] - ref["photometric_confidence"]).abs()
         print("C1 full size, %-5s vs fp32 mode: depth err / range max %.2e mean %.2e | conf abs err max %.2e mean %.2e" % (p, e.max().item() / rng, e.mean().item() / rng, ce.max().item(), ce.mean().item()))
+
+# ---- BASELINE.json shapes against the unmodified reference's outputs (tests/golden/config_*.npz)
+import json
+from test_gpu_config_goldens import TAGS, measure
+print("\nconfig-sized goldens (reference outputs at C1 / C3 / C2):")
+for tag in TAGS:
+    for p in ("fp32", "bf16"):
+        torch.cuda.empty_cache()
+        r = measure(tag, w, p)
+        print(tag, p, json.dumps({k: float("%.3g" % v) for k, v in r.items()}), flush=True)
