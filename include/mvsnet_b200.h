@@ -16,9 +16,9 @@
  *   - Inputs are borrowed and never written.  Outputs/workspaces are caller-allocated.
  *   - Every function returns MVS_OK (0) or a negative mvs_status; mvs_last_error() gives the
  *     message for the calling thread.  Nothing aborts the process.  There is no CPU fallback.
- *   - Re-entrant: no global mutable state except an atomic launch counter; safe to call from
- *     several host threads on several devices (nn.DataParallel calls the reference's forward
- *     from one thread per device, train.py:125).
+ *   - Re-entrant: safe to call from several host threads on several devices (nn.DataParallel calls the
+ *     reference's forward from one thread per device, train.py:125).  Global state: an atomic launch counter and
+ *     the mutex-protected packed-weight / launch-plan cache of the tensor-core layers (mvs_weight_cache_clear).
  */
 #ifndef MVSNET_B200_H
 #define MVSNET_B200_H
@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MVSNET_B200_ABI_VERSION 1
+#define MVSNET_B200_ABI_VERSION 2
 
 typedef enum {
     MVS_OK = 0,
@@ -40,8 +40,8 @@ typedef enum {
 } mvs_status;
 
 /* Precision of the CostRegNet contraction.  FP32 = CUDA-core fp32 FMA, matches the reference to
- * fp32 rounding.  BF16 = tcgen05 tensor-core implicit GEMM with bf16 operands, fp32 accumulate
- * (looser, separately stated tolerance). */
+ * fp32 rounding.  BF16 (the name is historical) = tcgen05 tensor-core implicit GEMM with 16-bit operands -- fp16
+ * since ABI 2, activations saturating at 65504 -- and fp32 accumulation (looser, separately stated tolerance). */
 typedef enum { MVS_PRECISION_FP32 = 0, MVS_PRECISION_BF16 = 1 } mvs_precision;
 
 int mvs_abi_version(void);
@@ -93,7 +93,7 @@ int mvs_conv3d_bn_relu(const float *x, const float *w, const float *shift, int r
 int mvs_conv_transpose3d_bn_relu(const float *x, const float *w, const float *shift, int relu, const float *skip,
                                  float *y, int B, int Cin, int Cout, int D, int H, int W, void *stream);
 
-/* Tensor-core variants of the two building blocks (tcgen05 implicit GEMM, bf16 operands, fp32
+/* Tensor-core variants of the two building blocks (tcgen05 implicit GEMM, fp16 operands, fp32
  * accumulate; same fp32 NCDHW interface, converted internally).  Cin % 8 == 0, Cout % 8 == 0 or 1. */
 int mvs_conv3d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin,
                           int Cout, int D, int H, int W, int stride, void *stream);
@@ -121,7 +121,7 @@ size_t mvs_costreg_workspace_bytes(int B, int D, int H, int W, int precision);
 int mvs_costreg_fwd(const float *volume, const mvs_costreg_params *params, float *logits, void *workspace, int B,
                     int D, int H, int W, int precision, void *stream);
 
-/* bf16 precision mode, fused layout: the warp+variance kernel writes the cost volume directly as bf16
+/* tensor-core precision mode, fused layout: the warp+variance kernel writes the cost volume directly as fp16
  * "CP8" [B][32/8][D][H][W][8] (mvs_volume_cp8_bytes bytes), which mvs_costreg_fwd_cp8 consumes on the
  * tensor cores -- the fp32 volume and its conversion pass never exist.  Workspaces as for the fp32 calls
  * (mvs_warp_variance_workspace_bytes / mvs_costreg_workspace_bytes with MVS_PRECISION_BF16). */
@@ -161,11 +161,10 @@ int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, in
                           int H, int W, int ksize, int stride, int s2d_out, void *stream);
 /* Fused warp+variance on features in the layout mvs_featurenet_tc_fwd produces: fea [B*V][H][4][W][8] fp16 with
  * image index n = b*V + v (view 0 = reference view).  workspace: mvs_warp_variance_workspace_bytes().
- * half_sums = 0: fp32 running sums of the warped values (|var - ref| <= 2^-7 |ref| + 8e-3 on N(0,1) features);
- * half_sums = 1: packed-half sums of the deviations from the reference view (7 % faster; variances >> 1, i.e.
- * mismatched voxels, can be off by up to 2^-6 relative). */
+ * fp16 texels, packed-half interpolation and packed-half sums of the deviations from the reference view; the fp16
+ * volume saturates at 65504 (|feature| up to ~250).  |var - ref| <= 2^-6 |ref| + 8e-3 on N(0,1) features. */
 int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const float *proj, const float *depth_values, void *vol_cp8,
-                                   void *workspace, int B, int V, int C, int D, int H, int W, int half_sums, void *stream);
+                                   void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
 
 /* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
  *                                                        models/mvsnet.py:192-193,204,214-218

@@ -55,7 +55,7 @@ SIGNATURES = {
     "mvs_volume_cp8_bytes": (ctypes.c_size_t, [_i] * 4),
     "mvs_warp_variance_fwd_cp8": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_warp_variance_fwd_cp8_f16": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
-    "mvs_warp_variance_fwd_cp8_feat": (_i, [_c_float_p] * 5 + [_i] * 7 + [ctypes.c_void_p]),
+    "mvs_warp_variance_fwd_cp8_feat": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_featurenet_tc_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "mvs_featurenet_tc_fwd": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
                               [ctypes.c_void_p]),
@@ -92,7 +92,7 @@ def load():
                 fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
                 fn.restype = res
                 fn.argtypes = args
-            if lib.mvs_abi_version() != 1:
+            if lib.mvs_abi_version() != 2:
                 raise RuntimeError("libmvsnet_b200.so ABI version mismatch")
             _lib = lib
     return _lib

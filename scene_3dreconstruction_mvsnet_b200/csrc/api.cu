@@ -31,7 +31,7 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
                       int B, int V, int D, int H, int W, cudaStream_t st);
 size_t costreg_tc_workspace_bytes(int B, int D, int H, int W);
 int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
-                           int B, int V, int D, int H, int W, int half_sums, cudaStream_t st);
+                           int B, int V, int D, int H, int W, cudaStream_t st);
 int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                           int B, int V, int D, int H, int W, cudaStream_t st);
 
@@ -136,13 +136,13 @@ extern "C" int mvs_warp_variance_fwd_cp8_f16(const void *fea16_nhwc, const float
 
 extern "C" int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const float *proj, const float *depth_values,
                                               void *vol_cp8, void *workspace, int B, int V, int C, int D, int H, int W,
-                                              int half_sums, void *stream) {
+                                              void *stream) {
     MVS_REQUIRE(fea_rcp8_f16 && proj && depth_values && vol_cp8 && workspace, "null pointer argument");
     MVS_REQUIRE(C == 32, "warp_variance: C must be 32, got %d", C);
     MVS_REQUIRE(B > 0 && V >= 1 && V <= 64 && D > 0 && H > 1 && W > 1, "bad shape");
     MVS_REQUIRE((long long)B * D <= 65535LL * 16 && (long long)H * W < (1LL << 27), "shape too large");
     MVS_REQUIRE(((uintptr_t)fea_rcp8_f16 & 15) == 0, "features must be 16-byte aligned");
-    return warp_variance_cp8_rcp8(fea_rcp8_f16, proj, depth_values, vol_cp8, workspace, B, V, D, H, W, half_sums, (cudaStream_t)stream);
+    return warp_variance_cp8_rcp8(fea_rcp8_f16, proj, depth_values, vol_cp8, workspace, B, V, D, H, W, (cudaStream_t)stream);
 }
 
 extern "C" int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *p, float *logits, void *workspace,

@@ -763,10 +763,10 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
     return MVS_OK;
 }
 
-// Internal: same op, output written as bf16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
+// Internal: same op, output written as fp16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
 namespace mvs {
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, int half_sums, cudaStream_t st);
+                          int H, int W, cudaStream_t st);
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st);
 int features_nhwc16_to_rcp8(const void *fea16, void *tex16, int N, int H, int W, cudaStream_t st);
 // fp32 NCHW features in: one layout pass to fp16 RCP8 texels (all V views), then the TMA-window kernel
@@ -779,16 +779,16 @@ int warp_variance_cp8(const float *fea, const float *proj, const float *depth_va
     if (nsrc > 0)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
     if (int rc = features_nchw_to_rcp8(fea, tex16, B * V, H, W, st)) return rc;
-    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
 }
 
 // fp16 RCP8 features of all V views in ([B*V][H][4][W][8], what the tensor-core FeatureNet writes): no layout pass.
 int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
-                           int B, int V, int D, int H, int W, int half_sums, cudaStream_t st) {
+                           int B, int V, int D, int H, int W, cudaStream_t st) {
     float *rt = (float *)workspace;
     if (V > 1)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, half_sums, st);
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
 }
 
 // fp16 channels-last features of all V views in ([B][V][H*W][32], what a half-precision cuDNN FeatureNet emits)
@@ -800,7 +800,7 @@ int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *dep
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
     void *tex16 = (char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float));
     if (int rc = features_nhwc16_to_rcp8(fea16, tex16, B * V, H, W, st)) return rc;
-    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, 0, st);
+    return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
 }
 }  // namespace mvs
 

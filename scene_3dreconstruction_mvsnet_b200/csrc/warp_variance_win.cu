@@ -1,35 +1,39 @@
-// Fused plane-sweep warp + variance, third generation: TMA-staged source WINDOWS in shared memory.
+// Fused plane-sweep warp + variance, fourth generation: TMA-staged source WINDOWS in shared memory, 16x8 pixel tiles,
+// window shape chosen per segment, packed-half deviation sums, fp16 volume out.
 //
-// Replaces, for the reference (olivier-2018/scene_3Dreconstruction_MVSNet), in the tensor-core precision modes:
+// Replaces, for the reference (olivier-2018/scene_3Dreconstruction_MVSNet), in the tensor-core precision mode:
 //   models/module.py:96-139   homo_warping  (grid construction + F.grid_sample, bilinear, zero padding)
 //   models/mvsnet.py:145-177  running sum / sum of squares over views and the variance
 //
-// Why (ncu on the second generation, profiles/r01e): ~120 instructions per (pixel, view, 8 channels) of which only 32
-// are arithmetic -- the rest is tap clamping and masking, 64-bit address arithmetic for 16 global loads, the smem
-// exchange of coordinates between the lane that computes them and the lanes that gather, and L2-latency stalls at 16
-// warps per SM.  This version removes those instead of hiding them:
-//   * Features of ALL views are stored as fp16 "RCP8" [n][y][chunk 0..3][x][8 ch]: a row of one 8-channel chunk is
-//     contiguous, so a TMA box over (x, chunk, y) lands in shared memory as [row][chunk][col][16 B].
-//   * A CTA owns a TW x TH pixel tile and a chunk of depth planes.  For a run ("segment") of planes, one elected warp
-//     bounds the source footprint of the tile in every source view from the 8 corners of (tile x depth range) -- the
-//     map (x*d, y*d, d) -> (u, v) is projective, so the corners' bounding box contains every sample while q_z > 0 --
-//     and one thread issues one TMA box per view at that origin.  TMA zero-fills outside the image, which IS
-//     grid_sample's padding_mode='zeros': no clamping, no validity masks.
-//   * Thread = pixel, all 32 channels: coordinates are computed by the thread that uses them (no exchange), the 16
-//     16-byte tap loads of a (pixel, view, plane) are LDS.128 at compile-time offsets from ONE 32-bit address, lanes of
-//     a warp read consecutive 16-byte columns (conflict-free), Sum / Sum^2 of 32 channels live in 64 registers and the
-//     bf16 CP8 output row is written with fully coalesced 16-byte stores.
-//   * Generality: if the footprint of a segment does not fit the window, the segment is halved; a single plane that
-//     still does not fit (extreme zoom, q_z <= 0 inside the tile, depth <= 0) takes a per-tap global gather with
-//     explicit clamps for that view -- slow, exact, never taken on camera-like geometry.  Every sample also checks that
-//     its 2x2 footprint is inside the window (memory safety for non-finite coordinates).
-// HBM traffic stays the algorithmic minimum (features once, volume once); the window fill is L2 -> smem traffic.
+// Structure (what survives from generation 3):
+//   * Features of ALL views are fp16 "RCP8" [n][y][chunk 0..3][x][8 ch]: a TMA box over (x, chunk, y) lands in shared
+//     memory as [row][chunk][col][16 B]; TMA zero-fills outside the image, which IS grid_sample's padding_mode='zeros'.
+//   * A CTA owns a pixel tile and a run of depth planes.  For a "segment" of planes one warp bounds the tile's footprint
+//     in every source view from the 8 corners of (tile x depth range) -- the map (x*d, y*d, d) -> (u, v) is projective, so
+//     the corners' bounding box contains every sample while q_z > 0 -- and issues one TMA box per view.
+//   * Thread = pixel x 32 channels; 16 LDS.128 tap loads per (pixel, view, plane) from ONE address.
+// What changed (round 2; measured reasons in profiles/r02_warp_kernel.md):
+//   * Tile 16 x 8 instead of 32 x 8, two plane phases per CTA (threads 0-127 take the even planes of the segment, 128-255
+//     the odd ones, same windows).  The footprint of a 32-wide tile under a 10 degree roll is 16 rows -- it never fitted the
+//     11-row windows, every plane fell back to per-tap global gathers and DTU-like (rotated) cameras ran 2.6x slower than
+//     rectified ones (2.84 vs 1.08 ms).  A 16-wide tile's footprint is 28 x 13 at 10 degrees.
+//   * Three window shapes of the same size (wide / medium / tall), one tensor map each; the planner picks, per segment, the
+//     first shape that holds the footprint of every view for the longest run of planes.
+//   * Projection hoisted: per (pixel, view) a = R.(x, y, 1) lives in registers, a plane costs q = a*d + t (3 FMA), one
+//     reciprocal and 2 FMA that land directly in window coordinates; clamping to the window replaces the bounds test.
+//   * Running sums over the DEVIATION from the reference view (the variance is shift invariant) in packed half: the
+//     interpolation chain starts from -x_ref, so the subtraction is free, and Sum d / Sum d^2 cost 2 HFMA2 per channel pair
+//     and view.  The variance itself is formed in packed half as well and IS the fp16 volume element: no conversions.
+//     On B200 HFMA2 issues at 0.5 / clk / scheduler and shares its pipe with every fp32 FMA (tools/pipe_microbench.cu),
+//     so the 96 packed-half operations per (pixel, view, plane) -- 64 interpolation, 32 sums -- are one floor of this
+//     formulation (0.46 ms at the DTU shape), the 256 bytes of LDS per (pixel, view, plane) the other (0.61 ms).
+// Generality: a segment whose footprint fits no shape is halved; a single plane that still does not fit (extreme zoom,
+// q_z <= 0 inside the tile, depth <= 0), or more source views than windows, takes a per-tap global gather with explicit
+// clamps -- slow, exact.
 #include <cuda.h>
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -40,7 +44,19 @@ namespace mvs {
 
 namespace {
 
+static_assert(kActF16, "the fused warp kernel writes the variance as packed half: the 16-bit volume format must be fp16");
+
 constexpr int kC = 32;
+constexpr int TW = 16, TH = 8;         // pixel tile
+constexpr int kPhase = 2;              // plane phases per CTA
+constexpr int kThreads = TW * TH * kPhase;
+constexpr int kMaxWin = 8;             // source views that can have a window
+constexpr int kShapes = 3;
+constexpr int kMaxSeg = 32;            // planes per segment (and per CTA)
+
+struct WinShapes {
+    int wx[kShapes], wy[kShapes];
+};
 
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
@@ -48,55 +64,28 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// shared-memory loads the compiler must leave where they are written (hoisting the per-view constants of all views out
+// of the plane loop costs 32 registers and spills the accumulators)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ __half2 as_half2(uint32_t u) { return *reinterpret_cast<const __half2 *>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<const uint32_t *>(&h); }
 
-// ix = px * W/(W-1) - 0.5 is module.py:130-131 composed with grid_sample's align_corners=False un-normalisation
-// (closed form of the reference's chain; differs from it by ~1e-7 relative, far below the fp16 texel quantisation).
-struct Coord {
-    float ix, iy;
-};
-__device__ __forceinline__ Coord project(const float4 c0, const float4 c1, const float4 c2, float xf, float yf, float dep,
-                                         float sx, float sy) {
-    const float rx = fmaf(c0.x, xf, fmaf(c0.y, yf, c0.z));
-    const float ry = fmaf(c1.x, xf, fmaf(c1.y, yf, c1.z));
-    const float rz = fmaf(c2.x, xf, fmaf(c2.y, yf, c2.z));
-    const float qx = fmaf(rx, dep, c0.w), qy = fmaf(ry, dep, c1.w), qz = fmaf(rz, dep, c2.w);
-    const float iz = rcp_approx(qz);
-    Coord c;
-    c.ix = fmaf(qx * iz, sx, -0.5f);
-    c.iy = fmaf(qy * iz, sy, -0.5f);
-    return c;
-}
-
-// one 8-channel chunk of one (pixel, view): 4 taps -> packed-half interpolation -> fp32 Sum / Sum^2
+// one 8-channel chunk of one (pixel, view): 4 taps, interpolation chain seeded with -x_ref, deviation sums.
+// FIRST: the first source view of a plane initialises the sums (no zeroing, no adds).
+template <bool FIRST>
 __device__ __forceinline__ void accumulate_chunk(const uint4 a, const uint4 b, const uint4 c, const uint4 d, const __half2 h00,
-                                                 const __half2 h01, const __half2 h10, const __half2 h11, float2 *S,
-                                                 float2 *Q) {
-    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
-    const uint32_t wc[4] = {c.x, c.y, c.z, c.w}, wd[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const __half2 vh =
-            __hfma2(as_half2(wd[j]), h11, __hfma2(as_half2(wc[j]), h10, __hfma2(as_half2(wb[j]), h01, __hmul2(as_half2(wa[j]), h00))));
-        // mixed-precision accumulate (FHADD / FHFMA: fp32 += f16, fp32 += f16 * f16, the half taken from either half of the
-        // register): no conversion instructions, same results as convert + fp32 add / fma (f16 -> f32 is exact)
-        const unsigned short lo = __half_as_ushort(__low2half(vh)), hi = __half_as_ushort(__high2half(vh));
-        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(S[j].x) : "h"(lo));
-        asm("add.rn.f32.f16 %0, %1, %0;" : "+f"(S[j].y) : "h"(hi));
-        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(Q[j].x) : "h"(lo));
-        asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(Q[j].y) : "h"(hi));
-    }
-}
-
-// Deviation form (HACC): the variance is shift invariant, so the running sums are kept over d = x_v - x_ref (zero for
-// the reference view itself) instead of x_v.  The subtraction is free -- the interpolation chain starts from -x_ref --
-// and the deviations are small exactly where the cost volume matters (matching pixels), so Sum d and Sum d^2 can stay
-// in packed half: 24 heavy-pipe instructions per 8 channels instead of 32 and one conversion per plane instead of one
-// per view.  Relative error of the sums 2^-11, the same class as the fp16 interpolation itself; |d| must stay below
-// 255 / sqrt(V-1) for d^2 not to overflow fp16 (features are O(1)).
-__device__ __forceinline__ void accumulate_chunk_dev(const uint4 a, const uint4 b, const uint4 c, const uint4 d, const __half2 h00,
-                                                     const __half2 h01, const __half2 h10, const __half2 h11,
-                                                     const uint4 nref, __half2 *S, __half2 *Q) {
+                                                 const __half2 h01, const __half2 h10, const __half2 h11, const uint4 nref,
+                                                 __half2 *S, __half2 *Q) {
     const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
     const uint32_t wc[4] = {c.x, c.y, c.z, c.w}, wd[4] = {d.x, d.y, d.z, d.w};
     const uint32_t wr[4] = {nref.x, nref.y, nref.z, nref.w};  // -x_ref
@@ -104,9 +93,36 @@ __device__ __forceinline__ void accumulate_chunk_dev(const uint4 a, const uint4 
     for (int j = 0; j < 4; ++j) {
         const __half2 dv = __hfma2(as_half2(wd[j]), h11,
                                    __hfma2(as_half2(wc[j]), h10, __hfma2(as_half2(wb[j]), h01, __hfma2(as_half2(wa[j]), h00, as_half2(wr[j])))));
-        S[j] = __hadd2(S[j], dv);
-        Q[j] = __hfma2(dv, dv, Q[j]);
+        if constexpr (FIRST) {
+            S[j] = dv;
+            Q[j] = __hmul2(dv, dv);
+        } else {
+            S[j] = __hadd2(S[j], dv);
+            Q[j] = __hfma2(dv, dv, Q[j]);
+        }
     }
+}
+
+// bilinear weights of (bx, by) in [0, 1): fp32 products, rounded once to half, each broadcast to both halves
+__device__ __forceinline__ void tap_weights(float bx, float by, __half2 &h00, __half2 &h01, __half2 &h10, __half2 &h11) {
+    const float w11 = bx * by;
+    const float w10 = by - w11, w01 = bx - w11;
+    const float w00 = (1.0f - bx) - w10;
+    h00 = __float2half2_rn(w00);
+    h01 = __float2half2_rn(w01);
+    h10 = __float2half2_rn(w10);
+    h11 = __float2half2_rn(w11);
+}
+
+// variance of the V views from the deviation sums, packed half, saturated: (Q - S*(S/V)) / V     (mvsnet.py:177)
+__device__ __forceinline__ uint32_t variance_f16x2(__half2 S, __half2 Q, __half2 invV) {
+    const __half2 t = __hmul2(S, invV);
+    const __half2 u = __hfma2(__hneg2(t), S, Q);   // the cancellation happens inside one fused operation
+    __half2 r = __hmul2(u, invV);
+    // inf / NaN (|deviation| > 255: sum of squares beyond fp16) -> largest finite value; -0 / tiny negatives -> 0
+    r = __hmin2(r, __float2half2_rn(65504.f));
+    r = __hmax2(r, __float2half2_rn(0.f));
+    return as_u32(r);
 }
 
 // fp32 NCHW [B,V,32,HW] -> fp16 RCP8 [B*V][H][4][W][8]; one thread per output 16-byte chunk
@@ -126,8 +142,7 @@ __global__ void nchw_to_rcp8_kernel(const float *__restrict__ in, uint4 *__restr
     for (int j = 0; j < 4; ++j) {
         const float lo = fminf(fmaxf(__ldg(src + (size_t)(2 * j) * HW), -65504.f), 65504.f);
         const float hi = fminf(fmaxf(__ldg(src + (size_t)(2 * j + 1) * HW), -65504.f), 65504.f);
-        const __half2 h = __floats2half2_rn(lo, hi);
-        w[j] = *reinterpret_cast<const uint32_t *>(&h);
+        w[j] = as_u32(__floats2half2_rn(lo, hi));
     }
     out[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -142,81 +157,152 @@ __global__ void nhwc16_to_rcp8_kernel(const uint4 *__restrict__ in, uint4 *__res
     out[i] = __ldg(in + ((r >> 2) * W + x) * 4 + c);
 }
 
+// per segment and source view, written by the planner warp
+struct SegView {
+    float cx, cy;    // window coordinate = q.xy / q.z (scaled) + c:  c = -0.5 - window origin
+    float hix, hiy;  // samples are clamped to [0, hi]: the planner guarantees every in-image sample is inside already
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// grid = (ceil(W / TW), ceil(H / TH), B * ceil(D / dchunk)), block = 32 * TWW * TH threads (warp = 32 consecutive x of a row)
-// dynamic smem: nwin windows of WY rows x [4 chunks][WX cols] x 16 B | homographies | window origins | depths | mbarrier
+// grid = (ceil(W / 16), ceil(H / 8), B * ceil(D / dchunk)), block = 256 threads:
+//   thread t: plane phase t >> 7; a warp = a 16 x 2 pixel strip of the tile, lanes laid out per CTA (see "Lane -> pixel")
+// dynamic smem: nwin windows of win_bytes | per-view constants | segment table | depths | mbarrier
+// NSRC > 0: number of source views known at compile time (view loop unrolled, a = R.(x,y,1) in registers);
+// NSRC = 0: any number of views (a recomputed from shared memory per plane).
 // ------------------------------------------------------------------------------------------------
-template <int TWW, int TH, int WX, bool HACC>
-__global__ void __launch_bounds__(32 * TWW * TH, (TWW * TH <= 8) ? 2 : 1)
-warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 RCP8 features, all views
-                         const uint4 *__restrict__ tex,                  // the same memory
-                         const float *__restrict__ rt,                   // [B*nsrc][12] rot(9) | trans(3)
-                         const float *__restrict__ depth_values,         // [B,D]
-                         uint4 *__restrict__ out,                        // bf16 CP8 [B,4,D,H,W,8]
-                         int V, int nsrc, int nwin, int D, int H, int W, int dchunk, int WY) {
+template <int NSRC>
+__global__ void __launch_bounds__(kThreads, 2)
+warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                         const __grid_constant__ CUtensorMap tmap2,
+                         const uint4 *__restrict__ tex,           // fp16 RCP8 features, all views (the maps' memory)
+                         const float *__restrict__ rt,            // [B*nsrc][12] rot(9) | trans(3)
+                         const float *__restrict__ depth_values,  // [B,D]
+                         uint4 *__restrict__ out,                 // fp16 CP8 [B,4,D,H,W,8]
+                         int V, int nsrc_rt, int nwin, int D, int H, int W, int dchunk, const WinShapes shp, uint32_t win_bytes) {
     // the next kernel (conv0, launched with programmatic stream serialization) may start its set-up on SMs this grid has left
     ptx::pdl_launch_dependents();
-    ptx::pdl_wait();  // launched with programmatic stream serialization: homographies and features are read below
-    constexpr int TW = 32 * TWW;
-    constexpr int ROWQ = 4 * WX;     // uint4 per window row
-    constexpr int ROWB = ROWQ * 16;  // bytes per window row
+    ptx::pdl_wait();  // homographies and features are read below
+    const int nsrc = NSRC > 0 ? NSRC : nsrc_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t win_bytes = (uint32_t)WY * ROWB;
     unsigned char *sp = smem_raw + (size_t)nwin * win_bytes;
-    float4 *s_rt = reinterpret_cast<float4 *>(sp);  // [nsrc][3]: (r0 r1 r2 t) per output coordinate
+    float4 *s_rt = reinterpret_cast<float4 *>(sp);  // [nsrc][3]: (r0 r1 r2 t) per output coordinate, x / y rows pre-scaled
     sp += (size_t)nsrc * 48;
-    int2 *s_org = reinterpret_cast<int2 *>(sp);  // [nwin] window origin (texel column / row of window element 0)
-    sp += (size_t)nwin * 8;
-    int *s_mode = reinterpret_cast<int *>(sp);  // [nwin] 0 = window, 1 = global gather (this segment)
-    sp += (size_t)nwin * 4;
+    SegView *s_sv = reinterpret_cast<SegView *>(sp);  // [nsrc]
+    sp += (size_t)nsrc * 16;
+    float4 *s_tv = reinterpret_cast<float4 *>(sp);  // [nsrc]: translation (x / y scaled) of each view
+    sp += (size_t)nsrc * 16;
     float *s_dep = reinterpret_cast<float *>(sp);  // [dchunk]
     sp += (size_t)dchunk * 4;
     sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(sp);
-    int *s_seg = reinterpret_cast<int *>(sp + 8);  // [0] = planes in the current segment
+    int *s_seg = reinterpret_cast<int *>(sp + 8);  // [0] planes in the current segment, [1] window shape or -1 (gather)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int phase = tid >> 7;
     const int nchunks = (D + dchunk - 1) / dchunk;
     const int b = blockIdx.z / nchunks;
     const int d_begin = (blockIdx.z % nchunks) * dchunk;
     const int d_end = min(D, d_begin + dchunk);
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const int x = tx0 + (warp % TWW) * 32 + lane, y = ty0 + warp / TWW;
-    const bool live = (x < W) & (y < H);
-    const float xf = (float)x, yf = (float)y;
+    // ix = px * W/(W-1) - 0.5 is module.py:130-131 composed with grid_sample's align_corners=False un-normalisation
     const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
-    const float xmax = (float)(W + 1), ymax = (float)(H + 1);
-    const float2 invV2 = make_float2(1.0f / (float)V, 1.0f / (float)V);
     const uint32_t bar = ptx::smem_u32(s_bar);
+    const uint32_t win0 = ptx::smem_u32(smem_raw);
+    const uint32_t sv0 = ptx::smem_u32(s_sv), tv0 = ptx::smem_u32(s_tv);
 
-    for (int i = tid; i < nsrc * 3; i += blockDim.x) {
+    for (int i = tid; i < nsrc * 3; i += kThreads) {
         const float *r = rt + (size_t)(b * nsrc + i / 3) * 12;
         const int k = i % 3;
-        s_rt[i] = make_float4(r[3 * k], r[3 * k + 1], r[3 * k + 2], r[9 + k]);
+        const float s = k == 0 ? sx : (k == 1 ? sy : 1.0f);
+        s_rt[i] = make_float4(r[3 * k] * s, r[3 * k + 1] * s, r[3 * k + 2] * s, r[9 + k] * s);
     }
-    for (int i = tid; i < d_end - d_begin; i += blockDim.x) s_dep[i] = __ldg(depth_values + (size_t)b * D + d_begin + i);
+    for (int i = tid; i < nsrc; i += kThreads) {
+        const float *r = rt + (size_t)(b * nsrc + i) * 12;
+        s_tv[i] = make_float4(r[9] * sx, r[10] * sy, r[11], 0.f);
+    }
+    for (int i = tid; i < d_end - d_begin; i += kThreads) s_dep[i] = __ldg(depth_values + (size_t)b * D + d_begin + i);
     if (tid == 0) {
         ptx::mbar_init(bar, 1);
         ptx::fence_barrier_init();
-        ptx::prefetch_tensormap(&tmap);
+        ptx::prefetch_tensormap(&tmap0);
+        ptx::prefetch_tensormap(&tmap1);
+        ptx::prefetch_tensormap(&tmap2);
     }
-    uint32_t phase = 0;
+    uint32_t bar_phase = 0;
+    __syncthreads();  // s_rt, s_dep
 
-    // reference-view texels of this pixel (view 0 of the same fp16 tensor): 4 chunks x 16 B
-    const uint4 *ref_px = tex + (((size_t)b * V * H + min(y, H - 1)) * 4) * W + min(x, W - 1);
+    // Lane -> pixel mapping, chosen per CTA.  A warp always covers a 16 x 2 pixel strip; the 8 lanes of a quarter warp
+    // (one LDS.128 wavefront) take either 8 consecutive pixels of one row -- conflict-free while their samples stay in
+    // one window row and advance by at most one texel per pixel: rectified cameras -- or a 4 x 2 block: the window row
+    // pitch is 64 mod 128 bytes (odd number of columns), so the block's two pixel rows land in disjoint halves of the 8
+    // bank groups, which survives roll and zoom far better (rotated cameras: 34-76 % excess wavefronts with the row
+    // mapping, 23 % with blocks; rectified: the row mapping is 3 % faster, ncu r2k).
+    if (tid == 0) {
+        const float cxp = (float)min(tx0 + 4, W - 1), cyp = (float)min(ty0 + TH / 2, H - 1);
+        bool rows_ok = true;
+        for (int k = 0; k < 2; ++k) {
+            const float dep = s_dep[k ? d_end - d_begin - 1 : 0];
+            for (int v = 0; v < nsrc; ++v) {
+                const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+                float px[2], py[2];
+                for (int e = 0; e < 2; ++e) {
+                    const float xx = cxp + 7.f * e;
+                    const float iz = 1.0f / fmaf(fmaf(c2.x, xx, fmaf(c2.y, cyp, c2.z)), dep, c2.w);
+                    px[e] = fmaf(fmaf(c0.x, xx, fmaf(c0.y, cyp, c0.z)), dep, c0.w) * iz;
+                    py[e] = fmaf(fmaf(c1.x, xx, fmaf(c1.y, cyp, c1.z)), dep, c1.w) * iz;
+                }
+                const float dx = px[1] - px[0], dy = py[1] - py[0];
+                rows_ok &= (fabsf(dy) < 0.25f) && (dx > 5.0f) && (dx < 7.15f);  // false for NaN
+            }
+        }
+        s_seg[2] = rows_ok ? 0 : 1;
+    }
+    __syncthreads();
+    const bool blk42 = s_seg[2] != 0;
+    const int x = blk42 ? tx0 + 4 * ((tid >> 3) & 3) + (tid & 3) : tx0 + (tid & 15);
+    const int y = blk42 ? ty0 + 2 * ((tid >> 5) & 3) + ((tid >> 2) & 1) : ty0 + ((tid >> 4) & 7);
+    const bool live = (x < W) & (y < H);
+    const float xf = (float)x, yf = (float)y;
+
+    // -x_ref of this pixel (view 0 of the same fp16 tensor), the seed of every interpolation chain: 4 chunks x 16 B
+    uint4 nref[4];
+    {
+        const uint4 *ref_px = tex + (((size_t)b * V * H + min(y, H - 1)) * 4) * W + min(x, W - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint4 rv = __ldg(ref_px + (size_t)c * W);
+            nref[c] = make_uint4(rv.x ^ 0x80008000u, rv.y ^ 0x80008000u, rv.z ^ 0x80008000u, rv.w ^ 0x80008000u);
+        }
+    }
+    const __half2 invV = __float2half2_rn(1.0f / (float)V);
+    const size_t hw = (size_t)H * W, dhw = (size_t)D * hw;
+    uint4 *const out_px = out + (size_t)b * 4 * dhw + (size_t)min(y, H - 1) * W + min(x, W - 1);  // + c * dhw + d * hw
+
+    // a = R.(x, y, 1) per view (x / y rows already scaled): registers when the view count is a template parameter
+    float ax[NSRC > 0 ? NSRC : 1], ay[NSRC > 0 ? NSRC : 1], az[NSRC > 0 ? NSRC : 1];
+    if constexpr (NSRC > 0) {
+#pragma unroll
+        for (int v = 0; v < NSRC; ++v) {
+            const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+            ax[v] = fmaf(c0.x, xf, fmaf(c0.y, yf, c0.z));
+            ay[v] = fmaf(c1.x, xf, fmaf(c1.y, yf, c1.z));
+            az[v] = fmaf(c2.x, xf, fmaf(c2.y, yf, c2.z));
+        }
+    }
 
     int ds = d_begin;
     while (ds < d_end) {
-        __syncthreads();  // previous segment's windows are no longer read; s_rt / s_dep visible (first pass)
+        __syncthreads();  // the previous segment's windows and table are no longer read
         if (warp == 0) {
-            // ---- plan the segment: the longest run of planes starting at ds whose footprint fits every window
-            const float cx = (lane & 1) ? (float)min(tx0 + TW - 1, W - 1) : (float)tx0;
-            const float cy = (lane & 2) ? (float)min(ty0 + TH - 1, H - 1) : (float)ty0;
-            int L = d_end - ds;
-            int my_mode = 0;
-            int2 my_org = make_int2(0, 0);
+            // ---- plan: the longest run of planes starting at ds whose footprint, in every view, fits one of the shapes
+            const int corner = lane & 7, vsub = lane >> 3;
+            const float cxp = (corner & 1) ? (float)min(tx0 + TW - 1, W - 1) : (float)tx0;
+            const float cyp = (corner & 2) ? (float)min(ty0 + TH - 1, H - 1) : (float)ty0;
+            int L = min(d_end - ds, kMaxSeg);
+            int shape = -1;
+            int ex0[kMaxWin / 4], ey0[kMaxWin / 4];
             while (true) {
                 float dlo = 3.0e38f, dhi = -3.0e38f;
                 for (int i = lane; i < L; i += 32) {
@@ -230,14 +316,20 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                     dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
                 }
                 const bool dep_ok = (dlo > 0.f) && (dhi < 3.0e38f);  // also false for NaN depths
-                const float cd = (lane & 4) ? dhi : dlo;
-                bool allfit = true;
-                for (int v = 0; v < nwin; ++v) {
-                    const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-                    const float qz = fmaf(fmaf(c2.x, cx, fmaf(c2.y, cy, c2.z)), cd, c2.w);
-                    const Coord c = project(c0, c1, c2, cx, cy, cd, sx, sy);
-                    bool ok = dep_ok && (qz > 1e-20f) && (fabsf(c.ix) < 1.0e8f) && (fabsf(c.iy) < 1.0e8f);
-                    float x_lo = ok ? c.ix : 0.f, x_hi = x_lo, y_lo = ok ? c.iy : 0.f, y_hi = y_lo;
+                const float cd = (corner & 4) ? dhi : dlo;
+                unsigned fitmask = (nsrc <= nwin) ? (1u << kShapes) - 1u : 0u;  // more views than windows: gather
+#pragma unroll
+                for (int it = 0; it < kMaxWin / 4; ++it) {
+                    const int v = it * 4 + vsub;
+                    const bool valid = v < nsrc && v < nwin;
+                    const int vv = valid ? v : 0;
+                    const float4 c0 = s_rt[3 * vv], c1 = s_rt[3 * vv + 1], c2 = s_rt[3 * vv + 2];
+                    const float qz = fmaf(fmaf(c2.x, cxp, fmaf(c2.y, cyp, c2.z)), cd, c2.w);
+                    const float iz = rcp_approx(qz);
+                    const float ix = fmaf(fmaf(fmaf(c0.x, cxp, fmaf(c0.y, cyp, c0.z)), cd, c0.w), iz, -0.5f);
+                    const float iy = fmaf(fmaf(fmaf(c1.x, cxp, fmaf(c1.y, cyp, c1.z)), cd, c1.w), iz, -0.5f);
+                    bool ok = dep_ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);
+                    float x_lo = ok ? ix : 0.f, x_hi = x_lo, y_lo = ok ? iy : 0.f, y_hi = y_lo;
 #pragma unroll
                     for (int o = 4; o; o >>= 1) {
                         x_lo = fminf(x_lo, __shfl_xor_sync(0xffffffffu, x_lo, o));
@@ -245,95 +337,138 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                         y_lo = fminf(y_lo, __shfl_xor_sync(0xffffffffu, y_lo, o));
                         y_hi = fmaxf(y_hi, __shfl_xor_sync(0xffffffffu, y_hi, o));
                     }
-                    ok = __all_sync(0xffffffffu, ok);
+                    const unsigned okb = __ballot_sync(0xffffffffu, ok);
+                    ok = ((okb >> (vsub * 8)) & 0xffu) == 0xffu;
                     // needed texel columns / rows, clipped to the part that can be non-zero: [-1, W] x [-1, H]
-                    const int ex0 = max((int)floorf(x_lo - 0.02f), -1), ex1 = min((int)floorf(x_hi + 0.02f) + 1, W);
-                    const int ey0 = max((int)floorf(y_lo - 0.02f), -1), ey1 = min((int)floorf(y_hi + 0.02f) + 1, H);
-                    const bool fit = ok && (ex1 - ex0 < WX) && (ey1 - ey0 < WY);
-                    if (lane == v) {
-                        my_mode = fit ? 0 : 1;
-                        // an empty clipped range (footprint entirely outside) gives ex1 < ex0: any origin works, every
-                        // sample then fails the in-window test or reads zero fill
-                        my_org = make_int2(max(min(ex0, W), -WX), max(min(ey0, H), -WY));
+                    const int e0 = max((int)floorf(x_lo - 0.02f), -1), e1 = min((int)floorf(x_hi + 0.02f) + 1, W);
+                    const int f0 = max((int)floorf(y_lo - 0.02f), -1), f1 = min((int)floorf(y_hi + 0.02f) + 1, H);
+                    ex0[it] = e0;
+                    ey0[it] = f0;
+#pragma unroll
+                    for (int s = 0; s < kShapes; ++s) {
+                        // two columns / rows of slack: element 0 is the first needed texel, the 2x2 footprint of a sample
+                        // clamped to the last needed texel still ends inside the window
+                        const bool fit = !valid || (ok && (e1 - e0 <= shp.wx[s] - 2) && (f1 - f0 <= shp.wy[s] - 2));
+                        if (!__all_sync(0xffffffffu, fit)) fitmask &= ~(1u << s);
                     }
-                    allfit &= fit;
                 }
-                if (allfit || L == 1) break;
+                if (fitmask) {
+                    shape = __ffs(fitmask) - 1;
+                    break;
+                }
+                if (L == 1) break;
                 L = (L + 1) >> 1;
             }
-            // nwin <= 32: lane v holds view v's decision
-            if (lane < nwin) {
-                s_org[lane] = my_org;
-                s_mode[lane] = my_mode;
-            }
-            const unsigned loadmask = __ballot_sync(0xffffffffu, (lane < nwin) && (my_mode == 0));
-            if (lane == 0) {
-                s_seg[0] = L;
-                ptx::mbar_arrive_expect_tx(bar, (uint32_t)__popc(loadmask) * win_bytes);
-            }
-            if ((lane < nwin) && (my_mode == 0))
-                ptx::tma_load_4d(ptx::smem_u32(smem_raw + (size_t)lane * win_bytes), &tmap, bar, 2 * my_org.x, 0, my_org.y,
-                                 b * V + 1 + lane);
-        }
-        __syncthreads();
-        const int L = s_seg[0];
-        ptx::mbar_wait(bar, phase);
-        phase ^= 1;
-
-        for (int d = ds; d < ds + L; ++d) {
-            const float dep = s_dep[d - d_begin];
-            float2 S[HACC ? 1 : 16], Q[HACC ? 1 : 16];
-            __half2 Sh[HACC ? 16 : 1], Qh[HACC ? 16 : 1];
-            uint4 nref[HACC ? 4 : 1];  // -x_ref, the start value of every interpolation chain
+            if (shape >= 0) {
+                const int wx = shp.wx[shape], wy = shp.wy[shape];
+                const CUtensorMap *tm = shape == 0 ? &tmap0 : (shape == 1 ? &tmap1 : &tmap2);
+                // one barrier for all windows (a barrier per window, waited on just before the view's first use, measured
+                // slower: 0.83 vs 0.79 ms -- the wait sits in the innermost view loop)
+                if (lane == 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nsrc * (uint32_t)(wx * wy * 64));
+                __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 rv = __ldg(ref_px + (size_t)c * W);
-                if constexpr (HACC) {
-                    nref[c] = make_uint4(rv.x ^ 0x80008000u, rv.y ^ 0x80008000u, rv.z ^ 0x80008000u, rv.w ^ 0x80008000u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) Sh[4 * c + j] = Qh[4 * c + j] = __float2half2_rn(0.f);
-                } else {
-                    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(as_half2(rw[j]));
-                        S[4 * c + j] = f;
-                        Q[4 * c + j] = __fmul2_rn(f, f);
+                for (int it = 0; it < kMaxWin / 4; ++it) {
+                    const int v = it * 4 + vsub;
+                    if (corner == 0 && v < nsrc) {
+                        // an empty clipped range (footprint entirely outside) gives any origin: every sample clamps onto
+                        // zero fill
+                        const int ox = max(min(ex0[it], W), -wx), oy = max(min(ey0[it], H), -wy);
+                        SegView sv;
+                        sv.cx = -0.5f - (float)ox;
+                        sv.cy = -0.5f - (float)oy;
+                        sv.hix = (float)min(wx - 2, W - ox);
+                        sv.hiy = (float)min(wy - 2, H - oy);
+                        s_sv[v] = sv;
+                        ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy, b * V + 1 + v);
                     }
                 }
             }
-            for (int v = 0; v < nsrc; ++v) {
-                const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-                Coord p = project(c0, c1, c2, xf, yf, dep, sx, sy);
-                // non-finite -> far outside (CUDA grid_sampler rule); everything beyond one texel outside is zero anyway
-                p.ix = fminf(fmaxf(p.ix, -2.f), xmax);
-                p.iy = fminf(fmaxf(p.iy, -2.f), ymax);
-                const float fx = floorf(p.ix), fy = floorf(p.iy);
-                const float bx = p.ix - fx, by = p.iy - fy;
-                const int x0 = (int)fx, y0 = (int)fy;
-                float w11 = bx * by;
-                float w10 = by - w11, w01 = bx - w11;
-                float w00 = (1.0f - bx) - w10;
-                const bool windowed = (v < nwin) && (s_mode[v] == 0);  // CTA-uniform
-                if (windowed) {
-                    const int2 org = s_org[v];
-                    int ox = x0 - org.x, oy = y0 - org.y;
-                    const bool in = ((unsigned)ox <= (unsigned)(WX - 2)) & ((unsigned)oy <= (unsigned)(WY - 2));
-                    if (!in) {
-                        ox = 0; oy = 0;
-                        w00 = 0.f; w01 = 0.f; w10 = 0.f; w11 = 0.f;
+            if (lane == 0) {
+                s_seg[0] = L;
+                s_seg[1] = shape;
+            }
+        }
+        __syncthreads();
+        const int L = s_seg[0], shape = s_seg[1];
+        if (shape >= 0) {
+            // ================= windowed segment (the fast path) =================
+            const int wx = shp.wx[shape];
+            const uint32_t chb = (uint32_t)wx * 16u;   // bytes between the 8-channel chunks of a window row
+            const uint32_t rowb = chb * 4u;            // bytes per window row
+            ptx::mbar_wait(bar, bar_phase);
+            bar_phase ^= 1;
+            for (int d = ds + phase; d < ds + L; d += kPhase) {
+                const float dep = s_dep[d - d_begin];
+                __half2 S[16], Q[16];
+                if constexpr (NSRC == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) S[j] = Q[j] = __float2half2_rn(0.f);
+                }
+#pragma unroll
+                for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
+                    for (int vr = (NSRC > 0 ? v : 0); vr < (NSRC > 0 ? v + 1 : nsrc); ++vr) {  // runtime view loop when NSRC = 0
+                        const float4 tv = lds_f4(tv0 + 16u * vr);
+                        const float4 sv = lds_f4(sv0 + 16u * vr);
+                        float pax, pay, paz;
+                        if constexpr (NSRC > 0) {
+                            pax = ax[v]; pay = ay[v]; paz = az[v];
+                        } else {
+                            const float4 c0 = s_rt[3 * vr], c1 = s_rt[3 * vr + 1], c2 = s_rt[3 * vr + 2];
+                            pax = fmaf(c0.x, xf, fmaf(c0.y, yf, c0.z));
+                            pay = fmaf(c1.x, xf, fmaf(c1.y, yf, c1.z));
+                            paz = fmaf(c2.x, xf, fmaf(c2.y, yf, c2.z));
+                        }
+                        const float iz = rcp_approx(fmaf(paz, dep, tv.z));
+                        float fx = fmaf(fmaf(pax, dep, tv.x), iz, sv.x);
+                        float fy = fmaf(fmaf(pay, dep, tv.y), iz, sv.y);
+                        fx = fminf(fmaxf(fx, 0.f), sv.z);   // NaN -> 0: memory safe whatever the coordinates
+                        fy = fminf(fmaxf(fy, 0.f), sv.w);
+                        const int ox = (int)fx, oy = (int)fy;      // >= 0: truncation is floor
+                        const float bx = fx - (float)ox, by = fy - (float)oy;
+                        __half2 h00, h01, h10, h11;
+                        tap_weights(bx, by, h00, h01, h10, h11);
+                        const uint32_t a0 = win0 + (uint32_t)vr * win_bytes + (uint32_t)oy * rowb + (uint32_t)ox * 16u;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t a = a0 + (uint32_t)c * chb;
+                            const uint4 ta = lds_u4(a), tb = lds_u4(a + 16u), tc = lds_u4(a + rowb), td = lds_u4(a + rowb + 16u);
+                            if (NSRC > 0 && v == 0) accumulate_chunk<true>(ta, tb, tc, td, h00, h01, h10, h11, nref[c], S + 4 * c, Q + 4 * c);
+                            else accumulate_chunk<false>(ta, tb, tc, td, h00, h01, h10, h11, nref[c], S + 4 * c, Q + 4 * c);
+                        }
                     }
-                    const __half2 h00 = __float2half2_rn(w00), h01 = __float2half2_rn(w01);
-                    const __half2 h10 = __float2half2_rn(w10), h11 = __float2half2_rn(w11);
-                    const uint4 *wp = reinterpret_cast<const uint4 *>(smem_raw + (size_t)v * win_bytes) + oy * ROWQ + ox;
+                }
+                if (live) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const uint4 ta = wp[c * WX], tb = wp[c * WX + 1], tc = wp[ROWQ + c * WX], td = wp[ROWQ + c * WX + 1];
-                        if constexpr (HACC) accumulate_chunk_dev(ta, tb, tc, td, h00, h01, h10, h11, nref[c], Sh + 4 * c, Qh + 4 * c);
-                        else accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
+                        uint4 pk;
+                        pk.x = variance_f16x2(S[4 * c], Q[4 * c], invV);
+                        pk.y = variance_f16x2(S[4 * c + 1], Q[4 * c + 1], invV);
+                        pk.z = variance_f16x2(S[4 * c + 2], Q[4 * c + 2], invV);
+                        pk.w = variance_f16x2(S[4 * c + 3], Q[4 * c + 3], invV);
+                        __stcs(out_px + (size_t)d * hw + (size_t)c * dhw, pk);
                     }
-                } else {
-                    // per-tap global gather with explicit zero padding (footprint too large for a window)
+                }
+            }
+        } else {
+            // ================= gather segment: per-tap global loads with explicit zero padding (exact, slow) ==========
+            const float xmax = (float)(W + 1), ymax = (float)(H + 1);
+            for (int d = ds + phase; d < ds + L; d += kPhase) {
+                const float dep = s_dep[d - d_begin];
+                __half2 S[16], Q[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) S[j] = Q[j] = __float2half2_rn(0.f);
+                for (int v = 0; v < nsrc; ++v) {
+                    const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+                    const float iz = rcp_approx(fmaf(fmaf(c2.x, xf, fmaf(c2.y, yf, c2.z)), dep, c2.w));
+                    float ix = fmaf(fmaf(fmaf(c0.x, xf, fmaf(c0.y, yf, c0.z)), dep, c0.w), iz, -0.5f);
+                    float iy = fmaf(fmaf(fmaf(c1.x, xf, fmaf(c1.y, yf, c1.z)), dep, c1.w), iz, -0.5f);
+                    // non-finite -> far outside (CUDA grid_sampler rule); everything beyond one texel outside is zero anyway
+                    ix = fminf(fmaxf(ix, -2.f), xmax);
+                    iy = fminf(fmaxf(iy, -2.f), ymax);
+                    const float fx = floorf(ix), fy = floorf(iy);
+                    const int x0 = (int)fx, y0 = (int)fy;
+                    const float bx = ix - fx, by = iy - fy;
+                    const float w11 = bx * by, w10 = by - w11, w01 = bx - w11, w00 = (1.0f - bx) - w10;
                     const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
                     const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
                     const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);
@@ -346,30 +481,19 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
                     for (int c = 0; c < 4; ++c) {
                         const uint4 ta = __ldg(r0 + c * W + cx0), tb = __ldg(r0 + c * W + cx1);
                         const uint4 tc = __ldg(r1 + c * W + cx0), td = __ldg(r1 + c * W + cx1);
-                        if constexpr (HACC) accumulate_chunk_dev(ta, tb, tc, td, h00, h01, h10, h11, nref[c], Sh + 4 * c, Qh + 4 * c);
-                        else accumulate_chunk(ta, tb, tc, td, h00, h01, h10, h11, S + 4 * c, Q + 4 * c);
+                        accumulate_chunk<false>(ta, tb, tc, td, h00, h01, h10, h11, nref[c], S + 4 * c, Q + 4 * c);
                     }
                 }
-            }
-            if (live) {
+                if (live) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // Q/V - (S/V)^2   (mvsnet.py:177), packed fp32x2
-                        const float2 sv = HACC ? __half22float2(Sh[HACC ? 4 * c + j : 0]) : S[HACC ? 0 : 4 * c + j];
-                        const float2 qv = HACC ? __half22float2(Qh[HACC ? 4 * c + j : 0]) : Q[HACC ? 0 : 4 * c + j];
-                        const float2 m = __fmul2_rn(sv, invV2);
-                        const float2 r = __ffma2_rn(qv, invV2, __fmul2_rn(m, make_float2(-m.x, -m.y)));
-                        if constexpr (kActF16) {  // saturating: a variance above 65504 (|feature| > 250) stays finite
-                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(r.y), "f"(r.x));
-                        } else {
-                            const __nv_bfloat162 o = __floats2bfloat162_rn(r.x, r.y);
-                            pk[j] = *reinterpret_cast<const uint32_t *>(&o);
-                        }
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 pk;
+                        pk.x = variance_f16x2(S[4 * c], Q[4 * c], invV);
+                        pk.y = variance_f16x2(S[4 * c + 1], Q[4 * c + 1], invV);
+                        pk.z = variance_f16x2(S[4 * c + 2], Q[4 * c + 2], invV);
+                        pk.w = variance_f16x2(S[4 * c + 3], Q[4 * c + 3], invV);
+                        __stcs(out_px + (size_t)d * hw + (size_t)c * dhw, pk);
                     }
-                    __stcs(out + ((((size_t)b * 4 + c) * D + d) * H + y) * W + x, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 }
             }
         }
@@ -382,26 +506,48 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap,      // fp16 
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int kSmemBudget = 113 * 1024;  // per CTA: two CTAs per SM
+
 struct WinPlan {
-    int nwin;  // source views with a shared-memory window (the rest gather from global memory)
-    int wy;    // rows per window
+    int nwin;            // source views with a shared-memory window (0: every segment gathers from global memory)
+    uint32_t win_bytes;  // bytes per window slot
+    WinShapes shp;
     size_t smem;
 };
 
-// rows per window: the tile's TH+1 rows plus room for vertical drift, within the per-CTA smem budget
-WinPlan plan_windows(int nsrc, int th, int wx, int dchunk, int smem_budget) {
-    const int rowb = 4 * wx * 16;
-    const int misc = nsrc * 48 + 32 * 12 + dchunk * 4 + 64;
-    WinPlan p;
-    p.nwin = std::min(nsrc, 32);
-    p.wy = 2;
-    while (p.nwin > 0) {
-        p.wy = std::min((smem_budget - misc) / (p.nwin * rowb), th + 8);
-        if (p.wy >= th + 2) break;
-        --p.nwin;  // more source views than fit: the last ones take the global-gather path
+// Three shapes with (nearly) the same number of texels: wide for rectified cameras and large disparity steps, tall for
+// rolled cameras.  Every shape holds at least the tile plus the bilinear halo.
+WinPlan plan_windows(int nsrc, int dchunk) {
+    WinPlan p = {};
+    const int misc = nsrc * 80 + dchunk * 4 + 64;
+    p.nwin = std::min(nsrc, kMaxWin);
+    if (nsrc > kMaxWin) p.nwin = 0;
+    int texels = p.nwin > 0 ? (kSmemBudget - misc) / (p.nwin * 64) : 0;
+    texels = std::min(texels, 1024);  // TMA box: <= 256 elements per dimension, keep windows sane for few views
+    if (p.nwin > 0 && texels < (TW + 4) * (TH + 2)) p.nwin = 0;  // too many views for useful windows
+    if (p.nwin == 0) {
+        for (int s = 0; s < kShapes; ++s) p.shp.wx[s] = p.shp.wy[s] = 2;
+        p.win_bytes = 0;
+        p.smem = misc;
+        return p;
     }
-    if (p.nwin == 0) p.wy = 2;
-    p.smem = (size_t)p.nwin * p.wy * rowb + misc;
+    const int rows[kShapes] = {TH + 2, TH + 6, TH + 10};
+    for (int s = 0; s < kShapes; ++s) {
+        int wy = rows[s];
+        // odd number of columns: row pitch = wx * 64 B = 64 mod 128 (see the lane mapping in the kernel)
+        int wx = (std::min(texels / wy, 121) - 1) | 1;
+        if (wx < TW + 4) {  // few texels: fall back to the flattest shape that holds the tile
+            wy = TH + 2;
+            wx = (texels / wy - 1) | 1;
+        }
+        p.shp.wx[s] = wx;
+        p.shp.wy[s] = wy;
+    }
+    p.win_bytes = (uint32_t)(((size_t)texels * 64 + 127) / 128 * 128);
+    while ((size_t)p.nwin * p.win_bytes + misc > (size_t)kSmemBudget) p.win_bytes -= 128;
+    for (int s = 0; s < kShapes; ++s)
+        while ((uint32_t)(p.shp.wx[s] * p.shp.wy[s] * 64) > p.win_bytes) p.shp.wx[s] -= 2;
+    p.smem = (size_t)p.nwin * p.win_bytes + misc;
     return p;
 }
 
@@ -420,25 +566,16 @@ int encode_window_map(CUtensorMap *tmap, const void *tex, int N, int H, int W, i
     return MVS_OK;
 }
 
-template <int TWW, int TH, int WX, bool HACC>
-int launch_win(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D, int H,
-               int W, int dchunk, int smem_budget, cudaStream_t st) {
-    const int nsrc = V - 1;
-    const WinPlan p = plan_windows(nsrc, TH, WX, dchunk, smem_budget);
-    CUtensorMap tmap;
-    if (int rc = encode_window_map(&tmap, tex16, B * V, H, W, WX, p.wy)) return rc;
-    auto kern = warp_variance_win_kernel<TWW, TH, WX, HACC>;
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    MVS_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_budget));
-        configured_dev = dev;
-    }
-    dim3 grid(cdiv(W, 32 * TWW), cdiv(H, TH), B * cdiv(D, dchunk));
+template <int NSRC>
+int launch_win(const CUtensorMap *maps, const WinPlan &p, const void *tex16, const float *rt, const float *depth_values,
+               void *vol_cp8, int B, int V, int D, int H, int W, int dchunk, cudaStream_t st) {
+    auto kern = warp_variance_win_kernel<NSRC>;
+    // a per-function attribute shared by every host thread and device: always the same value
+    MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    dim3 grid(cdiv(W, TW), cdiv(H, TH), B * cdiv(D, dchunk));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(32 * TWW * TH);
+    cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -446,8 +583,8 @@ int launch_win(const void *tex16, const float *rt, const float *depth_values, vo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, (const uint4 *)tex16, (const float *)rt, (const float *)depth_values, (uint4 *)vol_cp8, V,
-                                nsrc, p.nwin, D, H, W, dchunk, p.wy));
+    MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], (const uint4 *)tex16, (const float *)rt,
+                                (const float *)depth_values, (uint4 *)vol_cp8, V, V - 1, p.nwin, D, H, W, dchunk, p.shp, p.win_bytes));
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }
@@ -455,24 +592,24 @@ int launch_win(const void *tex16, const float *rt, const float *depth_values, vo
 }  // namespace
 
 // tex16: fp16 RCP8 features of all views [B*V][H][4][W][8].  Asynchronous on st.
-// half_sums: packed-half sums of deviations from the reference view (faster; relative error of large variances up to
-// 2^-6) instead of fp32 sums of the warped values (2^-7 everywhere, the tolerance stated for the tensor-core mode).
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, int half_sums, cudaStream_t st) {
-    static const int cfg = [] {
-        const char *e = getenv("MVS_WIN_CONFIG");  // tuning knob: 0 = 32x8 tile, 2 CTAs/SM; 1 = 64x8 tile, 1 CTA/SM
-        return e ? atoi(e) : 0;
-    }();
-    int dchunk = 16;
-    if (const char *e = getenv("MVS_WARP_DCHUNK")) dchunk = std::max(1, std::min(32, atoi(e)));
-    while ((long long)B * cdiv(D, dchunk) > 65535 && dchunk < 32) dchunk <<= 1;
+                          int H, int W, cudaStream_t st) {
+    MVS_REQUIRE(V >= 1, "warp_variance: V=%d", V);
+    int dchunk = kMaxSeg;
     MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
-    // MVS_WIN_HACC=0/1 overrides the caller's choice (tools/win_tune.py)
-    static const int force = [] { const char *e = getenv("MVS_WIN_HACC"); return e ? atoi(e) : -1; }();
-    const bool hacc = force >= 0 ? force != 0 : half_sums != 0;
-    if (cfg == 1) return launch_win<2, 8, 80, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 227 * 1024, st);
-    if (!hacc) return launch_win<1, 8, 40, false>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
-    return launch_win<1, 8, 40, true>(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, 113 * 1024, st);
+    MVS_REQUIRE(cdiv(H, TH) <= 65535, "feature map too tall");
+    const int nsrc = V - 1;
+    const WinPlan p = plan_windows(nsrc, dchunk);
+    CUtensorMap maps[kShapes];
+    for (int s = 0; s < kShapes; ++s)
+        if (int rc = encode_window_map(&maps[s], tex16, B * V, H, W, p.shp.wx[s], p.shp.wy[s])) return rc;
+    switch (p.nwin > 0 ? nsrc : 0) {
+        case 1: return launch_win<1>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+        case 2: return launch_win<2>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+        case 3: return launch_win<3>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+        case 4: return launch_win<4>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+        default: return launch_win<0>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+    }
 }
 
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st) {

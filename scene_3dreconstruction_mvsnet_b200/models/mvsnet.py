@@ -268,8 +268,7 @@ class MVSNet(nn.Module):
             # tensor-core modes: the cost volume goes from the fused warp+variance kernel to the tcgen05 CostRegNet
             # as bf16 chunk-planar data; no fp32 volume is written
             logits = ops.warp_variance_costreg_bf16(fea, proj_matrices.float(), depth_values.float(),
-                                                    self.cost_regularization.folded_params(), marks=mark,
-                                                    half_sums=self.precision == "fast")
+                                                    self.cost_regularization.folded_params(), marks=mark)
             mark("cost_regularization")
             depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
             mark("depth_tail")

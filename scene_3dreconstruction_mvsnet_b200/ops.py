@@ -349,7 +349,7 @@ def featurenet_tc(imgs, folded):
     return Rcp8Features(out, B, V, H // 4, W // 4)
 
 
-def warp_variance_cp8(fea, proj, depth_values, half_sums=False):
+def warp_variance_cp8(fea, proj, depth_values):
     """Fused warp+variance with the 16-bit chunk-planar output: returns an fp16 tensor [B, 4, D, h, w, 8]
     (channel = chunk*8 + last index).  fea: fp32 [B,V,32,h,w] (exact fp32 arithmetic) or fp16 channels-last
     [B,V,h,w,32] (fp16 texels).  Mostly for tests/diagnostics; the model uses warp_variance_costreg_bf16."""
@@ -373,14 +373,13 @@ def warp_variance_cp8(fea, proj, depth_values, half_sums=False):
     vol = torch.empty((B, 4, D, H, W, 8), dtype=torch.float16, device=fea.device)
     ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device)
     with torch.cuda.device(fea.device):
-        extra = (int(half_sums),) if rcp8 else ()
-        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, *extra, _stream(fea))
+        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
     _lib.check(rc, "mvs_warp_variance_fwd_cp8")
     return vol
 
 
-def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None, half_sums=False):
-    """bf16 precision mode: fused warp+variance writing the bf16 CP8 volume, then the tcgen05 CostRegNet.
+def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
+    """Tensor-core precision mode: fused warp+variance writing the fp16 CP8 volume, then the tcgen05 CostRegNet.
     fea: fp32 [B,V,32,h,w], or fp16 channels-last [B,V,h,w,32] (then no layout pre-pass runs) -> logits
     [B,D,h,w] (fp32).  `marks`, if a callable, is invoked between the two kernel families (stage timing)."""
     lib = _lib.load()
@@ -414,8 +413,7 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None, half
     with torch.cuda.device(fea.device):
         fn = lib.mvs_warp_variance_fwd_cp8_feat if rcp8 else (
             lib.mvs_warp_variance_fwd_cp8_f16 if half_nhwc else lib.mvs_warp_variance_fwd_cp8)
-        extra = (int(half_sums),) if rcp8 else ()
-        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, *extra, _stream(fea))
+        rc = fn(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1), B, V, C, D, H, W, _stream(fea))
         _lib.check(rc, "mvs_warp_variance_fwd_cp8")
         if marks is not None:
             marks("warp_variance")

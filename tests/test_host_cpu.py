@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.mvs_abi_version() == 1
+    assert lib.mvs_abi_version() == 2
     assert lib.mvs_arch() == b"sm_100a"
 
 

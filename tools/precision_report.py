@@ -39,7 +39,7 @@ import json
 from test_gpu_config_goldens import TAGS, measure
 print("\nconfig-sized goldens (reference outputs at C1 / C3 / C2):")
 for tag in TAGS:
-    for p in ("fp32", "bf16"):
+    for p in ("fp32", "bf16", "reference_cuda_default"):
         torch.cuda.empty_cache()
         r = measure(tag, w, p)
         print(tag, p, json.dumps({k: float("%.3g" % v) for k, v in r.items()}), flush=True)
