@@ -479,10 +479,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c4_train":
-        from scene_3dreconstruction_mvsnet_b200 import bench_workloads
+        import bench_workloads
         bench_workloads.run_train(args, sys.modules[__name__])
     elif args.workload == "c5_scan":
-        from scene_3dreconstruction_mvsnet_b200 import bench_workloads
+        import bench_workloads
         bench_workloads.run_scan(args, sys.modules[__name__])
     else:
         run_ours(args)

@@ -166,6 +166,15 @@ int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, in
 int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const float *proj, const float *depth_values, void *vol_cp8,
                                    void *workspace, int B, int V, int C, int D, int H, int W, void *stream);
 
+/* Same, features taken from a POOL of images [n_pool][H][4][W][8] fp16: view v of batch element b is image
+ * view_ids_host[b*V + v] (HOST array of B*V ints, B*V <= 32; read during the call).  This is the scan-level form of
+ * the reference's eval loop (eval.py:326-360): there every reference view re-loads and re-extracts its source images
+ * (datasets/dataloader_eval.py:101-176 -> mvsnet.py:125); with a pool each image of a scan passes FeatureNet once and
+ * serves every reference view whose pair list names it. */
+int mvs_warp_variance_fwd_cp8_pool(const void *pool_rcp8_f16, int n_pool, const int *view_ids_host, const float *proj,
+                                   const float *depth_values, void *vol_cp8, void *workspace, int B, int V, int C, int D,
+                                   int H, int W, void *stream);
+
 /* ---- (a5-a7) softmax over depth + depth expectation + 4-plane photometric confidence
  *                                                        models/mvsnet.py:192-193,204,214-218
  * logits [B,D,H,W], depth_values [B,D] -> depth [B,H,W], conf [B,H,W]; prob [B,D,H,W] optional. */

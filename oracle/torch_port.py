@@ -20,7 +20,13 @@ import torch.nn.functional as F
 EPS = 1e-5
 
 
+_TRAIN = [False]   # set by mvsnet_forward_train: BatchNorm with batch statistics (nn.Module.train())
+
+
 def _bn(x, sd, p):
+    if _TRAIN[0]:
+        return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                            True, 0.1, EPS)
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                         False, 0.0, EPS)
 
@@ -124,4 +130,37 @@ def mvsnet_forward(imgs, proj_matrices, depth_values, sd, stages=None):
     if stages is not None:
         stages["logits"] = logits
         stages["prob"] = prob
+    return {"depth": depth, "photometric_confidence": conf}
+
+
+def variance_volume_train(features, projs, depth_values):
+    """models/mvsnet.py:145-169,177 (training branch: out-of-place sums, every warped volume stays alive for autograd)."""
+    D = depth_values.shape[1]
+    V = len(features)
+    s = features[0].unsqueeze(2).repeat(1, 1, D, 1, 1)
+    q = s ** 2
+    for fea, proj in zip(features[1:], projs[1:]):
+        wv = homo_warping(fea, proj, projs[0], depth_values)
+        s = s + wv
+        q = q + wv ** 2
+    return q.div_(V).sub_(s.div_(V).pow_(2))
+
+
+def mvsnet_forward_train(imgs, proj_matrices, depth_values, sd):
+    """MVSNet.forward in train() mode with autograd (models/mvsnet.py:103-236; the step of train.py:241-300 around it is
+    the caller's): BatchNorm on batch statistics, the out-of-place variance branch, depth by soft argmin."""
+    _TRAIN[0] = True
+    try:
+        views = torch.unbind(imgs, 1)
+        projs = torch.unbind(proj_matrices, 1)
+        feats = [feature_net(v, sd) for v in views]
+        var = variance_volume_train(feats, projs, depth_values)
+        logits = cost_reg_net(var, sd).squeeze(1)
+        p = F.softmax(logits, dim=1)
+        B, D = depth_values.shape
+        depth = torch.sum(p * depth_values.view(B, D, 1, 1), 1)
+        with torch.no_grad():
+            _, conf, _ = depth_tail(logits.detach(), depth_values)
+    finally:
+        _TRAIN[0] = False
     return {"depth": depth, "photometric_confidence": conf}

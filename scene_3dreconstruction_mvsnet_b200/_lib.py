@@ -56,6 +56,8 @@ SIGNATURES = {
     "mvs_warp_variance_fwd_cp8": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_warp_variance_fwd_cp8_f16": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
     "mvs_warp_variance_fwd_cp8_feat": (_i, [_c_float_p] * 5 + [_i] * 6 + [ctypes.c_void_p]),
+    "mvs_warp_variance_fwd_cp8_pool": (_i, [_c_float_p, _i, ctypes.POINTER(ctypes.c_int)] + [_c_float_p] * 4 + [_i] * 6 +
+                                       [ctypes.c_void_p]),
     "mvs_featurenet_tc_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
     "mvs_featurenet_tc_fwd": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
                               [ctypes.c_void_p]),

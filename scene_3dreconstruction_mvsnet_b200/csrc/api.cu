@@ -34,6 +34,9 @@ int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *de
                            int B, int V, int D, int H, int W, cudaStream_t st);
 int warp_variance_cp8_f16(const void *fea16, const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
                           int B, int V, int D, int H, int W, cudaStream_t st);
+int warp_variance_cp8_pool(const void *pool16, int n_pool, const int *view_ids_host, const float *proj,
+                           const float *depth_values, void *vol_cp8, void *workspace, int B, int V, int D, int H, int W,
+                           cudaStream_t st);
 
 // layer table of CostRegNet (mvsnet.py:36-62): {Cin, Cout}; order conv0..conv6, conv7, conv9, conv11, prob
 static const int kLayerCin[MVS_COSTREG_LAYERS] = {32, 8, 16, 16, 32, 32, 64, 64, 32, 16, 8};
@@ -143,6 +146,18 @@ extern "C" int mvs_warp_variance_fwd_cp8_feat(const void *fea_rcp8_f16, const fl
     MVS_REQUIRE((long long)B * D <= 65535LL * 16 && (long long)H * W < (1LL << 27), "shape too large");
     MVS_REQUIRE(((uintptr_t)fea_rcp8_f16 & 15) == 0, "features must be 16-byte aligned");
     return warp_variance_cp8_rcp8(fea_rcp8_f16, proj, depth_values, vol_cp8, workspace, B, V, D, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int mvs_warp_variance_fwd_cp8_pool(const void *pool_rcp8_f16, int n_pool, const int *view_ids_host,
+                                              const float *proj, const float *depth_values, void *vol_cp8, void *workspace,
+                                              int B, int V, int C, int D, int H, int W, void *stream) {
+    MVS_REQUIRE(pool_rcp8_f16 && view_ids_host && proj && depth_values && vol_cp8 && workspace, "null pointer argument");
+    MVS_REQUIRE(C == 32, "warp_variance: C must be 32, got %d", C);
+    MVS_REQUIRE(B > 0 && V >= 1 && V <= 64 && D > 0 && H > 1 && W > 1 && n_pool > 0, "bad shape");
+    MVS_REQUIRE((long long)B * D <= 65535LL * 16 && (long long)H * W < (1LL << 27), "shape too large");
+    MVS_REQUIRE(((uintptr_t)pool_rcp8_f16 & 15) == 0, "features must be 16-byte aligned");
+    return warp_variance_cp8_pool(pool_rcp8_f16, n_pool, view_ids_host, proj, depth_values, vol_cp8, workspace, B, V, D, H, W,
+                                  (cudaStream_t)stream);
 }
 
 extern "C" int mvs_costreg_fwd_cp8(const void *vol_cp8, const mvs_costreg_params *p, float *logits, void *workspace,

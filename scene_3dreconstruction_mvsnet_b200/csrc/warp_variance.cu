@@ -766,7 +766,7 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
 // Internal: same op, output written as fp16 CP8 [B][4][D][H][W][8] for the tensor-core CostRegNet.
 namespace mvs {
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, cudaStream_t st);
+                          int H, int W, cudaStream_t st, int n_images = 0, const int *view_ids_host = nullptr);
 int features_nchw_to_rcp8(const float *fea, void *tex16, int N, int H, int W, cudaStream_t st);
 int features_nhwc16_to_rcp8(const void *fea16, void *tex16, int N, int H, int W, cudaStream_t st);
 // fp32 NCHW features in: one layout pass to fp16 RCP8 texels (all V views), then the TMA-window kernel
@@ -789,6 +789,16 @@ int warp_variance_cp8_rcp8(const void *tex16, const float *proj, const float *de
     if (V > 1)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
     return warp_variance_windows(tex16, rt, depth_values, vol_cp8, B, V, D, H, W, st);
+}
+
+// fp16 RCP8 features of a POOL of images; view v of batch element b is image view_ids_host[b*V + v]
+int warp_variance_cp8_pool(const void *pool16, int n_pool, const int *view_ids_host, const float *proj,
+                           const float *depth_values, void *vol_cp8, void *workspace, int B, int V, int D, int H, int W,
+                           cudaStream_t st) {
+    float *rt = (float *)workspace;
+    if (V > 1)
+        if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
+    return warp_variance_windows(pool16, rt, depth_values, vol_cp8, B, V, D, H, W, st, n_pool, view_ids_host);
 }
 
 // fp16 channels-last features of all V views in ([B][V][H*W][32], what a half-precision cuDNN FeatureNet emits)

@@ -58,6 +58,14 @@ struct WinShapes {
     int wx[kShapes], wy[kShapes];
 };
 
+// Image index of every (batch element, view) in the feature tensor; n = 0: the dense form b * V + v.  The indexed form
+// serves a feature POOL shared by the reference views of a scan (every image goes through FeatureNet once per scan).
+constexpr int kMaxViewIds = 32;
+struct ViewIds {
+    int n;
+    int id[kMaxViewIds];
+};
+
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -180,7 +188,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                          const float *__restrict__ rt,            // [B*nsrc][12] rot(9) | trans(3)
                          const float *__restrict__ depth_values,  // [B,D]
                          uint4 *__restrict__ out,                 // fp16 CP8 [B,4,D,H,W,8]
-                         int V, int nsrc_rt, int nwin, int D, int H, int W, int dchunk, const WinShapes shp, uint32_t win_bytes) {
+                         int V, int nsrc_rt, int nwin, int D, int H, int W, int dchunk, const WinShapes shp, uint32_t win_bytes,
+                         const ViewIds vid) {
     // the next kernel (conv0, launched with programmatic stream serialization) may start its set-up on SMs this grid has left
     ptx::pdl_launch_dependents();
     ptx::pdl_wait();  // homographies and features are read below
@@ -206,6 +215,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     const int d_begin = (blockIdx.z % nchunks) * dchunk;
     const int d_end = min(D, d_begin + dchunk);
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int img0 = b * V;  // index into vid.id / image index of the reference view in the dense form
     // ix = px * W/(W-1) - 0.5 is module.py:130-131 composed with grid_sample's align_corners=False un-normalisation
     const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
     const uint32_t bar = ptx::smem_u32(s_bar);
@@ -269,7 +279,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     // -x_ref of this pixel (view 0 of the same fp16 tensor), the seed of every interpolation chain: 4 chunks x 16 B
     uint4 nref[4];
     {
-        const uint4 *ref_px = tex + (((size_t)b * V * H + min(y, H - 1)) * 4) * W + min(x, W - 1);
+        const int ref_img = vid.n ? vid.id[img0] : img0;
+        const uint4 *ref_px = tex + (((size_t)ref_img * H + min(y, H - 1)) * 4) * W + min(x, W - 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint4 rv = __ldg(ref_px + (size_t)c * W);
@@ -379,7 +390,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                         sv.hix = (float)min(wx - 2, W - ox);
                         sv.hiy = (float)min(wy - 2, H - oy);
                         s_sv[v] = sv;
-                        ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy, b * V + 1 + v);
+                        ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy,
+                                         vid.n ? vid.id[img0 + 1 + v] : img0 + 1 + v);
                     }
                 }
             }
@@ -475,7 +487,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                     const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
                     const __half2 h00 = __float2half2_rn((vx0 & vy0) ? w00 : 0.f), h01 = __float2half2_rn((vx1 & vy0) ? w01 : 0.f);
                     const __half2 h10 = __float2half2_rn((vx0 & vy1) ? w10 : 0.f), h11 = __float2half2_rn((vx1 & vy1) ? w11 : 0.f);
-                    const uint4 *img = tex + ((size_t)(b * V + 1 + v) * H) * 4 * W;
+                    const uint4 *img = tex + ((size_t)(vid.n ? vid.id[img0 + 1 + v] : img0 + 1 + v) * H) * 4 * W;
                     const uint4 *r0 = img + (size_t)cy0 * 4 * W, *r1 = img + (size_t)cy1 * 4 * W;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -568,7 +580,7 @@ int encode_window_map(CUtensorMap *tmap, const void *tex, int N, int H, int W, i
 
 template <int NSRC>
 int launch_win(const CUtensorMap *maps, const WinPlan &p, const void *tex16, const float *rt, const float *depth_values,
-               void *vol_cp8, int B, int V, int D, int H, int W, int dchunk, cudaStream_t st) {
+               void *vol_cp8, int B, int V, int D, int H, int W, int dchunk, const ViewIds &vid, cudaStream_t st) {
     auto kern = warp_variance_win_kernel<NSRC>;
     // a per-function attribute shared by every host thread and device: always the same value
     MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -584,17 +596,31 @@ int launch_win(const CUtensorMap *maps, const WinPlan &p, const void *tex16, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], (const uint4 *)tex16, (const float *)rt,
-                                (const float *)depth_values, (uint4 *)vol_cp8, V, V - 1, p.nwin, D, H, W, dchunk, p.shp, p.win_bytes));
+                                (const float *)depth_values, (uint4 *)vol_cp8, V, V - 1, p.nwin, D, H, W, dchunk, p.shp, p.win_bytes, vid));
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }
 
 }  // namespace
 
-// tex16: fp16 RCP8 features of all views [B*V][H][4][W][8].  Asynchronous on st.
+// tex16: fp16 RCP8 features [n_images][H][4][W][8].  view_ids_host = nullptr: n_images = B*V, image b*V + v is view v of
+// batch element b; otherwise view_ids_host[b*V + v] names the image (a pool shared by several reference views).
+// Asynchronous on st.
 int warp_variance_windows(const void *tex16, const float *rt, const float *depth_values, void *vol_cp8, int B, int V, int D,
-                          int H, int W, cudaStream_t st) {
+                          int H, int W, cudaStream_t st, int n_images, const int *view_ids_host) {
     MVS_REQUIRE(V >= 1, "warp_variance: V=%d", V);
+    ViewIds vid = {};
+    if (view_ids_host) {
+        MVS_REQUIRE(B * V <= kMaxViewIds, "indexed features: B*V = %d exceeds %d", B * V, kMaxViewIds);
+        vid.n = B * V;
+        for (int i = 0; i < B * V; ++i) {
+            MVS_REQUIRE(view_ids_host[i] >= 0 && view_ids_host[i] < n_images, "view id %d = %d outside the pool of %d images", i,
+                        view_ids_host[i], n_images);
+            vid.id[i] = view_ids_host[i];
+        }
+    } else {
+        n_images = B * V;
+    }
     int dchunk = kMaxSeg;
     MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
     MVS_REQUIRE(cdiv(H, TH) <= 65535, "feature map too tall");
@@ -602,13 +628,13 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
     const WinPlan p = plan_windows(nsrc, dchunk);
     CUtensorMap maps[kShapes];
     for (int s = 0; s < kShapes; ++s)
-        if (int rc = encode_window_map(&maps[s], tex16, B * V, H, W, p.shp.wx[s], p.shp.wy[s])) return rc;
+        if (int rc = encode_window_map(&maps[s], tex16, n_images, H, W, p.shp.wx[s], p.shp.wy[s])) return rc;
     switch (p.nwin > 0 ? nsrc : 0) {
-        case 1: return launch_win<1>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
-        case 2: return launch_win<2>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
-        case 3: return launch_win<3>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
-        case 4: return launch_win<4>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
-        default: return launch_win<0>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, st);
+        case 1: return launch_win<1>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
+        case 2: return launch_win<2>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
+        case 3: return launch_win<3>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
+        case 4: return launch_win<4>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
+        default: return launch_win<0>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
     }
 }
 

@@ -299,6 +299,42 @@ class MVSNet(nn.Module):
         return {"depth": depth, "photometric_confidence": photometric_confidence}
 
 
+    # -- scan-level inference: features of an image are extracted once and shared by every reference view -----------
+    def features_to_pool(self, imgs, out):
+        """imgs [n,3,H,W] (fp32 in [0,1] or uint8) -> FeatureNet features written into `out`, a contiguous slice
+        [n, H/4, 4, W/4, 8] of an fp16 feature pool (tensor-core modes, eval, no autograd)."""
+        if self.training or torch.is_grad_enabled() or self.precision not in ("bf16", "fast"):
+            raise RuntimeError("features_to_pool: tensor-core inference only (eval mode, no_grad, precision 'bf16')")
+        x = imgs if imgs.dtype == torch.uint8 else imgs.float()
+        ops.featurenet_tc(x.unsqueeze(0), self.feature.folded_native(), out=out)
+
+    def forward_from_pool(self, pool, view_ids, proj_matrices, depth_values):
+        """The rest of forward() for one reference view whose views' features are pool[view_ids] (view_ids[0] = the
+        reference view; mvsnet.py:126-236 without :125).  proj_matrices [1,V,4,4], depth_values [1,D]."""
+        if len(view_ids) != proj_matrices.shape[1]:
+            raise AssertionError("Different number of images and projection matrices")  # mvsnet.py:106
+        if self.training or torch.is_grad_enabled() or self.precision not in ("bf16", "fast"):
+            raise RuntimeError("forward_from_pool: tensor-core inference only (eval mode, no_grad, precision 'bf16')")
+        marks = [] if self.stage_events is not None else None
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(pool.device))
+                marks.append((name, e))
+
+        mark("start")
+        depth_values = depth_values.float()
+        logits = ops.warp_variance_costreg_pool(pool, view_ids, proj_matrices.float(), depth_values,
+                                                self.cost_regularization.folded_params(), marks=mark)
+        mark("cost_regularization")
+        depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
+        mark("depth_tail")
+        if marks is not None:
+            self.stage_events.append(marks)
+        return {"depth": depth, "photometric_confidence": photometric_confidence}
+
+
 def mvsnet_loss(depth_est, depth_gt, mask):
     """Smooth-L1 over valid pixels (reference mvsnet.py:242-244)."""
     mask = mask > 0.5

@@ -33,6 +33,26 @@ def _ptr(t):
 
 
 _WS_CACHE = {}
+KERNEL_EVENTS = None  # set to a list to collect (name, start event, end event) around the fused warp kernels (bench.py)
+
+
+class _timed:
+    """Records CUDA events around a native call when KERNEL_EVENTS is a list (kernel time inside autograd graphs)."""
+
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        if KERNEL_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.device))
+            KERNEL_EVENTS.append((self.name, self.e0, e1))
+        return False
 
 
 def _ws(nbytes, device, tag=None):
@@ -151,7 +171,7 @@ def warp_variance_fwd(fea, proj, depth_values):
     lib = _lib.load()
     var = torch.empty((B, C, D, H, W), dtype=torch.float32, device=fea.device)
     ws = _ws(lib.mvs_warp_variance_workspace_bytes(B, V, C, H, W), fea.device, "warp")
-    with torch.cuda.device(fea.device):
+    with torch.cuda.device(fea.device), _timed("warp_variance_fwd", fea.device):
         rc = lib.mvs_warp_variance_fwd(_ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(var), _ptr(ws), B, V, C, D, H, W,
                                        _stream(fea))
     _lib.check(rc, "mvs_warp_variance_fwd")
@@ -165,7 +185,7 @@ def warp_variance_bwd(grad_var, fea, proj, depth_values):
     lib = _lib.load()
     grad_fea = torch.empty_like(fea)
     ws = _ws(lib.mvs_warp_variance_bwd_workspace_bytes(B, V, C, H, W), fea.device)
-    with torch.cuda.device(fea.device):
+    with torch.cuda.device(fea.device), _timed("warp_variance_bwd", fea.device):
         rc = lib.mvs_warp_variance_bwd(_ptr(grad_var), _ptr(fea), _ptr(proj), _ptr(depth_values), _ptr(grad_fea),
                                        _ptr(ws), B, V, C, D, H, W, _stream(fea))
     _lib.check(rc, "mvs_warp_variance_bwd")
@@ -314,10 +334,11 @@ def conv2d_bn_relu_tc(x, w_folded, shift, relu=True, stride=1, s2d_out=False):
     return y
 
 
-def featurenet_tc(imgs, folded):
+def featurenet_tc(imgs, folded, out=None):
     """FeatureNet.forward (reference models/mvsnet.py:10-30, eval mode) on the tensor cores.
     imgs [B,V,3,H,W] fp32; folded = 8 (weight, shift) CUDA tensors in layer order (native shapes, BN folded)
-    -> Rcp8Features (fp16 [B*V][H/4][4][W/4][8])."""
+    -> Rcp8Features (fp16 [B*V][H/4][4][W/4][8]).  out: optional contiguous fp16 tensor of that shape to write into
+    (a slice of a feature pool, see warp_variance_costreg_pool)."""
     u8 = isinstance(imgs, torch.Tensor) and imgs.dtype == torch.uint8
     if u8:  # 8-bit images as decoded from disk: /255 happens on the device (see mvs_featurenet_tc_fwd_u8)
         if not imgs.is_cuda or imgs.dim() != 5:
@@ -341,7 +362,11 @@ def featurenet_tc(imgs, folded):
         params.w[i] = w.data_ptr()
         params.shift[i] = s.data_ptr()
     ws = _ws(nbytes, imgs.device, "featurenet")
-    out = torch.empty((B * V, H // 4, 4, W // 4, 8), dtype=torch.float16, device=imgs.device)
+    shape = (B * V, H // 4, 4, W // 4, 8)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float16, device=imgs.device)
+    elif (tuple(out.shape) != shape or out.dtype != torch.float16 or out.device != imgs.device or not out.is_contiguous()):
+        raise RuntimeError("featurenet_tc: out must be a contiguous fp16 tensor %s on %s" % (shape, imgs.device))
     with torch.cuda.device(imgs.device):
         fn = lib.mvs_featurenet_tc_fwd_u8 if u8 else lib.mvs_featurenet_tc_fwd
         rc = fn(_ptr(imgs), ctypes.byref(params), _ptr(out), _ptr(ws), B * V, H, W, _stream(imgs))
@@ -418,6 +443,44 @@ def warp_variance_costreg_bf16(fea, proj, depth_values, folded, marks=None):
         if marks is not None:
             marks("warp_variance")
         rc = lib.mvs_costreg_fwd_cp8(_ptr(vol), ctypes.byref(params), _ptr(logits), _ptr(ws2), B, D, H, W, _stream(fea))
+        _lib.check(rc, "mvs_costreg_fwd_cp8")
+    return logits
+
+
+def warp_variance_costreg_pool(pool, view_ids, proj, depth_values, folded, marks=None):
+    """Scan-level form of warp_variance_costreg_bf16: `pool` is an fp16 tensor [n_pool, h, 4, w, 8] of FeatureNet
+    outputs (ops.featurenet_tc(..., out=pool[i:j])), `view_ids` the pool index of every view of this depth map (view 0 =
+    reference view), proj [1,V,4,4], depth_values [1,D] -> logits [1,D,h,w]."""
+    lib = _lib.load()
+    if not (isinstance(pool, torch.Tensor) and pool.is_cuda and pool.dtype == torch.float16 and pool.dim() == 5 and
+            pool.shape[2] == 4 and pool.shape[4] == 8 and pool.is_contiguous()):
+        raise RuntimeError("pool must be a contiguous CUDA fp16 tensor [n, h, 4, w, 8]")
+    n_pool, H, _, W, _ = pool.shape
+    view_ids = [int(i) for i in view_ids]
+    V = len(view_ids)
+    proj = _prep(proj, "proj_matrices", 4)
+    depth_values = _prep(depth_values, "depth_values", 2)
+    if proj.shape != (1, V, 4, 4):
+        raise RuntimeError("Different number of images and projection matrices: %d view ids, proj %s" % (V, tuple(proj.shape)))
+    if depth_values.shape[0] != 1:
+        raise RuntimeError("pool mode runs one reference view per call (depth_values %s)" % (tuple(depth_values.shape),))
+    D = depth_values.shape[1]
+    params, keep = _costreg_params(folded)
+    nbytes = lib.mvs_costreg_workspace_bytes(1, D, H, W, _lib.PRECISION_BF16)
+    if nbytes == 0:
+        raise RuntimeError("CostRegNet needs D, H, W divisible by 8 (got D=%d H=%d W=%d)" % (D, H, W))
+    vol = _ws(lib.mvs_volume_cp8_bytes(1, D, H, W), pool.device, "vol_cp8")
+    ws1 = _ws(lib.mvs_warp_variance_workspace_bytes(1, V, 32, H, W), pool.device, "warp")
+    ws2 = _ws(nbytes, pool.device, "costreg")
+    logits = torch.empty((1, D, H, W), dtype=torch.float32, device=pool.device)
+    ids = (ctypes.c_int * V)(*view_ids)
+    with torch.cuda.device(pool.device):
+        rc = lib.mvs_warp_variance_fwd_cp8_pool(_ptr(pool), n_pool, ids, _ptr(proj), _ptr(depth_values), _ptr(vol), _ptr(ws1),
+                                                1, V, 32, D, H, W, _stream(pool))
+        _lib.check(rc, "mvs_warp_variance_fwd_cp8_pool")
+        if marks is not None:
+            marks("warp_variance")
+        rc = lib.mvs_costreg_fwd_cp8(_ptr(vol), ctypes.byref(params), _ptr(logits), _ptr(ws2), 1, D, H, W, _stream(pool))
         _lib.check(rc, "mvs_costreg_fwd_cp8")
     return logits
 

@@ -106,3 +106,165 @@ class DepthMapRunner:
     def infer_host(self, imgs, proj, dv):
         """One reference view, host in / host out: (depth [B,h,w], confidence [B,h,w]) numpy arrays."""
         return self.run_views([(imgs, proj, dv)])[0]
+
+
+def plan_scan(pairs, capacity):
+    """Host-side schedule of a scan sweep (pure Python, no GPU): `pairs` is the ordered list of
+    (reference image id, [source image ids]) -- the reference's pair.txt (datasets/dataloader_eval.py:41-49) -- and
+    `capacity` the number of images whose features fit the device pool.  Returns one dict per reference view:
+        {"ref": k, "views": [image ids, reference first], "slots": [pool slot of every view],
+         "load": [(image id, pool slot), ...]}       # images whose features must be (re)computed before this view
+    Eviction is least-recently-used and never touches a view of the current step."""
+    slot_of, last_use, free = {}, {}, list(range(capacity - 1, -1, -1))
+    steps = []
+    for k, (ref, srcs) in enumerate(pairs):
+        views = [int(ref)] + [int(s) for s in srcs]
+        if len(set(views)) != len(views):
+            raise ValueError("reference view %d: duplicate image ids %s" % (k, views))
+        if len(views) > capacity:
+            raise ValueError("reference view %d needs %d images, the pool holds %d" % (k, len(views), capacity))
+        load = []
+        for img in views:
+            if img not in slot_of:
+                if not free:
+                    victim = min((i for i in slot_of if i not in views), key=lambda i: last_use[i])
+                    free.append(slot_of.pop(victim))
+                slot_of[img] = free.pop()
+                load.append((img, slot_of[img]))
+            last_use[img] = k
+        steps.append({"ref": k, "views": views, "slots": [slot_of[i] for i in views], "load": load})
+    return steps
+
+
+class ScanRunner:
+    """Scan-level inference with HOST buffers: the reference's eval loop (eval.py:326-360) over all reference views of
+    one scan, with every image uploaded ONCE and pushed through FeatureNet ONCE per scan.  The reference re-reads and
+    re-extracts the 4 source images of every reference view (dataloader_eval.py:101-176, mvsnet.py:125); in a DTU scan
+    (49 images, 49 reference views x 5 views) that is 5x the uploads and 5x the FeatureNet work.  Here the fp16
+    features stay in a device pool and the fused warp kernel reads the views of a depth map through an index table.
+
+    Pipelining: image uploads run on a copy stream into a ring of staging buffers, several images ahead of the compute
+    stream; depth / confidence maps return through pinned slots on a third stream, as in DepthMapRunner."""
+
+    def __init__(self, model, device="cuda:0", pool_images=64, ring=6, depth=3):
+        self.model = model.to(device).eval()
+        self.device = torch.device(device)
+        self.pool_images, self.ring, self.depth = pool_images, ring, depth
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
+        self._key = None
+        self.h2d_bytes = 0   # of the last run_scan
+        self.d2h_bytes = 0
+        self.featurenet_images = 0
+
+    def _alloc(self, img_shape, dtype, n_out):
+        C, H, W = img_shape
+        h, w = H // 4, W // 4
+        dev = self.device
+        self.pool = torch.empty((self.pool_images, h, 4, w, 8), dtype=torch.float16, device=dev)
+        self.stage = [{"d": torch.empty((C, H, W), dtype=dtype, device=dev), "h": None,
+                       "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False} for _ in range(self.ring)]
+        self.outs = [{"h": torch.empty((2, 1, h, w), dtype=torch.float32).pin_memory(), "done": torch.cuda.Event(),
+                      "copied": torch.cuda.Event()} for _ in range(n_out)]
+        self._key = (tuple(img_shape), dtype)
+
+    @torch.no_grad()
+    def run_scan(self, images, projs, depth_values, pairs, sink=None):
+        """images: sequence of HOST arrays [3,H,W] (float32 in [0,1] like the reference loader's output, or uint8 as
+        decoded from disk); projs [n_images,4,4]; depth_values [D] (shared) or [n_ref, D]; pairs: ordered
+        [(ref image id, [source image ids])].  Calls sink(k, depth_np, conf_np) per reference view k (numpy views of a
+        pinned buffer, valid until the next call) or, without a sink, returns the list of (depth, conf) copies."""
+        steps = plan_scan(pairs, self.pool_images)
+        first = torch.as_tensor(images[0])
+        dtype = torch.uint8 if first.dtype == torch.uint8 else torch.float32
+        if self._key != (tuple(first.shape), dtype):
+            self._alloc(tuple(first.shape), dtype, self.depth)
+        dev, compute = self.device, torch.cuda.current_stream(self.device)
+        projs = torch.as_tensor(projs, dtype=torch.float32)
+        dvs = torch.as_tensor(depth_values, dtype=torch.float32)
+        if dvs.dim() == 1:
+            dvs = dvs.unsqueeze(0)
+        # per-step projection matrices, assembled on the host and uploaded once (a few KB)
+        flat = torch.cat([projs[s["views"]] for s in steps]).contiguous()
+        d_proj = flat.to(dev, non_blocking=False)
+        d_dv = dvs.contiguous().to(dev)
+        self.h2d_bytes = 4 * (flat.numel() + dvs.numel())
+        self.d2h_bytes = 0
+        self.featurenet_images = 0
+
+        uploads = [(k, img, slot) for k, s in enumerate(steps) for img, slot in s["load"]]
+        issued = consumed = 0
+        results = [] if sink is None else None
+        pending = []
+
+        def issue(u):
+            _, img, _ = uploads[u]
+            st = self.stage[u % self.ring]
+            src = torch.as_tensor(images[img])
+            if src.dtype != dtype:
+                src = src.to(dtype)
+            if not (src.is_pinned() and src.is_contiguous()):
+                if st["h"] is None:
+                    st["h"] = torch.empty(src.shape, dtype=dtype).pin_memory()
+                if st["used"]:
+                    st["ready"].synchronize()   # the previous upload out of this pinned buffer has finished
+                st["h"].copy_(src)
+                src = st["h"]
+            with torch.cuda.stream(self.copy_stream):
+                if st["used"]:
+                    self.copy_stream.wait_event(st["free"])  # FeatureNet has consumed the previous occupant
+                st["d"].copy_(src, non_blocking=True)
+                st["ready"].record(self.copy_stream)
+            st["used"] = True
+            self.h2d_bytes += src.numel() * src.element_size()
+
+        def drain(entry):
+            k, o = entry
+            o["copied"].synchronize()
+            d, c = o["h"][0].numpy(), o["h"][1].numpy()
+            if sink is None:
+                results.append((d.copy(), c.copy()))
+            else:
+                sink(k, d, c)
+
+        off = 0
+        for k, s in enumerate(steps):
+            # keep the copy engine ahead of the compute stream: as many uploads in flight as the ring holds
+            while issued < len(uploads) and issued - consumed < self.ring:
+                issue(issued)
+                issued += 1
+            for img, slot in s["load"]:
+                if consumed == issued:
+                    issue(issued)
+                    issued += 1
+                st = self.stage[consumed % self.ring]
+                compute.wait_event(st["ready"])
+                self.model.features_to_pool(st["d"].unsqueeze(0), self.pool[slot:slot + 1])
+                st["free"].record(compute)
+                consumed += 1
+                self.featurenet_images += 1
+                while issued < len(uploads) and issued - consumed < self.ring:
+                    issue(issued)
+                    issued += 1
+            V = len(s["views"])
+            out = self.model.forward_from_pool(self.pool, s["slots"], d_proj[off:off + V].unsqueeze(0),
+                                               d_dv[min(k, d_dv.shape[0] - 1)].unsqueeze(0))
+            off += V
+            if len(pending) == self.depth:
+                drain(pending.pop(0))
+            o = self.outs[k % self.depth]
+            d_out = torch.stack((out["depth"], out["photometric_confidence"]))
+            o["done"].record(compute)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(o["done"])
+                o["h"].copy_(d_out, non_blocking=True)
+                d_out.record_stream(self.d2h_stream)
+                o["copied"].record(self.d2h_stream)
+            self.d2h_bytes += d_out.numel() * 4
+            pending.append((k, o))
+        for e in pending:
+            drain(e)
+        for st in self.stage:
+            st["used"] = False
+        torch.cuda.current_stream(dev).synchronize()
+        return results
