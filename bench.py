@@ -45,8 +45,8 @@ METRIC = "depth maps/s (DTU 1152x1600, D=192, 5 views) @1/2/4/8 B200; cost-vol H
 UNIT = "depth maps/s"
 DEFAULT_WORKLOAD = "c2_dtu_5view_1152x1600"
 REFERENCE_BUDGET_S = 150.0   # --impl reference: wall-clock budget for warm-up + timed steps of the CPU path
-TC_DTYPE = ("bf16 operands / f32 accumulate in CostRegNet, fp16 operands / f32 accumulate in FeatureNet (both tcgen05); fp16 "
-            "texels + packed-half tap interpolation, f32 sums in the fused warp kernel; bf16 cost volume")
+TC_DTYPE = ("f16 operands / f32 accumulate in CostRegNet and FeatureNet (tcgen05, kind::f16); fp16 texels, packed-half tap "
+            "interpolation and deviation sums in the fused warp kernel; fp16 cost volume and activations; f32 logits / softmax")
 
 
 def measured_peaks():

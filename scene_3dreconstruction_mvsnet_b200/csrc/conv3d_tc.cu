@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <string.h>
 #include <vector>
 
@@ -1736,6 +1737,10 @@ static long long *g_tc_dbg = nullptr;  // set by mvs_tc_set_debug_buffer (diagno
 // reused by later calls: 27 tiny launches per depth map disappear from the step.  The cache is keyed by POINTER: a
 // caller that changes weights in place or frees and re-creates them must call mvs_weight_cache_clear() (the Python
 // host does whenever it re-folds BatchNorm).  An event orders first use on one stream before reuse on another.
+// Lifetime: a forward pass (costreg_tc / featurenet_tc) holds g_wcache_life SHARED from its first lookup until its last
+// kernel is enqueued; a clear takes it EXCLUSIVELY, so every launch that uses an entry is already in a stream when the
+// entry is freed, and cudaFree waits for the device.  (No second-chance "graveyard": two clears from other threads could
+// free a pointer a third thread had looked up but not launched on yet.)
 // ------------------------------------------------------------------------------------------------
 struct WCacheKey {
     int dev;
@@ -1752,7 +1757,8 @@ struct WCacheEntry {
     cudaEvent_t ready;
     bool done;  // the fill has been observed complete: no event wait needed any more
 };
-static std::mutex g_wcache_mu;
+static std::mutex g_wcache_mu;            // the map itself
+static std::shared_mutex g_wcache_life;   // entry lifetime, see above
 static std::map<WCacheKey, WCacheEntry> g_wcache;
 
 static uint64_t fnv1a(const void *data, size_t n, uint64_t h = 1469598103934665603ull) {
@@ -1771,7 +1777,10 @@ static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void 
         WCacheEntry e;
         e.done = false;
         MVS_CUDA(cudaMalloc(&e.ptr, bytes));
-        MVS_CUDA(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+        if (cudaError_t ce = cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming); ce != cudaSuccess) {
+            cudaFree(e.ptr);
+            return set_error(MVS_ERR_CUDA, "cudaEventCreate (weight cache) failed: %s", cudaGetErrorString(ce));
+        }
         if (int rc = fill(e.ptr)) { cudaFree(e.ptr); cudaEventDestroy(e.ready); return rc; }
         MVS_CUDA(cudaEventRecord(e.ready, st));
         it = g_wcache.emplace(key, e).first;
@@ -1788,25 +1797,15 @@ static int wcache_get(const WCacheKey &key, size_t bytes, cudaStream_t st, void 
     return MVS_OK;
 }
 
-// Entries are retired in two steps: a clear moves them to a graveyard and frees the previous graveyard, so a launch on
-// another host thread that looked its pointer up just before the clear still reads valid memory.
-static std::vector<WCacheEntry> g_wcache_graveyard;
-static std::vector<int> g_wcache_graveyard_dev;
-
 int weight_cache_clear() {
+    std::unique_lock<std::shared_mutex> life(g_wcache_life);  // no forward pass is between a lookup and its launches
     std::lock_guard<std::mutex> lock(g_wcache_mu);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (size_t i = 0; i < g_wcache_graveyard.size(); ++i) {
-        cudaSetDevice(g_wcache_graveyard_dev[i]);
-        cudaFree(g_wcache_graveyard[i].ptr);  // synchronises with every stream that may still read it
-        cudaEventDestroy(g_wcache_graveyard[i].ready);
-    }
-    g_wcache_graveyard.clear();
-    g_wcache_graveyard_dev.clear();
     for (auto &kv : g_wcache) {
-        g_wcache_graveyard.push_back(kv.second);
-        g_wcache_graveyard_dev.push_back(kv.first.dev);
+        cudaSetDevice(kv.first.dev);
+        cudaFree(kv.second.ptr);  // waits for every kernel already enqueued on the device
+        cudaEventDestroy(kv.second.ready);
     }
     g_wcache.clear();
     cudaSetDevice(cur);
@@ -1912,6 +1911,7 @@ size_t costreg_tc_workspace_bytes(int B, int D, int H, int W) {
 
 int costreg_tc(const float *volume, const void *volume_cp8, const mvs_costreg_params *p, float *logits, void *workspace,
                int B, int D, int H, int W, cudaStream_t st) {
+    std::shared_lock<std::shared_mutex> lease(g_wcache_life);  // cached weight pointers stay valid until the last launch
     int dev = 0, num_sms = 148;
     MVS_CUDA(cudaGetDevice(&dev));
     MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -2101,6 +2101,7 @@ size_t featurenet_tc_workspace_bytes(int N, int H, int W) {
 // imgs fp32 [N][3][H][W] -> fea fp16 RCP8 [N][H/4][4][W/4][8]
 int featurenet_tc(const void *imgs, int imgs_u8, const mvs_featurenet_params *p, void *fea, void *workspace, int N, int H,
                   int W, cudaStream_t st) {
+    std::shared_lock<std::shared_mutex> lease(g_wcache_life);  // cached weight pointers stay valid until the last launch
     int dev = 0, num_sms = 148;
     MVS_CUDA(cudaGetDevice(&dev));
     MVS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -111,6 +111,27 @@ __device__ __forceinline__ void accumulate_chunk(const uint4 a, const uint4 b, c
     }
 }
 
+// a source view whose sample lies outside its image contributes x_v = 0, i.e. the deviation -x_ref: exactly what the
+// interpolation chain gives on four zero taps (0 * w + -x_ref), without the loads and the chain
+template <bool FIRST>
+__device__ __forceinline__ void accumulate_empty(const uint4 *nref, __half2 *S, __half2 *Q) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t wr[4] = {nref[c].x, nref[c].y, nref[c].z, nref[c].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 dv = as_half2(wr[j]);
+            if constexpr (FIRST) {
+                S[4 * c + j] = dv;
+                Q[4 * c + j] = __hmul2(dv, dv);
+            } else {
+                S[4 * c + j] = __hadd2(S[4 * c + j], dv);
+                Q[4 * c + j] = __hfma2(dv, dv, Q[4 * c + j]);
+            }
+        }
+    }
+}
+
 // bilinear weights of (bx, by) in [0, 1): fp32 products, rounded once to half, each broadcast to both halves
 __device__ __forceinline__ void tap_weights(float bx, float by, __half2 &h00, __half2 &h01, __half2 &h10, __half2 &h11) {
     const float w11 = bx * by;
@@ -176,7 +197,7 @@ struct SegView {
 // ------------------------------------------------------------------------------------------------
 // grid = (ceil(W / 16), ceil(H / 8), B * ceil(D / dchunk)), block = 256 threads:
 //   thread t: plane phase t >> 7; a warp = a 16 x 2 pixel strip of the tile, lanes laid out per CTA (see "Lane -> pixel")
-// dynamic smem: nwin windows of win_bytes | per-view constants | segment table | depths | mbarrier
+// dynamic smem: nwin windows of win_bytes | per-view constants | segment table | empty masks | depths | mbarrier
 // NSRC > 0: number of source views known at compile time (view loop unrolled, a = R.(x,y,1) in registers);
 // NSRC = 0: any number of views (a recomputed from shared memory per plane).
 // ------------------------------------------------------------------------------------------------
@@ -202,6 +223,8 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     sp += (size_t)nsrc * 16;
     float4 *s_tv = reinterpret_cast<float4 *>(sp);  // [nsrc]: translation (x / y scaled) of each view
     sp += (size_t)nsrc * 16;
+    uint32_t *s_emp = reinterpret_cast<uint32_t *>(sp);  // [nsrc]: bit i = plane ds + i of the segment is empty in view v
+    sp += (size_t)nsrc * 4;
     float *s_dep = reinterpret_cast<float *>(sp);  // [dchunk]
     sp += (size_t)dchunk * 4;
     sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
@@ -395,6 +418,37 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                     }
                 }
             }
+            if (shape >= 0) {
+                // ---- per plane (lane) and view: is the tile's footprint entirely outside the source image?  At a fixed
+                // depth the map is a homography, the tile's image is the convex quadrilateral of its 4 corners (q_z > 0),
+                // and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such (view, plane) pairs
+                // skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
+                const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
+                const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
+                const float dep = s_dep[ds - d_begin + min(lane, L - 1)];
+                for (int v = 0; v < nsrc; ++v) {
+                    const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+                    float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
+                    bool ok = (lane < L) && (dep > 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
+                        const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
+                        const float iz = 1.0f / qz;
+                        const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
+                        const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
+                        ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);  // false for NaN
+                        x_lo = fminf(x_lo, ix);
+                        x_hi = fmaxf(x_hi, ix);
+                        y_lo = fminf(y_lo, iy);
+                        y_hi = fmaxf(y_hi, iy);
+                    }
+                    const bool empty = ok && ((x_hi < -1.02f) || (x_lo > (float)W + 0.02f) || (y_hi < -1.02f) ||
+                                              (y_lo > (float)H + 0.02f));
+                    const unsigned m = __ballot_sync(0xffffffffu, empty);
+                    if (lane == 0) s_emp[v] = m;
+                }
+            }
             if (lane == 0) {
                 s_seg[0] = L;
                 s_seg[1] = shape;
@@ -407,10 +461,16 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
             const int wx = shp.wx[shape];
             const uint32_t chb = (uint32_t)wx * 16u;   // bytes between the 8-channel chunks of a window row
             const uint32_t rowb = chb * 4u;            // bytes per window row
+            uint32_t emp[NSRC > 0 ? NSRC : 1];
+            if constexpr (NSRC > 0) {
+#pragma unroll
+                for (int v = 0; v < NSRC; ++v) emp[v] = s_emp[v];
+            }
             ptx::mbar_wait(bar, bar_phase);
             bar_phase ^= 1;
             for (int d = ds + phase; d < ds + L; d += kPhase) {
                 const float dep = s_dep[d - d_begin];
+                const uint32_t dbit = 1u << (d - ds);
                 __half2 S[16], Q[16];
                 if constexpr (NSRC == 0) {
 #pragma unroll
@@ -419,6 +479,11 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
 #pragma unroll
                 for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
                     for (int vr = (NSRC > 0 ? v : 0); vr < (NSRC > 0 ? v + 1 : nsrc); ++vr) {  // runtime view loop when NSRC = 0
+                        if ((NSRC > 0 ? emp[v] : s_emp[vr]) & dbit) {  // CTA-uniform: nothing of this view under the tile
+                            if (NSRC > 0 && v == 0) accumulate_empty<true>(nref, S, Q);
+                            else accumulate_empty<false>(nref, S, Q);
+                            continue;
+                        }
                         const float4 tv = lds_f4(tv0 + 16u * vr);
                         const float4 sv = lds_f4(sv0 + 16u * vr);
                         float pax, pay, paz;
@@ -531,7 +596,7 @@ struct WinPlan {
 // rolled cameras.  Every shape holds at least the tile plus the bilinear halo.
 WinPlan plan_windows(int nsrc, int dchunk) {
     WinPlan p = {};
-    const int misc = nsrc * 80 + dchunk * 4 + 64;
+    const int misc = nsrc * 84 + dchunk * 4 + 64;
     p.nwin = std::min(nsrc, kMaxWin);
     if (nsrc > kMaxWin) p.nwin = 0;
     int texels = p.nwin > 0 ? (kSmemBudget - misc) / (p.nwin * 64) : 0;

@@ -200,6 +200,18 @@ class MVSNet(nn.Module):
                 "refine=True: the reference RefineNet cannot run (F.cat, mvsnet.py:85); use refine=False like "
                 "eval.py:308 and scripts/train_DTU.sh")
 
+    def invalidate_folded(self):
+        """Drop every derived copy of the weights: the BN-folded tensors cached on the modules and the packed 16-bit
+        operand blocks the native library caches per weight pointer.  The caches notice replaced tensors and in-place
+        updates that go through autograd's version counter (load_state_dict, optimizer steps, .to()); they cannot
+        notice writes through `.data` (p.data.copy_(...), EMA / SWA weight swaps, manual initialisation), which change
+        neither the pointer nor the version.  Call this after such an update and before the next eval forward."""
+        for m in (self.feature, self.cost_regularization):
+            for attr in ("_folded", "_native", "_half"):
+                if hasattr(m, attr):
+                    setattr(m, attr, None)
+        ops.weights_changed()
+
     # -- feature extraction ----------------------------------------------------------------------
     def extract_features(self, imgs):
         """imgs [B,V,3,H,W] -> [B,V,32,H/4,W/4].  Eval: one batched pass over all views (identical

@@ -354,6 +354,61 @@ def test_packed_weight_cache_follows_weight_changes(weights):
     assert torch.equal(a, d), "load_state_dict back to the original weights must restore the original result"
 
 
+def test_invalidate_folded_after_data_write(weights):
+    """Writes through `.data` change neither the pointer nor autograd's version counter: the caches cannot
+    see them, MVSNet.invalidate_folded() is the documented way to drop the folded / packed copies."""
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    imgs, proj, dv = synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=6)
+    imgs, proj, dv = imgs.to(DEV), proj.to(DEV), dv.to(DEV)
+    m = load_model(weights, precision="bf16")
+    with torch.no_grad():
+        a = m(imgs, proj, dv)["depth"].clone()
+        m.cost_regularization.conv2.conv.weight.data.mul_(1.25)
+        m.feature.conv3.conv.weight.data.mul_(0.75)
+        m.invalidate_folded()
+        b = m(imgs, proj, dv)["depth"].clone()
+        fresh = load_model(weights, precision="bf16")
+        fresh.cost_regularization.conv2.conv.weight.mul_(1.25)
+        fresh.feature.conv3.conv.weight.mul_(0.75)
+        c = fresh(imgs, proj, dv)["depth"]
+    assert not torch.equal(a, b) and torch.equal(b, c)
+
+
+def test_cache_clears_from_another_thread_do_not_break_forwards(weights):
+    """mvs_weight_cache_clear() takes the cache's lifetime lock exclusively: a forward pass on another host thread either
+    finishes enqueueing with its packed weights intact or starts after the clear and re-packs (the old
+    two-clear graveyard could free a buffer between a lookup and its launch)."""
+    import threading
+    from test_gpu_parity import load_model
+    from scene_3dreconstruction_mvsnet_b200 import ops, synth
+    inp = tuple(t.to(DEV) for t in synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=13))
+    m = load_model(weights, precision="bf16")
+    with torch.no_grad():
+        want = m(*inp)["depth"].clone()
+    torch.cuda.synchronize()
+    stop, errors = [False], []
+
+    def clearer():
+        while not stop[0]:
+            ops.weights_changed()
+
+    t = threading.Thread(target=clearer)
+    t.start()
+    try:
+        with torch.no_grad():
+            for _ in range(40):
+                got = m(*inp)["depth"]
+                if not torch.equal(got, want):
+                    errors.append("result changed")
+                    break
+    finally:
+        stop[0] = True
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+
+
 def test_two_host_threads_two_streams_same_results(weights):
     """nn.DataParallel calls forward from one host thread per replica (train.py:125): two threads, each with its own
     model replica and CUDA stream on the same device, must reproduce the serial results bit for bit (thread-local
