@@ -227,7 +227,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     sp += (size_t)nsrc * 4;
     float *s_dep = reinterpret_cast<float *>(sp);  // [dchunk]
     sp += (size_t)dchunk * 4;
-    sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
+    sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);  // (an integer round trip would make every access generic)
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(sp);
     int *s_seg = reinterpret_cast<int *>(sp + 8);  // [0] planes in the current segment, [1] window shape or -1 (gather)
 
@@ -272,25 +272,22 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     // pitch is 64 mod 128 bytes (odd number of columns), so the block's two pixel rows land in disjoint halves of the 8
     // bank groups, which survives roll and zoom far better (rotated cameras: 34-76 % excess wavefronts with the row
     // mapping, 23 % with blocks; rectified: the row mapping is 3 % faster, ncu r2k).
-    if (tid == 0) {
-        const float cxp = (float)min(tx0 + 4, W - 1), cyp = (float)min(ty0 + TH / 2, H - 1);
-        bool rows_ok = true;
-        for (int k = 0; k < 2; ++k) {
-            const float dep = s_dep[k ? d_end - d_begin - 1 : 0];
-            for (int v = 0; v < nsrc; ++v) {
-                const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-                float px[2], py[2];
-                for (int e = 0; e < 2; ++e) {
-                    const float xx = cxp + 7.f * e;
-                    const float iz = 1.0f / fmaf(fmaf(c2.x, xx, fmaf(c2.y, cyp, c2.z)), dep, c2.w);
-                    px[e] = fmaf(fmaf(c0.x, xx, fmaf(c0.y, cyp, c0.z)), dep, c0.w) * iz;
-                    py[e] = fmaf(fmaf(c1.x, xx, fmaf(c1.y, cyp, c1.z)), dep, c1.w) * iz;
-                }
-                const float dx = px[1] - px[0], dy = py[1] - py[0];
-                rows_ok &= (fabsf(dy) < 0.25f) && (dx > 5.0f) && (dx < 7.15f);  // false for NaN
-            }
-        }
-        s_seg[2] = rows_ok ? 0 : 1;
+    if (warp == 0) {
+        // lane = (pixel 4 or 11 of the tile's middle row, first / last plane, view slot): the displacement between the two
+        // pixels, 7 apart, in every view at both ends of the depth range (more than 8 views: the block mapping, always safe)
+        const int e = lane & 1, k = (lane >> 1) & 1, v = lane >> 2;
+        const float cyp = (float)min(ty0 + TH / 2, H - 1);
+        const float xx = (float)min(tx0 + 4, W - 1) + 7.f * e;
+        const float dep = s_dep[k ? d_end - d_begin - 1 : 0];
+        const int vv = v < nsrc ? v : 0;
+        const float4 c0 = s_rt[3 * vv], c1 = s_rt[3 * vv + 1], c2 = s_rt[3 * vv + 2];
+        const float iz = rcp_approx(fmaf(fmaf(c2.x, xx, fmaf(c2.y, cyp, c2.z)), dep, c2.w));
+        const float px = fmaf(fmaf(c0.x, xx, fmaf(c0.y, cyp, c0.z)), dep, c0.w) * iz;
+        const float py = fmaf(fmaf(c1.x, xx, fmaf(c1.y, cyp, c1.z)), dep, c1.w) * iz;
+        const float dx = __shfl_xor_sync(0xffffffffu, px, 1) - px, dy = __shfl_xor_sync(0xffffffffu, py, 1) - py;
+        const bool ok = (e != 0) || (v >= nsrc) || ((fabsf(dy) < 0.25f) && (dx > 5.0f) && (dx < 7.15f));  // false for NaN
+        const bool rows_ok = __all_sync(0xffffffffu, ok) && nsrc <= 8;
+        if (lane == 0) s_seg[2] = rows_ok ? 0 : 1;
     }
     __syncthreads();
     const bool blk42 = s_seg[2] != 0;
@@ -354,6 +351,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                 unsigned fitmask = (nsrc <= nwin) ? (1u << kShapes) - 1u : 0u;  // more views than windows: gather
 #pragma unroll
                 for (int it = 0; it < kMaxWin / 4; ++it) {
+                    if (it * 4 >= nsrc) break;  // warp-uniform: no second pass (12 shuffles, 3 votes) for up to 4 views
                     const int v = it * 4 + vsub;
                     const bool valid = v < nsrc && v < nwin;
                     const int vv = valid ? v : 0;
@@ -418,40 +416,42 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
                     }
                 }
             }
-            if (shape >= 0) {
-                // ---- per plane (lane) and view: is the tile's footprint entirely outside the source image?  At a fixed
-                // depth the map is a homography, the tile's image is the convex quadrilateral of its 4 corners (q_z > 0),
-                // and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such (view, plane) pairs
-                // skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
-                const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
-                const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
-                const float dep = s_dep[ds - d_begin + min(lane, L - 1)];
-                for (int v = 0; v < nsrc; ++v) {
-                    const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-                    float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
-                    bool ok = (lane < L) && (dep > 0.f);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
-                        const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
-                        const float iz = 1.0f / qz;
-                        const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
-                        const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
-                        ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);  // false for NaN
-                        x_lo = fminf(x_lo, ix);
-                        x_hi = fmaxf(x_hi, ix);
-                        y_lo = fminf(y_lo, iy);
-                        y_hi = fmaxf(y_hi, iy);
-                    }
-                    const bool empty = ok && ((x_hi < -1.02f) || (x_lo > (float)W + 0.02f) || (y_hi < -1.02f) ||
-                                              (y_lo > (float)H + 0.02f));
-                    const unsigned m = __ballot_sync(0xffffffffu, empty);
-                    if (lane == 0) s_emp[v] = m;
-                }
-            }
             if (lane == 0) {
                 s_seg[0] = L;
                 s_seg[1] = shape;
+            }
+        } else if (warp == 1) {
+            // ---- in parallel with the planner: per plane (lane) and view, is the tile's footprint entirely outside the
+            // source image?  At a fixed depth the map is a homography, the tile's image is the convex quadrilateral of its
+            // 4 corners (q_z > 0), and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such
+            // (view, plane) pairs skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
+            // Computed for the longest possible segment; the planner may choose a shorter one.
+            const int Lmax = min(d_end - ds, kMaxSeg);
+            const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
+            const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
+            const float dep = s_dep[ds - d_begin + min(lane, Lmax - 1)];
+            for (int v = 0; v < nsrc; ++v) {
+                const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+                float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
+                bool ok = (lane < Lmax) && (dep > 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
+                    const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
+                    const float iz = rcp_approx(qz);
+                    const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
+                    const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
+                    ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e5f) && (fabsf(iy) < 1.0e5f);  // false for NaN
+                    x_lo = fminf(x_lo, ix);
+                    x_hi = fmaxf(x_hi, ix);
+                    y_lo = fminf(y_lo, iy);
+                    y_hi = fmaxf(y_hi, iy);
+                }
+                // margins far above the error of the approximate reciprocal (2^-22 relative, coordinates below 1e5)
+                const bool empty = ok && ((x_hi < -1.05f) || (x_lo > (float)W + 0.05f) || (y_hi < -1.05f) ||
+                                          (y_lo > (float)H + 0.05f));
+                const unsigned m = __ballot_sync(0xffffffffu, empty);
+                if (lane == 0) s_emp[v] = m;
             }
         }
         __syncthreads();
