@@ -11,9 +11,19 @@ import torch
 
 
 class DepthMapRunner:
-    def __init__(self, model, device="cuda:0", depth=3):
+    """graphs=True (tensor-core modes): the forward pass of every staging slot is captured once into a CUDA graph --
+    the slot's device input buffers and its output tensor are static -- and replayed for later views.  One graph launch
+    replaces ~25 kernel launches with their Python / ctypes / tensor-map set-up (0.43 ms of host time per depth map).
+    Measured on an idle host (profiles/r02t): no gain -- the eager path already keeps the GPU busy (512 x 640, 4 views:
+    1834 eager vs 1814 depth maps/s replayed; 1152 x 1600: 416 vs 399) -- so it is off by default; it is for hosts whose
+    cores are contended (8 ranks per node) or slow."""
+
+    def __init__(self, model, device="cuda:0", depth=3, graphs=False):
         self.model = model.to(device).eval()
         self.device = torch.device(device)
+        self.graphs = bool(graphs) and getattr(model, "precision", "fp32") in ("bf16", "fast")
+        self._capture_stream = None
+        self._graph_pool = None
         # separate streams (and copy engines) for uploads and downloads: a download waits for its forward pass, and
         # on a shared stream it would hold back the next view's upload until that forward pass is over
         self.copy_stream = torch.cuda.Stream(self.device)
@@ -38,6 +48,7 @@ class DepthMapRunner:
                 "d_dv": torch.empty(dv.shape, dtype=torch.float32, device=self.device),
                 "h_out": torch.empty((2, B, h, w), dtype=torch.float32).pin_memory(),
                 "ready": torch.cuda.Event(), "done": torch.cuda.Event(), "copied": torch.cuda.Event(),
+                "graph": None, "d_out": None, "uses": 0,
             }
             slots.append(s)
         self._slots = slots
@@ -90,18 +101,44 @@ class DepthMapRunner:
                 s["d_dv"].copy_(src[2], non_blocking=True)
                 s["ready"].record(self.copy_stream)
             compute.wait_event(s["ready"])
-            out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
-            d_out = torch.stack((out["depth"], out["photometric_confidence"]))
+            d_out = self._forward(s, compute)
             s["done"].record(compute)
             with torch.cuda.stream(self.d2h_stream):
                 self.d2h_stream.wait_event(s["done"])
                 s["h_out"].copy_(d_out, non_blocking=True)
-                d_out.record_stream(self.d2h_stream)
+                if s["graph"] is None:
+                    d_out.record_stream(self.d2h_stream)
                 s["copied"].record(self.d2h_stream)
             pending.append((idx, s))
         for e in pending:
             drain(e)
         return results
+
+    def _forward(self, s, compute):
+        """depth + confidence [2,B,h,w] of the slot's device inputs: eagerly, or (graphs=True) by replaying the slot's
+        CUDA graph.  The first use of a slot runs eagerly (warm-up: weight packing, workspaces), the second captures."""
+        if not self.graphs:
+            out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
+            return torch.stack((out["depth"], out["photometric_confidence"]))
+        if s["graph"] is not None:
+            compute.wait_event(s["copied"])      # the previous result of this slot has left the static output tensor
+            s["graph"].replay()
+            return s["d_out"]
+        s["uses"] += 1
+        if s["uses"] < 2:
+            out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
+            return torch.stack((out["depth"], out["photometric_confidence"]))
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(self.device)   # one stream for every capture: shared workspaces
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        compute.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._graph_pool, stream=self._capture_stream):
+            out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
+            s["d_out"] = torch.stack((out["depth"], out["photometric_confidence"]))
+        s["graph"] = g
+        g.replay()
+        return s["d_out"]
 
     def infer_host(self, imgs, proj, dv):
         """One reference view, host in / host out: (depth [B,h,w], confidence [B,h,w]) numpy arrays."""
