@@ -369,6 +369,31 @@ def run_ours(args):
     e2e_u8_value = e2e_run(u8_imgs)
     e2e_u8_h2d = runner.h2d_bytes_per_view
 
+    # ---- the scan-level API on a DTU-shaped scan (49 images, 49 reference views x 5 views): float32 host images, each
+    # uploaded and passed through FeatureNet once per scan (ScanRunner; workload c5_scan has the full line)
+    e2e_scan = None
+    if args.workload == DEFAULT_WORKLOAD and args.precision != "fp32":
+        import bench_workloads
+        from scene_3dreconstruction_mvsnet_b200.runner import ScanRunner
+        s_images, s_projs, s_dv, s_pairs = bench_workloads.make_scan(seed=rank)
+        s_images = s_images.pin_memory()
+        srunner = ScanRunner(model, device=str(dev), pool_images=64)
+        srunner.run_scan(s_images, s_projs, s_dv, s_pairs, sink)
+        n_scans = max(1, args.steps // 10)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_scans):
+            srunner.run_scan(s_images, s_projs, s_dv, s_pairs, sink)
+        barrier()
+        t_scan = allmax(time.perf_counter() - t0)
+        e2e_scan = {"value": world * n_scans * len(s_pairs) / t_scan, "unit": UNIT, "scans": n_scans,
+                    "h2d_bytes_per_depth_map": srunner.h2d_bytes / len(s_pairs),
+                    "d2h_bytes_per_depth_map": srunner.d2h_bytes / len(s_pairs),
+                    "api": "ScanRunner.run_scan: one DTU-shaped scan per rank (49 float32 host images 1152x1600, 49 reference "
+                           "views x 5 views), every image uploaded and passed through FeatureNet once per scan"}
+        del srunner, s_images
+        torch.cuda.empty_cache()
+
     if rank == 0:
         hbm_peak, tf_peak, peak_kind = measured_peaks()
         alg_bytes, wv_ms, achieved = roofline_of(args.precision, stage_ms)
@@ -399,6 +424,7 @@ def run_ours(args):
             "e2e_uint8_images": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": e2e_u8_h2d,
                                  "d2h_bytes_per_step": runner.d2h_bytes_per_view,
                                  "note": "same API, images as uint8 host buffers; /255 on the device (reference: on the host)"},
+            "e2e_scan_api": e2e_scan,
             "gpu_launches": int(launches),
             "stage_ms": stage_ms,
             "roofline": {"kernel": ("warp_variance_fwd2_kernel" if args.precision == "fp32" else "warp_variance_win_kernel") +
