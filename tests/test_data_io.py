@@ -94,3 +94,64 @@ def test_async_writer(cases, tmp_path):
     wr2.submit(str(tmp_path / "missing_dir" / "a.pfm"), cases["gray"])
     with pytest.raises(OSError):
         wr2.close()
+
+
+@pytest.mark.gpu
+def test_eval_loop_from_disk_to_pfm(weights, tmp_path):
+    """The reference's eval loop end to end on a synthetic on-disk scan (eval.py:326-396 with
+    datasets/dataloader_eval.py:101-176): PNG images + cam files -> data_io loaders -> ScanRunner -> PfmWriter; the
+    PFMs read back equal MVSNet.forward on the float32 images the reference's loader would have produced."""
+    import torch
+    from PIL import Image
+    from scene_3dreconstruction_mvsnet_b200 import synth
+    from scene_3dreconstruction_mvsnet_b200.models import MVSNet
+    from scene_3dreconstruction_mvsnet_b200.runner import ScanRunner
+
+    n, H, W, D = 5, 64, 96, 16
+    rng = np.random.default_rng(3)
+    cams = synth.make_cameras(n, H // 4, W // 4, focal=60.0, yaw=0.02).astype(np.float64)
+    Kq = np.array([[60.0, 0, W / 8.0], [0, 60.0, H / 8.0], [0, 0, 1]])
+    for i in range(n):
+        Image.fromarray(rng.integers(0, 256, (H, W, 3), dtype=np.uint8)).save(tmp_path / ("%08d.png" % i))
+        E = np.eye(4)
+        E[:3, :4] = np.linalg.inv(Kq) @ cams[i][:3, :4]
+        K_full = Kq.copy()
+        K_full[:2] *= 4.0                                          # cam files hold full-resolution intrinsics
+        lines = ["extrinsic"] + [" ".join("%.9g" % v for v in r) for r in E] + ["", "intrinsic"] + \
+                [" ".join("%.9g" % v for v in r) for r in K_full] + ["", "425.0 20.0"]
+        (tmp_path / ("%08d_cam.txt" % i)).write_text("\n".join(lines) + "\n")
+
+    images_u8, images_f32, projs = [], [], []
+    for i in range(n):
+        K, E, dmin, dint = data_io.read_cam_file(str(tmp_path / ("%08d_cam.txt" % i)))
+        img8, K2 = data_io.read_rescale_crop_img(str(tmp_path / ("%08d.png" % i)), K.copy(), img_res=(H, W), as_uint8=True)
+        imgf, _ = data_io.read_rescale_crop_img(str(tmp_path / ("%08d.png" % i)), K.copy(), img_res=(H, W))
+        K2[:2] /= 4.0                                              # dataloader_eval.py: intrinsics at feature resolution
+        P = E.copy()
+        P[:3, :4] = K2 @ E[:3, :4]
+        images_u8.append(img8)
+        images_f32.append(np.ascontiguousarray(imgf.transpose(2, 0, 1)))
+        projs.append(P)
+    projs = np.stack(projs).astype(np.float32)
+    dv = (dmin + dint * np.arange(D)).astype(np.float32)
+    pairs = [(i, [j for j in sorted(range(n), key=lambda j: (abs(j - i), j)) if j != i][:2]) for i in range(n)]
+
+    model = MVSNet(refine=False, precision="bf16")
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    model = model.to("cuda:0").eval()
+    out_dir = tmp_path / "out"
+    path_of = lambda k: (str(out_dir / "depth_est" / ("%08d.pfm" % k)), str(out_dir / "confidence" / ("%08d.pfm" % k)))
+    with data_io.PfmWriter(threads=2) as wr:
+        ScanRunner(model, device="cuda:0", pool_images=8).run_scan(images_u8, projs, dv, pairs, wr.sink(path_of))
+    assert wr.files_written == 2 * n
+    with torch.no_grad():
+        for k, (ref, srcs) in enumerate(pairs):
+            ids = [ref] + srcs
+            imgs = torch.from_numpy(np.stack([images_f32[j] for j in ids])).unsqueeze(0).cuda()
+            out = model(imgs, torch.from_numpy(projs[ids]).unsqueeze(0).cuda(), torch.from_numpy(dv).unsqueeze(0).cuda())
+            depth, scale = data_io.read_pfm(path_of(k)[0])
+            conf, _ = data_io.read_pfm(path_of(k)[1])
+            assert scale == 1.0 and depth.shape == (H // 4, W // 4)
+            assert np.array_equal(depth, out["depth"][0].cpu().numpy())
+            assert np.array_equal(conf, out["photometric_confidence"][0].cpu().numpy())
+            assert float(depth.std()) > 0

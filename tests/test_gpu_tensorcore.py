@@ -111,7 +111,8 @@ def _check_cp8_against_oracle(fea, proj, dv, what):
 
 @pytest.mark.parametrize("B,V,h,w,D", [(1, 5, 24, 40, 16), (2, 3, 9, 33, 5), (1, 4, 16, 104, 8), (1, 2, 8, 31, 3),
                                        (1, 1, 8, 16, 4), (1, 3, 40, 72, 40),
-                                       (1, 8, 16, 40, 8)])   # 7 source views: 4 get shared-memory windows, 3 gather from global memory
+                                       (1, 8, 16, 40, 8),    # 7 source views: run-time view loop, smaller windows
+                                       (1, 10, 16, 40, 8)])  # 9 source views: more than windows -> every plane gathers
 def test_warp_variance_cp8(B, V, h, w, D):
     """Tensor-core-mode fused kernel (TMA-window generation) on camera-like geometry."""
     from scene_3dreconstruction_mvsnet_b200 import synth
