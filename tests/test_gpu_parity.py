@@ -202,7 +202,8 @@ def test_tail_golden(case, request):
     assert float(rel[safe].max()) < PROB_RTOL
 
 
-@pytest.mark.parametrize("B,D,H,W", [(1, 192, 16, 40), (2, 8, 5, 7), (1, 3, 4, 33), (1, 1, 2, 2), (1, 1000, 3, 5)])
+@pytest.mark.parametrize("B,D,H,W", [(1, 192, 16, 40), (2, 8, 5, 7), (1, 3, 4, 33), (1, 1, 2, 2), (1, 1000, 3, 5),
+                                     (2, 48, 8, 20), (1, 200, 7, 12), (3, 8, 2, 2), (1, 256, 4, 160)])
 def test_tail_oracle(B, D, H, W):
     g = torch.Generator().manual_seed(D)
     logits = torch.randn(B, D, H, W, generator=g) * 3
@@ -213,6 +214,23 @@ def test_tail_oracle(B, D, H, W):
     assert maxabs(depth, rd) < 1e-5 * rng + 1e-3
     safe = (np.abs(ri - np.round(ri)) > 1e-3) | (D == 1)
     assert float(np.max((np.abs(conf.cpu().numpy() - rc) / rc)[safe])) < PROB_RTOL
+
+
+@pytest.mark.parametrize("B,D,H,W", [(1, 192, 16, 40), (2, 40, 9, 12), (1, 8, 1, 4)])
+def test_tail_pipelined_kernel_equals_direct_kernel(B, D, H, W):
+    """The TMA-pipelined tail kernel (H*W % 4 == 0, D <= 256, 16-byte aligned logits) and the direct kernel (any shape)
+    share slice boundaries and reduction order: bit-identical depth, confidence and probabilities.  A logits tensor whose
+    storage starts 4 bytes off a 16-byte boundary takes the direct kernel."""
+    g = torch.Generator().manual_seed(B * 1000 + D)
+    logits = (torch.randn(B, D, H, W, generator=g) * 3).to(DEV)
+    dv = ((400 + 2.5 * torch.arange(D, dtype=torch.float32)).repeat(B, 1) + torch.arange(B).view(B, 1)).to(DEV)
+    off = torch.empty(logits.numel() + 1, device=DEV)[1:].view_as(logits)
+    off.copy_(logits)
+    assert logits.data_ptr() % 16 == 0 and off.data_ptr() % 16 == 4
+    a = ops.softmax_depth_conf(logits, dv, want_prob=True)
+    b = ops.softmax_depth_conf(off, dv, want_prob=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
 
 
 def test_depth_regression_both_forms(case_a):
