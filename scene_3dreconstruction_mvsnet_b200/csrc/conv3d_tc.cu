@@ -26,6 +26,7 @@
 #include <map>
 #include <mutex>
 #include <shared_mutex>
+#include <stddef.h>
 #include <string.h>
 #include <vector>
 
@@ -1816,8 +1817,35 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
                      void *out, int out_f32, void *wpacked_scratch, int B, int cin, int cout, int Din, int Hin, int Win,
                      int num_sms, cudaStream_t st, int f16 = 0, int out_mode = 0, bool cache_weights = false, void *out2 = nullptr,
                      bool in_split = false) {
-    static thread_local TcPlan pl;  // ~3 KB; not kept across calls
-    if (int rc = make_plan(pl, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split, f16 != 0 && skip == nullptr && !out_f32, skip)) return rc;
+    // Plans (tile geometry, op table, tensor maps) depend only on the layer's shape and on the addresses baked into the
+    // tensor maps.  The workspaces of consecutive forward passes are the same buffers, so a small per-thread cache turns the
+    // per-launch planning and cuTensorMapEncodeTiled calls (~10 us per layer, 20 layers per depth map) into a lookup.
+    struct PlanKey {
+        int kind, B, cin, cout, Din, Hin, Win, num_sms, in_split, allow_kw2d;
+        const void *in, *skip;
+        bool operator==(const PlanKey &o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
+    };
+    struct PlanSlot { PlanKey key; TcPlan plan; bool used; };
+    constexpr int kPlanSlots = 48;
+    static thread_local std::vector<PlanSlot> plan_cache;
+    static thread_local int plan_next = 0;
+    PlanKey key;
+    memset(&key, 0, sizeof(key));  // padding bytes too: the comparison is bytewise
+    key.kind = (int)kind; key.B = B; key.cin = cin; key.cout = cout; key.Din = Din; key.Hin = Hin; key.Win = Win;
+    key.num_sms = num_sms; key.in_split = in_split ? 1 : 0; key.allow_kw2d = (f16 != 0 && skip == nullptr && !out_f32) ? 1 : 0;
+    key.in = in; key.skip = skip;
+    TcPlan *plp = nullptr;
+    for (auto &sl : plan_cache)
+        if (sl.used && sl.key == key) { plp = &sl.plan; break; }
+    if (plp == nullptr) {
+        if ((int)plan_cache.size() < kPlanSlots) plan_cache.resize(plan_cache.size() + 1), plp = &plan_cache.back().plan, plan_cache.back().used = false;
+        else { plan_next = (plan_next + 1) % kPlanSlots; plan_cache[plan_next].used = false; plp = &plan_cache[plan_next].plan; }
+        PlanSlot *slot = reinterpret_cast<PlanSlot *>(reinterpret_cast<char *>(plp) - offsetof(PlanSlot, plan));
+        if (int rc = make_plan(*plp, kind, B, cin, cout, Din, Hin, Win, in, num_sms, true, in_split, key.allow_kw2d != 0, skip)) return rc;
+        slot->key = key;
+        slot->used = true;
+    }
+    TcPlan &pl = *plp;
     MVS_REQUIRE(out2 == nullptr || (out_mode == 0 && !out_f32 && !f16 && (pl.L.fold || pl.L.nacc == 1) && skip == nullptr && Hin % 2 == 0 && Win % 2 == 0), "second output: plain conv layers only");
     pl.L.out2 = out2;
     MVS_REQUIRE(!f16 || (kind == TC_CONV2D && (pl.npad <= 32 || pl.kw2d) && skip == nullptr && !out_f32), "fp16 operands: 2-D layers only");
@@ -1856,7 +1884,19 @@ static int run_layer(TcKind kind, const void *in, const float *w_fp32, const flo
     auto launch = [&](auto kern) -> int {
         // a per-function attribute shared by every host thread: always the same value (the opt-in maximum), never a
         // per-layer one that a concurrent launch of another layer could lower between this call and the launch
-        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+        // once per (kernel, device) and host thread.  Every kernel has the same function-pointer TYPE, so this lambda has
+        // one instantiation: the table is keyed by the pointer's value
+        struct AttrDone { const void *fn; uint64_t devs; };
+        static thread_local AttrDone attr_done[32] = {};
+        int adev = 0;
+        MVS_CUDA(cudaGetDevice(&adev));
+        AttrDone *ad = nullptr;
+        for (auto &a : attr_done)
+            if (a.fn == (const void *)kern || a.fn == nullptr) { ad = &a; break; }
+        if (ad == nullptr || adev >= 64 || ad->fn == nullptr || !((ad->devs >> adev) & 1ull)) {
+            MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            if (ad != nullptr && adev < 64) { ad->fn = (const void *)kern; ad->devs |= 1ull << adev; }
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)pl.grid);
         cfg.blockDim = dim3((unsigned)(pl.L.fold ? fold_threads(pl.L.fold_sets) : (pl.L.dual ? kTcThreadsDual : kTcThreads)));

@@ -690,10 +690,26 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
     MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
     MVS_REQUIRE(cdiv(H, TH) <= 65535, "feature map too tall");
     const int nsrc = V - 1;
-    const WinPlan p = plan_windows(nsrc, dchunk);
-    CUtensorMap maps[kShapes];
-    for (int s = 0; s < kShapes; ++s)
-        if (int rc = encode_window_map(&maps[s], tex16, n_images, H, W, p.shp.wx[s], p.shp.wy[s])) return rc;
+    // window plan + tensor maps depend on (features address, image count, H, W, views): cached per host thread, the
+    // feature tensor of consecutive depth maps is the same workspace / pool
+    struct MapSlot { const void *tex; int n, H, W, nsrc; WinPlan p; CUtensorMap maps[kShapes]; };
+    static thread_local MapSlot cache[4];
+    static thread_local int cache_next = 0;
+    MapSlot *slot = nullptr;
+    for (auto &c : cache)
+        if (c.tex == tex16 && c.n == n_images && c.H == H && c.W == W && c.nsrc == nsrc) { slot = &c; break; }
+    if (slot == nullptr) {
+        MapSlot &c = cache[cache_next];
+        cache_next = (cache_next + 1) % 4;
+        c.tex = nullptr;
+        c.p = plan_windows(nsrc, dchunk);
+        for (int s = 0; s < kShapes; ++s)
+            if (int rc = encode_window_map(&c.maps[s], tex16, n_images, H, W, c.p.shp.wx[s], c.p.shp.wy[s])) return rc;
+        c.tex = tex16; c.n = n_images; c.H = H; c.W = W; c.nsrc = nsrc;
+        slot = &c;
+    }
+    const WinPlan &p = slot->p;
+    const CUtensorMap *maps = slot->maps;
     switch (p.nwin > 0 ? nsrc : 0) {
         case 1: return launch_win<1>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
         case 2: return launch_win<2>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);

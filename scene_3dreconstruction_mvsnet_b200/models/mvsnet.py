@@ -22,6 +22,19 @@ from .. import ops
 from .module import ConvBnReLU, ConvBnReLU3D, depth_regression, fold_bn, homo_warping  # noqa: F401
 
 
+def _weights_key(module):
+    """Cheap change detector for the folded-weight caches: autograd's version counter of every parameter and buffer
+    (in-place updates: optimizer steps, load_state_dict) and the storage address of the first one (replaced storage:
+    .to() / .cuda() go through nn.Module._apply, which MVSNet overrides to drop the caches as well).  The tensor list
+    is collected once: ~10 us per forward instead of ~100 us for (data_ptr, version) of ~100 tensors."""
+    ts = module.__dict__.get("_key_tensors")
+    # (nn.DataParallel replicas copy __dict__ shallowly: a list that belongs to another module's parameters is rebuilt)
+    if ts is None or ts[0] is not next(module.parameters()):
+        ts = list(module.parameters()) + list(module.buffers())
+        module.__dict__["_key_tensors"] = ts
+    return (ts[0].data_ptr(), ts[-1].data_ptr()) + tuple([t._version for t in ts])
+
+
 class FeatureNet(nn.Module):
     """8-layer 2-D CNN, 3 -> 32 channels at 1/4 resolution (reference mvsnet.py:10-30)."""
 
@@ -46,8 +59,7 @@ class FeatureNet(nn.Module):
 
     def folded_params(self):
         """[(weight NHWC, bias, stride, padding)] x 7 with eval-mode BN folded in; cached like CostRegNet's."""
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = _weights_key(self)
         if getattr(self, "_folded", None) is None or key != self._folded_key:
             with torch.no_grad():
                 out = []
@@ -62,8 +74,7 @@ class FeatureNet(nn.Module):
     def folded_native(self):
         """[(weight [Cout,Cin,k,k] fp32, shift)] x 8 in layer order with eval-mode BN folded in (the last entry is the
         plain `feature` conv and its bias): the parameter set of ops.featurenet_tc.  Cached like folded_params()."""
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = _weights_key(self)
         if getattr(self, "_native", None) is None or key != self._native_key:
             with torch.no_grad():
                 out = []
@@ -73,14 +84,22 @@ class FeatureNet(nn.Module):
                     out.append((w.float().contiguous(), b.float().contiguous()))
                 out.append((self.feature.weight.detach().float().contiguous(), self.feature.bias.detach().float().contiguous()))
             self._native, self._native_key = out, key
+            self._native_prepared = None
             ops.weights_changed()
         return self._native
+
+    def native_prepared(self):
+        """folded_native() validated once and packed for the C ABI (ops.PreparedParams)."""
+        folded = self.folded_native()
+        if getattr(self, "_native_prepared", None) is None:
+            self._native_prepared = ops.PreparedParams(folded, "featurenet")
+        return self._native_prepared
 
     def infer_half(self, x):
         """fp16 variant of infer() for the tensor-core mode: x fp16 channels-last -> fp16 channels-last features
         (1.34 ms vs 1.64 ms with TF32 at 5 x 1152x1600, same 1e-4 accuracy class), emitted in exactly the texel layout
         the fused warp+variance kernel samples, so no conversion pass runs in between."""
-        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = _weights_key(self)
         if getattr(self, "_half", None) is None or key != self._half_key:
             with torch.no_grad():
                 layers = [(w.half().contiguous(memory_format=torch.channels_last), b.half(), s, p)
@@ -143,8 +162,7 @@ class CostRegNet(nn.Module):
     def folded_params(self):
         """[(weight, shift)] x 11 with eval-mode BN folded in; cached until a parameter or buffer
         is modified in place or replaced (load_state_dict, optimizer step, .to())."""
-        tensors = list(self.parameters()) + list(self.buffers())
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = _weights_key(self)
         if self._folded is None or key != self._folded_key:
             with torch.no_grad():
                 out = [getattr(self, n).folded() for n in self._ORDER]
@@ -153,8 +171,16 @@ class CostRegNet(nn.Module):
                     out.append(fold_bn(seq[0].weight, seq[1], out_dim=1))
                 out.append((self.prob.weight.detach().contiguous(), self.prob.bias.detach().contiguous()))
             self._folded, self._folded_key = out, key
+            self._prepared = None
             ops.weights_changed()
         return self._folded
+
+    def folded_prepared(self):
+        """folded_params() validated once and packed for the C ABI (ops.PreparedParams)."""
+        folded = self.folded_params()
+        if getattr(self, "_prepared", None) is None:
+            self._prepared = ops.PreparedParams(folded, "costreg")
+        return self._prepared
 
     def infer(self, volume, precision="fp32"):
         """Inference path: 11 fused CUDA launches, logits [B,D,h,w]."""
@@ -207,10 +233,20 @@ class MVSNet(nn.Module):
         notice writes through `.data` (p.data.copy_(...), EMA / SWA weight swaps, manual initialisation), which change
         neither the pointer nor the version.  Call this after such an update and before the next eval forward."""
         for m in (self.feature, self.cost_regularization):
-            for attr in ("_folded", "_native", "_half"):
+            for attr in ("_folded", "_native", "_half", "_prepared", "_native_prepared"):
                 if hasattr(m, attr):
                     setattr(m, attr, None)
+            m.__dict__.pop("_key_tensors", None)
         ops.weights_changed()
+
+    def _apply(self, fn, *args, **kwargs):
+        """.to() / .cuda() / .half() replace the parameters' storage: drop everything derived from the old one."""
+        before = [(p.data_ptr(), p.dtype, p.device) for p in (next(self.feature.parameters()), next(self.cost_regularization.parameters()))]
+        out = super()._apply(fn, *args, **kwargs)
+        after = [(p.data_ptr(), p.dtype, p.device) for p in (next(self.feature.parameters()), next(self.cost_regularization.parameters()))]
+        if before != after:   # a no-op .to(device) keeps the caches (and any CUDA graph captured over them)
+            self.invalidate_folded()
+        return out
 
     # -- feature extraction ----------------------------------------------------------------------
     def extract_features(self, imgs):
@@ -268,7 +304,7 @@ class MVSNet(nn.Module):
             # numpy's -- dividing by a Python scalar on CUDA multiplies by the rounded reciprocal instead.
             imgs = imgs.float() / torch.full((), 255.0, dtype=torch.float32, device=imgs.device)
         if tc_features:
-            fea = ops.featurenet_tc(imgs if imgs.dtype == torch.uint8 else imgs.float(), self.feature.folded_native())
+            fea = ops.featurenet_tc(imgs if imgs.dtype == torch.uint8 else imgs.float(), self.feature.native_prepared())
         elif infer and self.precision == "fast":
             fea = self.extract_features_half(imgs)
         else:
@@ -280,7 +316,7 @@ class MVSNet(nn.Module):
             # tensor-core modes: the cost volume goes from the fused warp+variance kernel to the tcgen05 CostRegNet
             # as bf16 chunk-planar data; no fp32 volume is written
             logits = ops.warp_variance_costreg_bf16(fea, proj_matrices.float(), depth_values.float(),
-                                                    self.cost_regularization.folded_params(), marks=mark)
+                                                    self.cost_regularization.folded_prepared(), marks=mark)
             mark("cost_regularization")
             depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
             mark("depth_tail")
@@ -318,7 +354,7 @@ class MVSNet(nn.Module):
         if self.training or torch.is_grad_enabled() or self.precision not in ("bf16", "fast"):
             raise RuntimeError("features_to_pool: tensor-core inference only (eval mode, no_grad, precision 'bf16')")
         x = imgs if imgs.dtype == torch.uint8 else imgs.float()
-        ops.featurenet_tc(x.unsqueeze(0), self.feature.folded_native(), out=out)
+        ops.featurenet_tc(x.unsqueeze(0), self.feature.native_prepared(), out=out)
 
     def forward_from_pool(self, pool, view_ids, proj_matrices, depth_values):
         """The rest of forward() for one reference view whose views' features are pool[view_ids] (view_ids[0] = the
@@ -338,7 +374,7 @@ class MVSNet(nn.Module):
         mark("start")
         depth_values = depth_values.float()
         logits = ops.warp_variance_costreg_pool(pool, view_ids, proj_matrices.float(), depth_values,
-                                                self.cost_regularization.folded_params(), marks=mark)
+                                                self.cost_regularization.folded_prepared(), marks=mark)
         mark("cost_regularization")
         depth, photometric_confidence = ops.softmax_depth_conf(logits, depth_values)
         mark("depth_tail")

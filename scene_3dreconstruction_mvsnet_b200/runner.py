@@ -6,6 +6,8 @@ double buffering so the host->device copy of view i+1 and the device->host copy 
 the kernels of view i.  Every byte still crosses PCIe inside the call -- this is the path bench.py
 times as `e2e`.
 """
+import itertools
+
 import numpy as np
 import torch
 
@@ -76,10 +78,11 @@ class DepthMapRunner:
         n_streams = self.n_streams
         if n_streams == "auto":
             n_streams = 1
-            if not isinstance(views, (list, tuple)):
-                views = list(views)
-            if views:
-                shp = tuple(views[0][0].shape)
+            it = iter(views)          # peek at the first view without materialising a lazy sweep
+            first = next(it, None)
+            views = [] if first is None else itertools.chain([first], it)
+            if first is not None:
+                shp = tuple(np.shape(first[0]))
                 n_streams = 2 if int(np.prod(shp[:2] + shp[3:])) >= 2_000_000 else 1
         if n_streams == 1:
             cstreams = [caller]
@@ -146,16 +149,25 @@ class DepthMapRunner:
 
     def _forward(self, s, compute):
         """depth + confidence [2,B,h,w] of the slot's device inputs: eagerly, or (graphs=True) by replaying the slot's
-        CUDA graph.  The first use of a slot runs eagerly (warm-up: weight packing, workspaces), the second captures."""
+        CUDA graph.  The first two uses of a slot run eagerly (warm-up: weight packing, workspaces), the third captures."""
         if not self.graphs:
             out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
             return torch.stack((out["depth"], out["photometric_confidence"]))
+        # a captured graph holds the addresses of the packed weights: weights changed since -> capture again
+        wkey = (id(self.model.feature.native_prepared()), id(self.model.cost_regularization.folded_prepared()))
+        if s["graph"] is not None and s.get("wkey") != wkey:
+            compute.synchronize()
+            for t in self._slots:                # every graph of the pool goes, with the workspaces captured in it
+                t["graph"], t["d_out"], t["uses"] = None, None, 0
+            from . import ops
+            ops.release_workspaces(self._capture_stream)
+            self._graph_pool = torch.cuda.graph_pool_handle()
         if s["graph"] is not None:
             compute.wait_event(s["copied"])      # the previous result of this slot has left the static output tensor
             s["graph"].replay()
             return s["d_out"]
         s["uses"] += 1
-        if s["uses"] < 2:
+        if s["uses"] < 3:                        # two eager passes: weight packing, workspaces, cache entries settled
             out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
             return torch.stack((out["depth"], out["photometric_confidence"]))
         if self._capture_stream is None:
@@ -166,7 +178,7 @@ class DepthMapRunner:
         with torch.cuda.graph(g, pool=self._graph_pool, stream=self._capture_stream):
             out = self.model(s["d_imgs"], s["d_proj"], s["d_dv"])
             s["d_out"] = torch.stack((out["depth"], out["photometric_confidence"]))
-        s["graph"] = g
+        s["graph"], s["wkey"] = g, wkey
         g.replay()
         return s["d_out"]
 

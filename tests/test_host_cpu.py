@@ -106,3 +106,36 @@ def test_oracle_is_not_imported_by_product():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/mvsnet_oracle.c:orc_compose_homography", ""), f
+
+
+def test_folded_weight_cache_keys_on_cpu():
+    """The folded-BN caches (host logic, no GPU): in-place updates through autograd's version counter are noticed,
+    writes through .data need MVSNet.invalidate_folded(), a shallow module copy (what nn.DataParallel's replicate does
+    to __dict__) does not inherit another module's tensor list, and ._apply (.to / .double) drops the caches."""
+    import copy
+    import torch
+    from scene_3dreconstruction_mvsnet_b200.models import MVSNet
+    torch.manual_seed(0)
+    m = MVSNet(refine=False).eval()
+    cr = m.cost_regularization
+    a = cr.folded_params()
+    assert cr.folded_params() is a                                   # cached
+    w0 = a[0][0].clone()
+    with torch.no_grad():
+        cr.conv0.conv.weight.mul_(2.0)                               # version bump
+    b = cr.folded_params()
+    assert b is not a and torch.allclose(b[0][0], 2.0 * w0)
+    cr.conv0.conv.weight.data.mul_(0.5)                              # invisible to the key ...
+    assert cr.folded_params() is b
+    m.invalidate_folded()                                            # ... until told
+    c = cr.folded_params()
+    assert c is not b and torch.allclose(c[0][0], w0)
+    # shallow copy with its own parameters: must not reuse the original's tensor list or folded weights
+    r = copy.copy(cr)
+    r._parameters = dict(cr._parameters)
+    r._modules = {k: copy.deepcopy(v) for k, v in cr._modules.items()}
+    with torch.no_grad():
+        r.conv0.conv.weight.mul_(3.0)
+    assert torch.allclose(r.folded_params()[0][0], 3.0 * w0) and torch.allclose(cr.folded_params()[0][0], w0)
+    m.double()
+    assert cr.folded_params()[0][0].dtype == torch.float64

@@ -124,7 +124,7 @@ def test_depth_map_runner_cuda_graphs_match_eager(weights):
     model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
     model = model.to(dev).eval()
     views = [synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=20 + i, yaw=0.01 * i)
-             for i in range(9)]
+             for i in range(11)]
     eager = DepthMapRunner(model, device=dev, depth=2).run_views(views)
     runner = DepthMapRunner(model, device=dev, depth=2, graphs=True)
     graphed = runner.run_views(views)
@@ -133,4 +133,12 @@ def test_depth_map_runner_cuda_graphs_match_eager(weights):
         assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
     again = runner.run_views(views[::-1])
     for (d0, c0), (d1, c1) in zip(eager[::-1], again):
+        assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
+    # weights change: the graphs (which hold the packed weights' addresses) are dropped and captured again
+    with torch.no_grad():
+        model.cost_regularization.conv0.conv.weight.mul_(1.5)
+    want = DepthMapRunner(model, device=dev, depth=2).run_views(views)
+    got = runner.run_views(views)
+    assert not np.array_equal(want[0][0], eager[0][0])
+    for (d0, c0), (d1, c1) in zip(want, got):
         assert np.array_equal(d0, d1) and np.array_equal(c0, c1)
