@@ -225,10 +225,15 @@ class ScanRunner:
     Pipelining: image uploads run on a copy stream into a ring of staging buffers, several images ahead of the compute
     stream; depth / confidence maps return through pinned slots on a third stream, as in DepthMapRunner."""
 
-    def __init__(self, model, device="cuda:0", pool_images=64, ring=6, depth=3):
+    def __init__(self, model, device="cuda:0", pool_images=64, ring=6, depth=3, streams="auto"):
+        """streams: compute streams the reference views alternate over ("auto": two from 1 M pixels per image on, see
+        DepthMapRunner).  Features written on one stream are handed to the other through events, and a pool slot is
+        only refilled after every forward pass that read it -- on either stream -- has finished."""
         self.model = model.to(device).eval()
         self.device = torch.device(device)
         self.pool_images, self.ring, self.depth = pool_images, ring, depth
+        self.n_streams = streams if streams == "auto" else max(1, int(streams))
+        self._compute_streams = None
         self.copy_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
         self._key = None
@@ -258,7 +263,16 @@ class ScanRunner:
         dtype = torch.uint8 if first.dtype == torch.uint8 else torch.float32
         if self._key != (tuple(first.shape), dtype):
             self._alloc(tuple(first.shape), dtype, self.depth)
-        dev, compute = self.device, torch.cuda.current_stream(self.device)
+        dev, caller = self.device, torch.cuda.current_stream(self.device)
+        n_streams = self.n_streams
+        if n_streams == "auto":
+            n_streams = 2 if int(first.shape[-1]) * int(first.shape[-2]) >= 1_000_000 else 1
+        if n_streams == 1:
+            cstreams = [caller]
+        else:
+            if self._compute_streams is None or len(self._compute_streams) != n_streams:
+                self._compute_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+            cstreams = self._compute_streams
         projs = torch.as_tensor(projs, dtype=torch.float32)
         dvs = torch.as_tensor(depth_values, dtype=torch.float32)
         if dvs.dim() == 1:
@@ -271,10 +285,15 @@ class ScanRunner:
         self.d2h_bytes = 0
         self.featurenet_images = 0
 
+        for cs in cstreams:
+            if cs is not caller:
+                cs.wait_stream(caller)       # the small uploads above, and whatever the caller enqueued before
         uploads = [(k, img, slot) for k, s in enumerate(steps) for img, slot in s["load"]]
         issued = consumed = 0
         results = [] if sink is None else None
         pending = []
+        slot_written = {}   # pool slot -> (event after the FeatureNet pass that filled it, index of its stream)
+        slot_read = {}      # pool slot -> {stream index: event after the last forward pass on that stream that read it}
 
         def issue(u):
             _, img, _ = uploads[u]
@@ -308,7 +327,9 @@ class ScanRunner:
 
         off = 0
         for k, s in enumerate(steps):
-            # keep the copy engine ahead of the compute stream: as many uploads in flight as the ring holds
+            ci = k % len(cstreams)
+            compute = cstreams[ci]
+            # keep the copy engine ahead of the compute streams: as many uploads in flight as the ring holds
             while issued < len(uploads) and issued - consumed < self.ring:
                 issue(issued)
                 issued += 1
@@ -318,21 +339,40 @@ class ScanRunner:
                     issued += 1
                 st = self.stage[consumed % self.ring]
                 compute.wait_event(st["ready"])
-                self.model.features_to_pool(st["d"].unsqueeze(0), self.pool[slot:slot + 1])
+                for cj, ev in slot_read.pop(slot, {}).items():   # the slot's previous occupant is no longer read
+                    if cj != ci:
+                        compute.wait_event(ev)
+                with torch.cuda.stream(compute):
+                    self.model.features_to_pool(st["d"].unsqueeze(0), self.pool[slot:slot + 1])
                 st["free"].record(compute)
+                if len(cstreams) > 1:
+                    ev = torch.cuda.Event()
+                    ev.record(compute)
+                    slot_written[slot] = (ev, ci)
                 consumed += 1
                 self.featurenet_images += 1
                 while issued < len(uploads) and issued - consumed < self.ring:
                     issue(issued)
                     issued += 1
             V = len(s["views"])
-            out = self.model.forward_from_pool(self.pool, s["slots"], d_proj[off:off + V].unsqueeze(0),
-                                               d_dv[min(k, d_dv.shape[0] - 1)].unsqueeze(0))
+            if len(cstreams) > 1:
+                for slot in s["slots"]:                          # features filled on the other stream
+                    ev, cj = slot_written[slot]
+                    if cj != ci:
+                        compute.wait_event(ev)
+            with torch.cuda.stream(compute):
+                out = self.model.forward_from_pool(self.pool, s["slots"], d_proj[off:off + V].unsqueeze(0),
+                                                   d_dv[min(k, d_dv.shape[0] - 1)].unsqueeze(0))
+                d_out = torch.stack((out["depth"], out["photometric_confidence"]))
+            if len(cstreams) > 1:
+                rev = torch.cuda.Event()
+                rev.record(compute)
+                for slot in s["slots"]:
+                    slot_read.setdefault(slot, {})[ci] = rev
             off += V
             if len(pending) == self.depth:
                 drain(pending.pop(0))
             o = self.outs[k % self.depth]
-            d_out = torch.stack((out["depth"], out["photometric_confidence"]))
             o["done"].record(compute)
             with torch.cuda.stream(self.d2h_stream):
                 self.d2h_stream.wait_event(o["done"])
@@ -345,5 +385,8 @@ class ScanRunner:
             drain(e)
         for st in self.stage:
             st["used"] = False
-        torch.cuda.current_stream(dev).synchronize()
+        for cs in cstreams:
+            if cs is not caller:
+                caller.wait_stream(cs)
+        caller.synchronize()
         return results

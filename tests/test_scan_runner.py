@@ -54,8 +54,9 @@ def test_plan_scan_ragged_and_errors():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype,capacity", [(torch.float32, 8), (torch.uint8, 3)])
-def test_scan_runner_is_bit_identical_to_per_view_forward(weights, dtype, capacity):
+@pytest.mark.parametrize("dtype,capacity,streams", [(torch.float32, 8, 1), (torch.uint8, 3, 1), (torch.float32, 8, 2),
+                                                     (torch.uint8, 3, 2), (torch.float32, 4, 3)])
+def test_scan_runner_is_bit_identical_to_per_view_forward(weights, dtype, capacity, streams):
     from scene_3dreconstruction_mvsnet_b200 import synth
     from scene_3dreconstruction_mvsnet_b200.models import MVSNet
     from scene_3dreconstruction_mvsnet_b200.runner import ScanRunner
@@ -74,7 +75,7 @@ def test_scan_runner_is_bit_identical_to_per_view_forward(weights, dtype, capaci
     model = MVSNet(refine=False, precision="bf16")
     model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
     model = model.to(dev).eval()
-    runner = ScanRunner(model, device=dev, pool_images=capacity, ring=2, depth=2)
+    runner = ScanRunner(model, device=dev, pool_images=capacity, ring=2, depth=2, streams=streams)
     got = runner.run_scan([images[i] for i in range(n)], projs, dv, pairs)
     assert len(got) == n and runner.featurenet_images >= n
     if capacity >= n:
