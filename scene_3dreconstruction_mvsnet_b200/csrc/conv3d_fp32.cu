@@ -13,6 +13,16 @@
 
 namespace mvs {
 
+// 4-byte asynchronous copy global -> shared; src_bytes = 0 writes a zero instead (nothing is read)
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Direct 3x3x3 convolution, NCDHW.  One CTA: TZ x TY x 32 output voxels x COUT_T output channels.
 // Thread: 4 consecutive x outputs x COUT_T channels in registers.  Input channels are processed in
@@ -55,18 +65,30 @@ conv3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, con
 
     for (int ci0 = 0; ci0 < Cin; ci0 += CK) {
         __syncthreads();
-        for (int idx = tid; idx < CK * T::IZ * T::IY * T::IX; idx += T::THREADS) {
-            const int xx = idx % T::IX;
-            const int r = idx / T::IX;
-            const int yy = r % T::IY;
-            const int r2 = r / T::IY;
-            const int zz = r2 % T::IZ;
-            const int c = r2 / T::IZ;
-            const int gx = ix0 + xx, gy = iy0 + yy, gz = iz0 + zz;
-            float v = 0.f;
-            if (ci0 + c < Cin && gx >= 0 && gx < Win && gy >= 0 && gy < Hin && gz >= 0 && gz < Din)
-                v = __ldg(x + ((size_t)b * Cin + ci0 + c) * in_cs + ((size_t)gz * Hin + gy) * Win + gx);
-            s_in[((c * T::IZ + zz) * T::IY + yy) * T::IXP + xx] = v;
+        // halo tile, one row of IX floats per warp iteration: the (channel, z, y) decode and the y / z bounds are
+        // warp-uniform, a lane only adds its x, and the copies are asynchronous (cp.async with zero fill outside the volume), so a
+        // whole tile is in flight before anything waits.  (An element-indexed loop of __ldg + st.shared spent ~60 instructions per element on
+        // div / mod chains and 64-bit address arithmetic -- a third of this kernel's instructions at stride 1 and
+        // three quarters at stride 2, where the halo is 4x the outputs.)
+        {
+            constexpr int NW = T::THREADS / 32;
+            const int wid = tid >> 5, ln = tid & 31;
+            for (int row = wid; row < CK * T::IZ * T::IY; row += NW) {
+                const int yy = row % T::IY;
+                const int r2 = row / T::IY;
+                const int zz = r2 % T::IZ;
+                const int c = r2 / T::IZ;
+                const int gy = iy0 + yy, gz = iz0 + zz;
+                const bool row_ok = (ci0 + c < Cin) && gy >= 0 && gy < Hin && gz >= 0 && gz < Din;
+                const float *src = x + ((size_t)b * Cin + ci0 + c) * in_cs + ((size_t)(row_ok ? gz : 0) * Hin + (row_ok ? gy : 0)) * Win;
+                float *dst = s_in + ((c * T::IZ + zz) * T::IY + yy) * T::IXP;
+#pragma unroll
+                for (int xx = ln; xx < T::IX; xx += 32) {
+                    const int gx = ix0 + xx;
+                    const bool ok = row_ok && gx >= 0 && gx < Win;
+                    cp_async4(dst + xx, src + (ok ? gx : 0), ok ? 4 : 0);   // asynchronous: every row of the tile in flight at once
+                }
+            }
         }
         for (int idx = tid; idx < CK * 27 * COUT_T; idx += T::THREADS) {
             const int co = idx % COUT_T;
@@ -76,6 +98,7 @@ conv3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, con
             if (co0 + co < Cout && ci0 + c < Cin) v = __ldg(w + ((size_t)(co0 + co) * Cin + ci0 + c) * 27 + tap);
             s_w[idx] = v;
         }
+        cp_async_wait_all();
         __syncthreads();
 
 #pragma unroll 1
