@@ -9,7 +9,10 @@
 // cost no extra pass over the activation (the reference runs each as a separate kernel).
 //
 // This file is the strict-precision (fp32 FMA) path.  The tensor-core path is conv3d_tc.cu.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mvs {
 
@@ -38,13 +41,104 @@ struct ConvTile {
     static constexpr int THREADS = TZ * TY * 8;
 };
 
+// shift (+ ReLU) and the 4-wide store of a thread's outputs
+template <int COUT_T, bool SCALAR = false>
+__device__ __forceinline__ void conv_store(const float (&acc)[4][COUT_T], const float *__restrict__ shift, int relu,
+                                           float *__restrict__ y, int b, int co0, int Cout, int oz, int oy, int ox, int Do, int Ho,
+                                           int Wo) {
+    if (oz >= Do || oy >= Ho || ox >= Wo) return;   // (ox may be negative in the SCALAR form: per-element test below)
+    const size_t out_cs = (size_t)Do * Ho * Wo;
+#pragma unroll
+    for (int q = 0; q < COUT_T; ++q) {
+        if (co0 + q >= Cout) break;
+        const float sh = __ldg(shift + co0 + q);
+        float v[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            v[o] = acc[o][q] + sh;
+            if (relu) v[o] = fmaxf(v[o], 0.f);
+        }
+        float *op = y + ((size_t)b * Cout + co0 + q) * out_cs + ((size_t)oz * Ho + oy) * Wo + ox;
+        if (!SCALAR && (Wo & 3) == 0) {
+            *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
+        } else if (SCALAR) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (ox + o >= 0 && ox + o < Wo) op[o] = v[o];
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (ox + o < Wo) op[o] = v[o];
+        }
+    }
+}
+
+// One chunk of CK input channels from a halo tile in shared memory: the 27 taps of every channel, 4 x COUT_T FMAs per tap and
+// thread, in the order (channel, kd, kh, kw) -- both kernels below accumulate through this function, so their results are
+// bit-identical.
+// XO: column of the tile row at which a thread's first input sits, relative to tx * 4 * S (0: the tile starts at the first
+// needed column; 3 (stride 2, TMA tiles): the tile starts 3 columns earlier, see conv3d_fp32_tma_kernel).
+template <int S, int CK, int TZ, int TY, int COUT_T, int XO = 0>
+__device__ __forceinline__ void conv_chunk(const float *__restrict__ s_in, const float *__restrict__ s_w, int tx, int ty, int tz,
+                                           float (&acc)[4][COUT_T]) {
+    using T = ConvTile<S, TZ, TY>;
+#pragma unroll 1
+    for (int c = 0; c < CK; ++c) {
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float *row = s_in + ((c * T::IZ + tz * S + kd) * T::IY + ty * S + kh) * T::IXP + tx * 4 * S;
+                float in[4 * S + 4];
+                if (S == 1) {
+                    const float4 a = *reinterpret_cast<const float4 *>(row);
+                    const float2 e = *reinterpret_cast<const float2 *>(row + 4);
+                    in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = e.x; in[5] = e.y;
+                } else if (XO == 0) {
+                    const float4 a = *reinterpret_cast<const float4 *>(row);
+                    const float4 e = *reinterpret_cast<const float4 *>(row + 4);
+                    in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
+                    in[4] = e.x; in[5] = e.y; in[6] = e.z; in[7] = e.w;
+                    in[8] = row[8];
+                } else {
+                    static_assert(XO == 0 || XO == 3, "tile column offset");
+                    const float4 a = *reinterpret_cast<const float4 *>(row + 4);
+                    const float4 e = *reinterpret_cast<const float4 *>(row + 8);
+                    in[0] = row[3];
+                    in[1] = a.x; in[2] = a.y; in[3] = a.z; in[4] = a.w;
+                    in[5] = e.x; in[6] = e.y; in[7] = e.z; in[8] = e.w;
+                }
+                const float *wp = s_w + (c * 27 + (kd * 3 + kh) * 3) * COUT_T;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    float wr[COUT_T];
+                    if (COUT_T % 4 == 0) {
+#pragma unroll
+                        for (int q = 0; q < COUT_T / 4; ++q) {
+                            const float4 t = *reinterpret_cast<const float4 *>(wp + kw * COUT_T + 4 * q);
+                            wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < COUT_T; ++q) wr[q] = wp[kw * COUT_T + q];
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+#pragma unroll
+                        for (int q = 0; q < COUT_T; ++q) acc[o][q] = fmaf(in[o * S + kw], wr[q], acc[o][q]);
+                }
+            }
+        }
+    }
+}
+
 template <int S, int CK, int TZ, int TY, int COUT_T>
 __global__ void __launch_bounds__(TZ *TY * 8)
 conv3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ shift, int relu,
                    float *__restrict__ y, int Cin, int Cout, int Din, int Hin, int Win, int Do, int Ho, int Wo,
                    int tiles_x) {
     using T = ConvTile<S, TZ, TY>;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float *s_in = smem;                      // [CK][IZ][IY][IXP]
     float *s_w = smem + CK * T::PER_CH;      // [CK][27][COUT_T]
 
@@ -101,71 +195,97 @@ conv3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, con
         cp_async_wait_all();
         __syncthreads();
 
-#pragma unroll 1
-        for (int c = 0; c < CK; ++c) {
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                    const float *row = s_in + ((c * T::IZ + tz * S + kd) * T::IY + ty * S + kh) * T::IXP + tx * 4 * S;
-                    float in[4 * S + 4];
-                    if (S == 1) {
-                        const float4 a = *reinterpret_cast<const float4 *>(row);
-                        const float2 e = *reinterpret_cast<const float2 *>(row + 4);
-                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = e.x; in[5] = e.y;
-                    } else {
-                        const float4 a = *reinterpret_cast<const float4 *>(row);
-                        const float4 e = *reinterpret_cast<const float4 *>(row + 4);
-                        in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
-                        in[4] = e.x; in[5] = e.y; in[6] = e.z; in[7] = e.w;
-                        in[8] = row[8];
-                    }
-                    const float *wp = s_w + (c * 27 + (kd * 3 + kh) * 3) * COUT_T;
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        float wr[COUT_T];
-                        if (COUT_T % 4 == 0) {
-#pragma unroll
-                            for (int q = 0; q < COUT_T / 4; ++q) {
-                                const float4 t = *reinterpret_cast<const float4 *>(wp + kw * COUT_T + 4 * q);
-                                wr[4 * q] = t.x; wr[4 * q + 1] = t.y; wr[4 * q + 2] = t.z; wr[4 * q + 3] = t.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < COUT_T; ++q) wr[q] = wp[kw * COUT_T + q];
-                        }
-#pragma unroll
-                        for (int o = 0; o < 4; ++o)
-#pragma unroll
-                            for (int q = 0; q < COUT_T; ++q) acc[o][q] = fmaf(in[o * S + kw], wr[q], acc[o][q]);
-                    }
-                }
-            }
-        }
+        conv_chunk<S, CK, TZ, TY, COUT_T>(s_in, s_w, tx, ty, tz, acc);
     }
 
-    const int oz = oz0 + tz, oy = oy0 + ty, ox = ox0 + tx * 4;
-    if (oz >= Do || oy >= Ho || ox >= Wo) return;
-    const size_t out_cs = (size_t)Do * Ho * Wo;
-#pragma unroll
-    for (int q = 0; q < COUT_T; ++q) {
-        if (co0 + q >= Cout) break;
-        const float sh = __ldg(shift + co0 + q);
-        float v[4];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            v[o] = acc[o][q] + sh;
-            if (relu) v[o] = fmaxf(v[o], 0.f);
-        }
-        float *op = y + ((size_t)b * Cout + co0 + q) * out_cs + ((size_t)oz * Ho + oy) * Wo + ox;
-        if ((Wo & 3) == 0) {
-            *reinterpret_cast<float4 *>(op) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
-                if (ox + o < Wo) op[o] = v[o];
-        }
+    conv_store<COUT_T>(acc, shift, relu, y, b, co0, Cout, oz0 + tz, oy0 + ty, ox0 + tx * 4, Do, Ho, Wo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same tile and arithmetic with the halo tile brought by TMA: one 5-D box (x, y, z, channel chunk, batch element) per
+// chunk, zero-filled outside the volume by the copy engine (= the convolution's zero padding), two stages so that the next
+// chunk is in flight while this one is computed.  The element-wise cp.async loop of the kernel above executes ~190
+// instructions per tile row (bounds, 64-bit addresses, one 4-byte copy per lane): 43 % of all instructions of conv0 at the DTU
+// shape (ncu, profiles/r02z).  Needs W % 4 == 0 and a 16-byte aligned input (tensor-map strides); other shapes take the kernel
+// above.  Weights of the next chunk arrive by cp.async next to the tile.
+// ------------------------------------------------------------------------------------------------
+template <int S, int CK, int TZ, int TY, int COUT_T>
+__global__ void __launch_bounds__(TZ *TY * 8)
+conv3d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ w, const float *__restrict__ shift,
+                       int relu, float *__restrict__ y, int Cin, int Cout, int Do, int Ho, int Wo, int tiles_x) {
+    using T = ConvTile<S, TZ, TY>;
+    // The innermost start coordinate of a TMA box must be a multiple of 16 bytes: the box starts at column S * ox0 - 4, not
+    // S * ox0 - 1.  Stride 1: the OUTPUT tile moves 3 columns to the left with it (ox0 - 3 ...), so a thread's six inputs stay
+    // an aligned float4 + float2 of its row and only its four stores become scalar.  Stride 2: inputs sit at column 3 of the
+    // thread's span (scalar + 2 x float4 instead of 2 x float4 + scalar).
+    constexpr int kOutShift = (S == 1) ? 3 : 0;
+    constexpr int kXO = (S == 1) ? 0 : 3;
+    constexpr int kBox = CK * T::PER_CH;            // floats a TMA box delivers
+    constexpr int kTile = (kBox + 31) / 32 * 32;    // floats per stage: 128-byte aligned TMA destinations
+    constexpr int kW = CK * 27 * COUT_T;
+    extern __shared__ __align__(128) float smem[];
+    // TMA destinations must be 128-byte aligned: align by hand (the launch allocates 128 bytes of slack)
+    float *s_in = smem + ((128u - (ptx::smem_u32(smem) & 127u)) & 127u) / 4;   // [2][CK][IZ][IY][IXP]
+    float *s_w = s_in + 2 * kTile;                                            // [2][CK][27][COUT_T]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_w + 2 * kW);             // [2]  (2 * kW floats: a multiple of 8 bytes)
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = (tid >> 3) % TY, tz = tid / (8 * TY);
+    const int cgroups = (Cout + COUT_T - 1) / COUT_T;
+    const int b = blockIdx.z / cgroups;
+    const int co0 = (blockIdx.z % cgroups) * COUT_T;
+    const int ox0 = (blockIdx.x % tiles_x) * 32, oy0 = (blockIdx.x / tiles_x) * TY, oz0 = blockIdx.y * TZ;
+    const int nchunks = (Cin + CK - 1) / CK;
+    const uint32_t bar0 = ptx::smem_u32(s_bar), in0 = ptx::smem_u32(s_in);
+
+    if (tid == 0) {
+        ptx::mbar_init(bar0, 1);
+        ptx::mbar_init(bar0 + 8, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmap);
     }
+    __syncthreads();
+
+    const CUtensorMap *const tm = &tmap;  // (taken here, not inside a lambda: the descriptor must stay in parameter space)
+    auto issue = [=](int k) {
+        const int st = k & 1, ci0 = k * CK;
+        if (tid == 0) {
+            ptx::fence_proxy_async_smem();  // the stage was read through the generic proxy two chunks ago
+            ptx::mbar_arrive_expect_tx(bar0 + 8 * st, (uint32_t)(kBox * 4));
+            ptx::tma_load_5d(in0 + (uint32_t)(st * kTile * 4), tm, bar0 + 8 * st, ox0 * S - 4, oy0 * S - 1, oz0 * S - 1, ci0, b);
+        }
+        float *dw = s_w + st * kW;
+        for (int idx = tid; idx < kW; idx += T::THREADS) {
+            const int co = idx % COUT_T;
+            const int tap = (idx / COUT_T) % 27;
+            const int c = idx / (COUT_T * 27);
+            const bool ok = co0 + co < Cout && ci0 + c < Cin;
+            cp_async4(dw + idx, w + (ok ? ((size_t)(co0 + co) * Cin + ci0 + c) * 27 + tap : 0), ok ? 4 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[4][COUT_T];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < COUT_T; ++c) acc[o][c] = 0.f;
+
+    issue(0);
+    for (int k = 0; k < nchunks; ++k) {
+        const int st = k & 1;
+        if (k + 1 < nchunks) {
+            issue(k + 1);  // into the other stage: its readers finished behind the barrier that ended chunk k - 1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        ptx::mbar_wait(bar0 + 8 * st, (uint32_t)((k >> 1) & 1));
+        __syncthreads();  // every thread's weight copies of this chunk have landed
+        conv_chunk<S, CK, TZ, TY, COUT_T, kXO>(s_in + st * kTile, s_w + st * kW, tx, ty, tz, acc);
+        __syncthreads();  // the stage may be refilled
+    }
+    conv_store<COUT_T, S == 1>(acc, shift, relu, y, b, co0, Cout, oz0 + tz, oy0 + ty, ox0 - kOutShift + tx * 4, Do, Ho, Wo);
 }
 
 template <int S, int CK, int TZ, int TY, int COUT_T>
@@ -176,11 +296,34 @@ static int launch_conv(const float *x, const float *w, const float *shift, int r
     const int tiles_x = cdiv(Wo, 32), tiles_y = cdiv(Ho, TY), tiles_z = cdiv(Do, TZ);
     const int cgroups = cdiv(Cout, COUT_T);
     MVS_REQUIRE(tiles_z <= 65535 && (long long)B * cgroups <= 65535, "conv3d: grid too large");
+    const dim3 grid(tiles_x * tiles_y, tiles_z, B * cgroups);
+    if ((W & 3) == 0 && ((uintptr_t)x & 15) == 0) {
+        // halo tiles by TMA (tensor-map strides must be multiples of 16 bytes)
+        tmap_encode_fn enc = get_tmap_encode();
+        MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+        CUtensorMap tmap;
+        const cuuint64_t gdim[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)Cin, (cuuint64_t)B};
+        const cuuint64_t gstr[4] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4,
+                                    (cuuint64_t)Cin * D * H * W * 4};
+        const cuuint32_t box[5] = {(cuuint32_t)T::IXP, (cuuint32_t)T::IY, (cuuint32_t)T::IZ, (cuuint32_t)CK, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float *>(x), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return set_error(MVS_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 conv input) failed (%d)", (int)cr);
+        const size_t smem = (size_t)2 * ((CK * T::PER_CH + 31) / 32 * 32 + CK * 27 * COUT_T) * sizeof(float) + 16 + 128;
+        auto kern = conv3d_fp32_tma_kernel<S, CK, TZ, TY, COUT_T>;
+        MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles_xt = (S == 1) ? cdiv(Wo + 3, 32) : tiles_x;  // stride 1: tiles start at 32 i - 3
+        kern<<<dim3(tiles_xt * tiles_y, tiles_z, B * cgroups), T::THREADS, smem, st>>>(tmap, w, shift, relu, y, Cin, Cout, Do, Ho, Wo,
+                                                                                     tiles_xt);
+        MVS_LAUNCH_CHECK(1);
+        return MVS_OK;
+    }
     const size_t smem = (size_t)(CK * T::PER_CH + CK * 27 * COUT_T) * sizeof(float);
     auto kern = conv3d_fp32_kernel<S, CK, TZ, TY, COUT_T>;
     if (smem > 48 * 1024) MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(tiles_x * tiles_y, tiles_z, B * cgroups), T::THREADS, smem, st>>>(x, w, shift, relu, y, Cin, Cout, D, H, W,
-                                                                                 Do, Ho, Wo, tiles_x);
+    kern<<<grid, T::THREADS, smem, st>>>(x, w, shift, relu, y, Cin, Cout, D, H, W, Do, Ho, Wo, tiles_x);
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }
