@@ -159,6 +159,18 @@ int mvs_featurenet_tc_fwd_u8(const uint8_t *imgs_u8, const mvs_featurenet_params
  * [N, 4*Cout, H'/2, W'/2] (channel = (y&1)*2+(x&1) major) that a following stride-2 layer consumes. */
 int mvs_conv2d_bn_relu_tc(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin, int Cout,
                           int H, int W, int ksize, int stride, int s2d_out, void *stream);
+/* ---- FeatureNet.forward (models/mvsnet.py:10-30), eval mode, at the reference's precision: fp32 FMA on the CUDA cores
+ * (TMA-staged halo tiles, BN folded, bias / ReLU in the epilogue).  imgs [N,3,H,W] fp32 -> fea [N,32,H/4,W/4] fp32 NCHW,
+ * what mvs_warp_variance_fwd takes.  Same parameter struct as mvs_featurenet_tc_fwd.  H % 4 == 0 and W % 16 == 0 (every
+ * layer's row pitch must be a multiple of 16 bytes for the tensor maps); mvs_featurenet_workspace_bytes() returns 0
+ * otherwise.  workspace: mvs_featurenet_workspace_bytes() bytes. */
+size_t mvs_featurenet_workspace_bytes(int N, int H, int W);
+int mvs_featurenet_fwd(const float *imgs, const mvs_featurenet_params *params, float *fea, void *workspace, int N, int H,
+                       int W, void *stream);
+/* One ConvBnReLU (models/module.py:8-15) of that path: x [N,Cin,H,W] -> y [N,Cout,H',W'] fp32 NCHW, ksize 3 / stride 1 /
+ * pad 1 or ksize 5 / stride 2 / pad 2, BN folded into w [Cout][Cin][k][k] and shift.  W % 4 == 0, x 16-byte aligned. */
+int mvs_conv2d_bn_relu(const float *x, const float *w, const float *shift, int relu, float *y, int N, int Cin, int Cout, int H,
+                       int W, int ksize, int stride, void *stream);
 /* Fused warp+variance on features in the layout mvs_featurenet_tc_fwd produces: fea [B*V][H][4][W][8] fp16 with
  * image index n = b*V + v (view 0 = reference view).  workspace: mvs_warp_variance_workspace_bytes().
  * fp16 texels, packed-half interpolation and packed-half sums of the deviations from the reference view; the fp16

@@ -63,6 +63,10 @@ SIGNATURES = {
                               [ctypes.c_void_p]),
     "mvs_featurenet_tc_fwd_u8": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
                                  [ctypes.c_void_p]),
+    "mvs_featurenet_workspace_bytes": (ctypes.c_size_t, [_i] * 3),
+    "mvs_featurenet_fwd": (_i, [_c_float_p, ctypes.POINTER(FeatureNetParams), _c_float_p, ctypes.c_void_p] + [_i] * 3 +
+                           [ctypes.c_void_p]),
+    "mvs_conv2d_bn_relu": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 7 + [ctypes.c_void_p]),
     "mvs_conv2d_bn_relu_tc": (_i, [_c_float_p] * 3 + [_i, _c_float_p] + [_i] * 8 + [ctypes.c_void_p]),
     "mvs_costreg_fwd_cp8": (_i, [_c_float_p, ctypes.POINTER(CostRegParams), _c_float_p, ctypes.c_void_p] + [_i] * 4 +
                             [ctypes.c_void_p]),

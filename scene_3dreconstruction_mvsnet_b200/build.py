@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmvsnet_b200.so")
-SOURCES = ["api.cu", "warp_variance.cu", "warp_variance_win.cu", "depth_tail.cu", "conv3d_fp32.cu", "conv3d_tc.cu", "fusion.cu"]
+SOURCES = ["api.cu", "warp_variance.cu", "warp_variance_win.cu", "depth_tail.cu", "conv3d_fp32.cu", "conv2d_fp32.cu", "conv3d_tc.cu", "fusion.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

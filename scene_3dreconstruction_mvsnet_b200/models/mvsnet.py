@@ -4,7 +4,7 @@ Same constructor, same forward signature, same output dict and the same paramete
 as the reference (so `load_state_dict` of a reference checkpoint is strict-clean), but the body of
 the forward is the B200 path:
 
-    FeatureNet (cuDNN, out of scope)                              reference mvsnet.py:125
+    FeatureNet (tcgen05 / fp32 CUDA-core kernels; cuDNN in training)  reference mvsnet.py:125
  -> fused plane-sweep warp + variance volume   [mvs_warp_variance_fwd]      :145-177
  -> CostRegNet as fused conv+BN+ReLU(+skip) kernels [mvs_costreg_fwd]        :180
  -> softmax + depth expectation + confidence  [mvs_softmax_depth_conf]      :192-218
@@ -204,8 +204,9 @@ class MVSNet(nn.Module):
                         of 2^-7); with featurenet="cudnn" also a cuDNN FeatureNet in fp16.
     featurenet: "auto" (default) - in the tensor-core modes FeatureNet runs on the same tcgen05 implicit-GEMM
                         kernel as CostRegNet (fp16 operands, fp32 accumulate, ops.featurenet_tc) and writes the warp
-                        kernel's texel layout directly; "cudnn" keeps it on cuDNN (always the case in "fp32" mode,
-                        in train() mode and under autograd).
+                        kernel's texel layout directly, and in "fp32" mode on the strict fp32 CUDA-core kernels
+                        (ops.featurenet_fp32; image widths that are not a multiple of 16 fall back to cuDNN);
+                        "cudnn" keeps it on cuDNN (always the case in train() mode and under autograd).
     """
 
     def __init__(self, refine=True, debug=0, precision="fp32", featurenet="auto"):
@@ -305,6 +306,11 @@ class MVSNet(nn.Module):
             imgs = imgs.float() / torch.full((), 255.0, dtype=torch.float32, device=imgs.device)
         if tc_features:
             fea = ops.featurenet_tc(imgs if imgs.dtype == torch.uint8 else imgs.float(), self.feature.native_prepared())
+        elif (infer and self.precision == "fp32" and self.featurenet != "cudnn"
+              and ops.featurenet_fp32_supported(imgs.shape[-2], imgs.shape[-1])):
+            # the reference's precision on our own kernels: fp32 FMA, BN folded (shapes whose rows the TMA tensor maps
+            # cannot describe keep the cuDNN path below)
+            fea = ops.featurenet_fp32(imgs.float(), self.feature.native_prepared())
         elif infer and self.precision == "fast":
             fea = self.extract_features_half(imgs)
         else:

@@ -410,6 +410,58 @@ def featurenet_tc(imgs, folded, out=None):
     return Rcp8Features(out, B, V, H // 4, W // 4)
 
 
+def featurenet_fp32_supported(H, W):
+    """The strict-fp32 FeatureNet kernels stage their halo tiles by TMA: every layer's row pitch (W, W/2, W/4 floats) must
+    be a multiple of 16 bytes."""
+    return H % 4 == 0 and W % 16 == 0
+
+
+def featurenet_fp32(imgs, folded):
+    """FeatureNet.forward (reference models/mvsnet.py:10-30, eval mode) at the reference's precision: fp32 FMA on the CUDA
+    cores.  imgs [B,V,3,H,W] fp32; folded = 8 (weight, shift) CUDA tensors in layer order (native shapes, BN folded) or the
+    PreparedParams of them -> fp32 features [B,V,32,H/4,W/4]."""
+    imgs = _prep(imgs, "imgs", 5)
+    B, V, C, H, W = imgs.shape
+    if C != 3:
+        raise RuntimeError("FeatureNet expects 3-channel images, got %d" % C)
+    lib = _lib.load()
+    nbytes = lib.mvs_featurenet_workspace_bytes(B * V, H, W)
+    if nbytes == 0:
+        raise RuntimeError("strict-fp32 FeatureNet needs H %% 4 == 0 and W %% 16 == 0 (got %dx%d)" % (H, W))
+    if isinstance(folded, PreparedParams):
+        if folded.kind != "featurenet":
+            raise RuntimeError("prepared CostRegNet parameters passed where FeatureNet's are expected")
+        params, keep = folded.params, folded.keep
+    else:
+        params, keep = _featurenet_params(folded)
+    if keep[0].device != imgs.device:
+        raise RuntimeError("FeatureNet weights are on %s, images on %s" % (keep[0].device, imgs.device))
+    ws = _ws(nbytes, imgs.device, "featurenet32")
+    out = torch.empty((B, V, 32, H // 4, W // 4), dtype=torch.float32, device=imgs.device)
+    with torch.cuda.device(imgs.device):
+        rc = lib.mvs_featurenet_fwd(_ptr(imgs), ctypes.byref(params), _ptr(out), _ptr(ws), B * V, H, W, _stream(imgs))
+    _lib.check(rc, "mvs_featurenet_fwd")
+    return out
+
+
+def conv2d_bn_relu(x, w_folded, shift, relu=True, stride=1):
+    """One ConvBnReLU (reference models/module.py:8-15, BN folded) on the strict-fp32 kernel: k3 s1 p1 or k5 s2 p2."""
+    x = _prep(x, "x", 4)
+    w_folded = _prep(w_folded, "weight", 4)
+    shift = _prep(shift, "shift", 1)
+    N, Cin, H, W = x.shape
+    Cout, k = w_folded.shape[0], w_folded.shape[2]
+    if w_folded.shape != (Cout, Cin, k, k) or shift.shape[0] != Cout:
+        raise RuntimeError("conv2d: weight %s / shift %s do not match input %s" % (tuple(w_folded.shape), tuple(shift.shape),
+                                                                                   tuple(x.shape)))
+    y = torch.empty((N, Cout, (H - 1) // stride + 1, (W - 1) // stride + 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().mvs_conv2d_bn_relu(_ptr(x), _ptr(w_folded), _ptr(shift), int(relu), _ptr(y), N, Cin, Cout, H, W, k,
+                                            stride, _stream(x))
+    _lib.check(rc, "mvs_conv2d_bn_relu")
+    return y
+
+
 def warp_variance_cp8(fea, proj, depth_values):
     """Fused warp+variance with the 16-bit chunk-planar output: returns an fp16 tensor [B, 4, D, h, w, 8]
     (channel = chunk*8 + last index).  fea: fp32 [B,V,32,h,w] (exact fp32 arithmetic) or fp16 channels-last

@@ -189,6 +189,70 @@ def test_costreg_golden(case, request, weights):
     assert maxabs(logits, c["logits"]) < 2e-4
 
 
+# ------------------------------------------------------------------------------------------------ f2 (strict fp32)
+@pytest.mark.parametrize("cin,cout,k,hw", [(3, 8, 3, (40, 64)), (8, 8, 3, (33, 36)), (8, 16, 5, (40, 64)), (16, 32, 5, (31, 44)),
+                                           (32, 32, 3, (9, 8)), (5, 11, 3, (17, 20)), (6, 9, 5, (64, 100))])
+def test_conv2d_fp32_layer(cin, cout, k, hw):
+    """One ConvBnReLU of FeatureNet on the strict-fp32 kernel (TMA halo tiles) against torch's fp32 convolution: ragged
+    tiles, channel counts that are not multiples of the chunk / group sizes, both layer kinds."""
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (1.0 / (k * k * cin) ** 0.5)
+    shift = torch.randn(cout, generator=g) * 0.3
+    stride = 2 if k == 5 else 1
+    for relu in (True, False):
+        y = ops.conv2d_bn_relu(x.to(DEV), w.to(DEV), shift.to(DEV), relu=relu, stride=stride)
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), shift.double(), stride=stride, padding=k // 2)
+        ref = torch.relu(ref) if relu else ref
+        assert tuple(y.shape) == tuple(ref.shape)
+        assert (y.cpu().double() - ref).abs().max().item() < 2e-5
+
+
+def test_conv2d_fp32_rejects_unaligned_rows():
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        ops.conv2d_bn_relu(torch.zeros(1, 3, 8, 10, device=DEV), torch.zeros(8, 3, 3, 3, device=DEV), torch.zeros(8, device=DEV))
+
+
+@pytest.mark.parametrize("B,V,H,W", [(1, 3, 64, 96), (2, 2, 36, 160)])
+def test_featurenet_fp32_matches_module(B, V, H, W, weights):
+    """Whole FeatureNet on the strict-fp32 kernels against the nn.Module on cuDNN without TF32 (BN-calibrated checkpoint):
+    same arithmetic class, differences are summation order only."""
+    m = load_model(weights)
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.rand(B, V, 3, H, W, generator=g).to(DEV)
+    with torch.no_grad():
+        fea = ops.featurenet_fp32(imgs, m.feature.folded_native())
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref = torch.stack([m.feature(img) for img in torch.unbind(imgs, 1)], 1)
+        ref64 = torch.stack([m.feature.double()(img.double()) for img in torch.unbind(imgs, 1)], 1)
+        m.feature.float()
+    scale = max(ref64.abs().max().item(), 1.0)
+    assert tuple(fea.shape) == tuple(ref.shape)
+    err, err_cudnn = (fea.double() - ref64).abs().max().item(), (ref.double() - ref64).abs().max().item()
+    assert err < 2e-5 * scale, "max err %.3g (cuDNN fp32: %.3g), feature absmax %.3g" % (err, err_cudnn, scale)
+
+
+def test_fp32_mode_uses_native_featurenet(weights):
+    """precision='fp32' inference runs FeatureNet on the library's kernels when the shape allows (launch counter), and
+    gives the depth map of the cuDNN FeatureNet path to fp32 rounding."""
+    from scene_3dreconstruction_mvsnet_b200 import _lib
+    imgs, proj, dv = synth.make_inputs(B=1, V=3, H=64, W=96, D=16, focal=90.0, interval_scale=8.0, seed=2)
+    m = load_model(weights)
+    m2 = MVSNet(refine=False, precision="fp32", featurenet="cudnn")
+    m2.load_state_dict(m.state_dict())
+    m2 = m2.to(DEV).eval()
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        a = m(imgs.to(DEV), proj.to(DEV), dv.to(DEV))
+        n1 = _lib.launch_count()
+        b = m2(imgs.to(DEV), proj.to(DEV), dv.to(DEV))
+        n2 = _lib.launch_count()
+    assert (n1 - n0) - (n2 - n1) == 8          # the eight FeatureNet layers
+    rng = float(dv.max() - dv.min())
+    assert (a["depth"] - b["depth"]).abs().max().item() < 1e-4 * rng
+    assert (a["photometric_confidence"] - b["photometric_confidence"]).abs().max().item() < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ a5-a7
 @pytest.mark.parametrize("case", ["case_a", "case_b"])
 def test_tail_golden(case, request):
