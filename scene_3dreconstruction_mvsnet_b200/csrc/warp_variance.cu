@@ -338,9 +338,9 @@ warp_volume_fwd_kernel(const float *__restrict__ fea,       // [B,V,32,H,W]; vie
 // index + the two clamp-aware increments in bits 30/31): LDS.128 + LDS.32 = 5 wavefronts; the four
 // weights are re-formed with 4 multiplies per step.  Masking the factors instead of the products
 // gives bit-identical weights (a product with a zeroed factor is the zero the mask would write).
-// This is the strict-fp32 kernel (fp32 texels, the reference's operation order, fp32 NCDHW volume); the
-// tensor-core precision modes use the TMA-window kernel of warp_variance_win.cu, which superseded the
-// 16-bit-texel variants of this generation (1.66 ms) at 1.06-1.14 ms.
+// fp32 texels, the reference's operation order, fp32 NCDHW volume.  Since round 2 the strict-fp32 mode runs the
+// TMA-window form of the same arithmetic (warp_variance_win32_kernel in warp_variance_win.cu: 2.46 ms against 4.11 ms at the
+// DTU shape, bit-identical volumes); this kernel serves more than 8 source views, where no view gets a window.
 // ------------------------------------------------------------------------------------------------
 struct PackedTap {
     float4 f;       // ax, bx, ay, by  (zeroed where the corresponding column / row is out of range)
@@ -704,6 +704,9 @@ warp_volume_bwd_kernel(const float *__restrict__ gout,      // [B,32,D,H,W]
 // ------------------------------------------------------------------------------------------------
 static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
+int warp_variance_windows_f32(const float *fea, void *tex32, const float *rt, const float *depth_values, float *var, int B, int V,
+                              int D, int H, int W, cudaStream_t st);  // warp_variance_win.cu
+
 static int pick_dchunk(int B, int D, int H, int W) {
     // enough CTAs for >= 4 waves of 148 SMs x 2 resident CTAs, but keep depth runs long (L1 reuse)
     const long long tiles = (long long)cdiv(W, 32) * cdiv(H, kWarps) * B;
@@ -748,17 +751,19 @@ extern "C" int mvs_warp_variance_fwd(const float *fea, const float *proj, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int nsrc = V - 1;
     float *rt = (float *)workspace;
-    float *src_cl = (float *)((char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float)));
-    const int HW = H * W;
-    if (nsrc > 0) {
+    // behind the homographies: room for every view's feature map in the window kernel's layout (B*V*H*W*128 bytes)
+    float *tex32 = (float *)((char *)workspace + align256((size_t)B * (nsrc > 0 ? nsrc : 1) * 12 * sizeof(float)));
+    if (nsrc > 0)
         if (int rc = compose_homographies(proj, rt, B, V, st)) return rc;
-        nchw_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, src_cl, HW, nsrc, V);
-        MVS_LAUNCH_CHECK(1);
-    }
+    // TMA-window kernel (warp_variance_win.cu) for up to 8 source views; beyond that no view gets a window and the older
+    // per-tap gather kernel below is the faster of the two (bit-identical results either way)
+    if (nsrc <= 8) return warp_variance_windows_f32(fea, tex32, rt, depth_values, var, B, V, D, H, W, st);
+    const int HW = H * W;
+    nchw_to_nhwc32_kernel<<<dim3(cdiv(HW, 32), B * nsrc), dim3(32, 8), 0, st>>>(fea, tex32, HW, nsrc, V);
+    MVS_LAUNCH_CHECK(1);
     const int dchunk = pick_dchunk(B, D, H, W);
     dim3 grid(cdiv(W, 32), cdiv(H, kWarps), B * cdiv(D, dchunk));
-    warp_variance_fwd2_kernel<<<grid, kThreads, 0, st>>>(fea, (const float4 *)src_cl, rt, depth_values, var, V,
-                                                                  nsrc, D, H, W, dchunk);
+    warp_variance_fwd2_kernel<<<grid, kThreads, 0, st>>>(fea, (const float4 *)tex32, rt, depth_values, var, V, nsrc, D, H, W, dchunk);
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
 }

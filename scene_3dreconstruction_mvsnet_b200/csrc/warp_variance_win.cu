@@ -192,6 +192,151 @@ struct SegView {
     float hix, hiy;  // samples are clamped to [0, hi]: the planner guarantees every in-image sample is inside already
 };
 
+// ------------------------------------------------------------------------------------------------
+// Window planner (one warp, once per segment): the longest run of planes starting at ds whose footprint, in every view,
+// fits one of the window shapes; issues one TMA box per view and fills the segment table.  TEXB: bytes per texel of the
+// feature tensor behind the maps (64: fp16 RCP8, 128: fp32 RCP4; both are [n][y][chunk][x][16 B], so the box coordinates
+// are the same).  s_seg[0] = planes in the segment, s_seg[1] = window shape or -1 (gather from global memory).
+// ------------------------------------------------------------------------------------------------
+template <int TEXB>
+__device__ __forceinline__ void plan_segment(int lane, int ds, int d_begin, int d_end, int tx0, int ty0, int H, int W, int nsrc,
+                                             int nwin, const float4 *s_rt, const float *s_dep, SegView *s_sv, int *s_seg,
+                                             const WinShapes &shp, const CUtensorMap *tmap0p, const CUtensorMap *tmap1p,
+                                             const CUtensorMap *tmap2p, uint32_t win0, uint32_t win_bytes, uint32_t bar,
+                                             const ViewIds &vid, int img0) {
+    // ---- plan: the longest run of planes starting at ds whose footprint, in every view, fits one of the shapes
+    const int corner = lane & 7, vsub = lane >> 3;
+    const float cxp = (corner & 1) ? (float)min(tx0 + TW - 1, W - 1) : (float)tx0;
+    const float cyp = (corner & 2) ? (float)min(ty0 + TH - 1, H - 1) : (float)ty0;
+    int L = min(d_end - ds, kMaxSeg);
+    int shape = -1;
+    int ex0[kMaxWin / 4], ey0[kMaxWin / 4];
+    while (true) {
+        float dlo = 3.0e38f, dhi = -3.0e38f;
+        for (int i = lane; i < L; i += 32) {
+            const float dv = s_dep[ds - d_begin + i];
+            dlo = fminf(dlo, dv);
+            dhi = fmaxf(dhi, dv);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
+            dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
+        }
+        const bool dep_ok = (dlo > 0.f) && (dhi < 3.0e38f);  // also false for NaN depths
+        const float cd = (corner & 4) ? dhi : dlo;
+        unsigned fitmask = (nsrc <= nwin) ? (1u << kShapes) - 1u : 0u;  // more views than windows: gather
+#pragma unroll
+        for (int it = 0; it < kMaxWin / 4; ++it) {
+            if (it * 4 >= nsrc) break;  // warp-uniform: no second pass (12 shuffles, 3 votes) for up to 4 views
+            const int v = it * 4 + vsub;
+            const bool valid = v < nsrc && v < nwin;
+            const int vv = valid ? v : 0;
+            const float4 c0 = s_rt[3 * vv], c1 = s_rt[3 * vv + 1], c2 = s_rt[3 * vv + 2];
+            const float qz = fmaf(fmaf(c2.x, cxp, fmaf(c2.y, cyp, c2.z)), cd, c2.w);
+            const float iz = rcp_approx(qz);
+            const float ix = fmaf(fmaf(fmaf(c0.x, cxp, fmaf(c0.y, cyp, c0.z)), cd, c0.w), iz, -0.5f);
+            const float iy = fmaf(fmaf(fmaf(c1.x, cxp, fmaf(c1.y, cyp, c1.z)), cd, c1.w), iz, -0.5f);
+            bool ok = dep_ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);
+            float x_lo = ok ? ix : 0.f, x_hi = x_lo, y_lo = ok ? iy : 0.f, y_hi = y_lo;
+#pragma unroll
+            for (int o = 4; o; o >>= 1) {
+                x_lo = fminf(x_lo, __shfl_xor_sync(0xffffffffu, x_lo, o));
+                x_hi = fmaxf(x_hi, __shfl_xor_sync(0xffffffffu, x_hi, o));
+                y_lo = fminf(y_lo, __shfl_xor_sync(0xffffffffu, y_lo, o));
+                y_hi = fmaxf(y_hi, __shfl_xor_sync(0xffffffffu, y_hi, o));
+            }
+            const unsigned okb = __ballot_sync(0xffffffffu, ok);
+            ok = ((okb >> (vsub * 8)) & 0xffu) == 0xffu;
+            // needed texel columns / rows, clipped to the part that can be non-zero: [-1, W] x [-1, H]
+            const int e0 = max((int)floorf(x_lo - 0.02f), -1), e1 = min((int)floorf(x_hi + 0.02f) + 1, W);
+            const int f0 = max((int)floorf(y_lo - 0.02f), -1), f1 = min((int)floorf(y_hi + 0.02f) + 1, H);
+            ex0[it] = e0;
+            ey0[it] = f0;
+#pragma unroll
+            for (int s = 0; s < kShapes; ++s) {
+                // two columns / rows of slack: element 0 is the first needed texel, the 2x2 footprint of a sample
+                // clamped to the last needed texel still ends inside the window
+                const bool fit = !valid || (ok && (e1 - e0 <= shp.wx[s] - 2) && (f1 - f0 <= shp.wy[s] - 2));
+                if (!__all_sync(0xffffffffu, fit)) fitmask &= ~(1u << s);
+            }
+        }
+        if (fitmask) {
+            shape = __ffs(fitmask) - 1;
+            break;
+        }
+        if (L == 1) break;
+        L = (L + 1) >> 1;
+    }
+    if (shape >= 0) {
+        const int wx = shp.wx[shape], wy = shp.wy[shape];
+        const CUtensorMap *tm = shape == 0 ? tmap0p : (shape == 1 ? tmap1p : tmap2p);
+        // one barrier for all windows (a barrier per window, waited on just before the view's first use, measured
+        // slower: 0.83 vs 0.79 ms -- the wait sits in the innermost view loop)
+        if (lane == 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nsrc * (uint32_t)(wx * wy * TEXB));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < kMaxWin / 4; ++it) {
+            const int v = it * 4 + vsub;
+            if (corner == 0 && v < nsrc) {
+                // an empty clipped range (footprint entirely outside) gives any origin: every sample clamps onto
+                // zero fill
+                const int ox = max(min(ex0[it], W), -wx), oy = max(min(ey0[it], H), -wy);
+                SegView sv;
+                sv.cx = -0.5f - (float)ox;
+                sv.cy = -0.5f - (float)oy;
+                sv.hix = (float)min(wx - 2, W - ox);
+                sv.hiy = (float)min(wy - 2, H - oy);
+                s_sv[v] = sv;
+                ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy,
+                                 vid.n ? vid.id[img0 + 1 + v] : img0 + 1 + v);
+            }
+        }
+    }
+    if (lane == 0) {
+        s_seg[0] = L;
+        s_seg[1] = shape;
+    }
+}
+
+// In parallel with the planner (a second warp): per plane (lane) and view, is the tile's footprint entirely outside the
+// source image?  Bit i of s_emp[v] = plane ds + i of the segment is empty in view v.
+__device__ __forceinline__ void mark_empty_planes(int lane, int ds, int d_begin, int d_end, int tx0, int ty0, int H, int W, int nsrc,
+                                                  const float4 *s_rt, const float *s_dep, uint32_t *s_emp) {
+    // ---- in parallel with the planner: per plane (lane) and view, is the tile's footprint entirely outside the
+    // source image?  At a fixed depth the map is a homography, the tile's image is the convex quadrilateral of its
+    // 4 corners (q_z > 0), and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such
+    // (view, plane) pairs skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
+    // Computed for the longest possible segment; the planner may choose a shorter one.
+    const int Lmax = min(d_end - ds, kMaxSeg);
+    const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
+    const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
+    const float dep = s_dep[ds - d_begin + min(lane, Lmax - 1)];
+    for (int v = 0; v < nsrc; ++v) {
+        const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
+        float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
+        bool ok = (lane < Lmax) && (dep > 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
+            const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
+            const float iz = rcp_approx(qz);
+            const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
+            const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
+            ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e5f) && (fabsf(iy) < 1.0e5f);  // false for NaN
+            x_lo = fminf(x_lo, ix);
+            x_hi = fmaxf(x_hi, ix);
+            y_lo = fminf(y_lo, iy);
+            y_hi = fmaxf(y_hi, iy);
+        }
+        // margins far above the error of the approximate reciprocal (2^-22 relative, coordinates below 1e5)
+        const bool empty = ok && ((x_hi < -1.05f) || (x_lo > (float)W + 0.05f) || (y_hi < -1.05f) ||
+                                  (y_lo > (float)H + 0.05f));
+        const unsigned m = __ballot_sync(0xffffffffu, empty);
+        if (lane == 0) s_emp[v] = m;
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -326,134 +471,11 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     int ds = d_begin;
     while (ds < d_end) {
         __syncthreads();  // the previous segment's windows and table are no longer read
-        if (warp == 0) {
-            // ---- plan: the longest run of planes starting at ds whose footprint, in every view, fits one of the shapes
-            const int corner = lane & 7, vsub = lane >> 3;
-            const float cxp = (corner & 1) ? (float)min(tx0 + TW - 1, W - 1) : (float)tx0;
-            const float cyp = (corner & 2) ? (float)min(ty0 + TH - 1, H - 1) : (float)ty0;
-            int L = min(d_end - ds, kMaxSeg);
-            int shape = -1;
-            int ex0[kMaxWin / 4], ey0[kMaxWin / 4];
-            while (true) {
-                float dlo = 3.0e38f, dhi = -3.0e38f;
-                for (int i = lane; i < L; i += 32) {
-                    const float dv = s_dep[ds - d_begin + i];
-                    dlo = fminf(dlo, dv);
-                    dhi = fmaxf(dhi, dv);
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
-                    dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
-                }
-                const bool dep_ok = (dlo > 0.f) && (dhi < 3.0e38f);  // also false for NaN depths
-                const float cd = (corner & 4) ? dhi : dlo;
-                unsigned fitmask = (nsrc <= nwin) ? (1u << kShapes) - 1u : 0u;  // more views than windows: gather
-#pragma unroll
-                for (int it = 0; it < kMaxWin / 4; ++it) {
-                    if (it * 4 >= nsrc) break;  // warp-uniform: no second pass (12 shuffles, 3 votes) for up to 4 views
-                    const int v = it * 4 + vsub;
-                    const bool valid = v < nsrc && v < nwin;
-                    const int vv = valid ? v : 0;
-                    const float4 c0 = s_rt[3 * vv], c1 = s_rt[3 * vv + 1], c2 = s_rt[3 * vv + 2];
-                    const float qz = fmaf(fmaf(c2.x, cxp, fmaf(c2.y, cyp, c2.z)), cd, c2.w);
-                    const float iz = rcp_approx(qz);
-                    const float ix = fmaf(fmaf(fmaf(c0.x, cxp, fmaf(c0.y, cyp, c0.z)), cd, c0.w), iz, -0.5f);
-                    const float iy = fmaf(fmaf(fmaf(c1.x, cxp, fmaf(c1.y, cyp, c1.z)), cd, c1.w), iz, -0.5f);
-                    bool ok = dep_ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);
-                    float x_lo = ok ? ix : 0.f, x_hi = x_lo, y_lo = ok ? iy : 0.f, y_hi = y_lo;
-#pragma unroll
-                    for (int o = 4; o; o >>= 1) {
-                        x_lo = fminf(x_lo, __shfl_xor_sync(0xffffffffu, x_lo, o));
-                        x_hi = fmaxf(x_hi, __shfl_xor_sync(0xffffffffu, x_hi, o));
-                        y_lo = fminf(y_lo, __shfl_xor_sync(0xffffffffu, y_lo, o));
-                        y_hi = fmaxf(y_hi, __shfl_xor_sync(0xffffffffu, y_hi, o));
-                    }
-                    const unsigned okb = __ballot_sync(0xffffffffu, ok);
-                    ok = ((okb >> (vsub * 8)) & 0xffu) == 0xffu;
-                    // needed texel columns / rows, clipped to the part that can be non-zero: [-1, W] x [-1, H]
-                    const int e0 = max((int)floorf(x_lo - 0.02f), -1), e1 = min((int)floorf(x_hi + 0.02f) + 1, W);
-                    const int f0 = max((int)floorf(y_lo - 0.02f), -1), f1 = min((int)floorf(y_hi + 0.02f) + 1, H);
-                    ex0[it] = e0;
-                    ey0[it] = f0;
-#pragma unroll
-                    for (int s = 0; s < kShapes; ++s) {
-                        // two columns / rows of slack: element 0 is the first needed texel, the 2x2 footprint of a sample
-                        // clamped to the last needed texel still ends inside the window
-                        const bool fit = !valid || (ok && (e1 - e0 <= shp.wx[s] - 2) && (f1 - f0 <= shp.wy[s] - 2));
-                        if (!__all_sync(0xffffffffu, fit)) fitmask &= ~(1u << s);
-                    }
-                }
-                if (fitmask) {
-                    shape = __ffs(fitmask) - 1;
-                    break;
-                }
-                if (L == 1) break;
-                L = (L + 1) >> 1;
-            }
-            if (shape >= 0) {
-                const int wx = shp.wx[shape], wy = shp.wy[shape];
-                const CUtensorMap *tm = shape == 0 ? &tmap0 : (shape == 1 ? &tmap1 : &tmap2);
-                // one barrier for all windows (a barrier per window, waited on just before the view's first use, measured
-                // slower: 0.83 vs 0.79 ms -- the wait sits in the innermost view loop)
-                if (lane == 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nsrc * (uint32_t)(wx * wy * 64));
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < kMaxWin / 4; ++it) {
-                    const int v = it * 4 + vsub;
-                    if (corner == 0 && v < nsrc) {
-                        // an empty clipped range (footprint entirely outside) gives any origin: every sample clamps onto
-                        // zero fill
-                        const int ox = max(min(ex0[it], W), -wx), oy = max(min(ey0[it], H), -wy);
-                        SegView sv;
-                        sv.cx = -0.5f - (float)ox;
-                        sv.cy = -0.5f - (float)oy;
-                        sv.hix = (float)min(wx - 2, W - ox);
-                        sv.hiy = (float)min(wy - 2, H - oy);
-                        s_sv[v] = sv;
-                        ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy,
-                                         vid.n ? vid.id[img0 + 1 + v] : img0 + 1 + v);
-                    }
-                }
-            }
-            if (lane == 0) {
-                s_seg[0] = L;
-                s_seg[1] = shape;
-            }
-        } else if (warp == 1) {
-            // ---- in parallel with the planner: per plane (lane) and view, is the tile's footprint entirely outside the
-            // source image?  At a fixed depth the map is a homography, the tile's image is the convex quadrilateral of its
-            // 4 corners (q_z > 0), and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such
-            // (view, plane) pairs skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
-            // Computed for the longest possible segment; the planner may choose a shorter one.
-            const int Lmax = min(d_end - ds, kMaxSeg);
-            const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
-            const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
-            const float dep = s_dep[ds - d_begin + min(lane, Lmax - 1)];
-            for (int v = 0; v < nsrc; ++v) {
-                const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-                float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
-                bool ok = (lane < Lmax) && (dep > 0.f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
-                    const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
-                    const float iz = rcp_approx(qz);
-                    const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
-                    const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
-                    ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e5f) && (fabsf(iy) < 1.0e5f);  // false for NaN
-                    x_lo = fminf(x_lo, ix);
-                    x_hi = fmaxf(x_hi, ix);
-                    y_lo = fminf(y_lo, iy);
-                    y_hi = fmaxf(y_hi, iy);
-                }
-                // margins far above the error of the approximate reciprocal (2^-22 relative, coordinates below 1e5)
-                const bool empty = ok && ((x_hi < -1.05f) || (x_lo > (float)W + 0.05f) || (y_hi < -1.05f) ||
-                                          (y_lo > (float)H + 0.05f));
-                const unsigned m = __ballot_sync(0xffffffffu, empty);
-                if (lane == 0) s_emp[v] = m;
-            }
-        }
+        if (warp == 0)
+            plan_segment<64>(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, nwin, s_rt, s_dep, s_sv, s_seg, shp, &tmap0, &tmap1, &tmap2,
+                             win0, win_bytes, bar, vid, img0);
+        else if (warp == 1)
+            mark_empty_planes(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, s_rt, s_dep, s_emp);
         __syncthreads();
         const int L = s_seg[0], shape = s_seg[1];
         if (shape >= 0) {
@@ -578,6 +600,260 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     }
 }
 
+// ================================================================================================
+// Strict-fp32 form of the same kernel (precision = "fp32", the reference's arithmetic): fp32 texels in "RCP4"
+// [n][y][chunk 0..7][x][4 ch] -- again 16 bytes per (chunk, texel), so windows, planner and tap addressing are those of the
+// fp16 kernel with eight chunks per texel instead of four -- the sample position of every (pixel, view, plane) in the
+// reference's exact fp32 operation order (IEEE divisions, no contraction: module.py:119-136 composed with grid_sample's
+// un-normalisation, the arithmetic of warp_variance_fwd2_kernel in warp_variance.cu), zero padding through masked
+// interpolation factors as there, running sum / sum of squares over the views in fp32, fp32 NCDHW volume out.  The planner
+// only decides WHERE the windows go (approximate arithmetic, generous margins); what a thread computes from a window is
+// bit-identical to what the per-tap global gathers of warp_variance_fwd2_kernel compute.
+// One CTA of 512 threads per SM (windows of 128-byte texels need all of shared memory): thread = pixel x 16 channels,
+// tid bit 7 = plane phase, bit 8 = channel half.
+// ================================================================================================
+namespace {
+
+constexpr int kThreads32 = 2 * kThreads;
+
+__device__ __forceinline__ float safe_coord32(float v) {
+    return (v <= 2147483520.0f && v >= -2147483648.0f) ? v : -100.0f;  // NaN fails both compares (CUDA grid_sampler rule)
+}
+
+// exact sample of pixel (rx, ry, rz) = R.(x, y, 1) at depth d: masked factors (ax, bx, ay, by) and the texel (x0, y0)
+__device__ __forceinline__ void sample_exact(float rx, float ry, float rz, float tx, float ty, float tz, float d, int H, int W,
+                                             float4 &f, int &x0, int &y0) {
+    const float qx = __fadd_rn(__fmul_rn(rx, d), tx);
+    const float qy = __fadd_rn(__fmul_rn(ry, d), ty);
+    const float qz = __fadd_rn(__fmul_rn(rz, d), tz);
+    const float px = __fdiv_rn(qx, qz);
+    const float py = __fdiv_rn(qy, qz);
+    const float gx = __fsub_rn(__fdiv_rn(px, (float)(W - 1) * 0.5f), 1.0f);
+    const float gy = __fsub_rn(__fdiv_rn(py, (float)(H - 1) * 0.5f), 1.0f);
+    const float ix = safe_coord32(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 0.5f));
+    const float iy = safe_coord32(__fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 0.5f));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    x0 = (int)fx0;
+    y0 = (int)fy0;
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool vx0 = (x0 >= 0) & (x0 < W), vx1 = (x1 >= 0) & (x1 < W);
+    const bool vy0 = (y0 >= 0) & (y0 < H), vy1 = (y1 >= 0) & (y1 < H);
+    f.x = vx0 ? __fsub_rn(__fadd_rn(fx0, 1.0f), ix) : 0.f;
+    f.y = vx1 ? __fsub_rn(ix, fx0) : 0.f;
+    f.z = vy0 ? __fsub_rn(__fadd_rn(fy0, 1.0f), iy) : 0.f;
+    f.w = vy1 ? __fsub_rn(iy, fy0) : 0.f;
+}
+
+__device__ __forceinline__ void accumulate4(const float4 a, const float4 b, const float4 c, const float4 d, float w00, float w01,
+                                            float w10, float w11, float *S, float *Q) {
+    const float vx = fmaf(d.x, w11, fmaf(c.x, w10, fmaf(b.x, w01, a.x * w00)));
+    const float vy = fmaf(d.y, w11, fmaf(c.y, w10, fmaf(b.y, w01, a.y * w00)));
+    const float vz = fmaf(d.z, w11, fmaf(c.z, w10, fmaf(b.z, w01, a.z * w00)));
+    const float vw = fmaf(d.w, w11, fmaf(c.w, w10, fmaf(b.w, w01, a.w * w00)));
+    S[0] += vx; Q[0] = fmaf(vx, vx, Q[0]);
+    S[1] += vy; Q[1] = fmaf(vy, vy, Q[1]);
+    S[2] += vz; Q[2] = fmaf(vz, vz, Q[2]);
+    S[3] += vw; Q[3] = fmaf(vw, vw, Q[3]);
+}
+
+// fp32 NCHW [N][32][HW] -> fp32 RCP4 [N][H][8][W][4]; one thread per output float4
+__global__ void nchw_to_rcp4_kernel(const float *__restrict__ in, float4 *__restrict__ out, int H, int W, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int c = (int)(r & 7);
+    r >>= 3;
+    const int y = (int)(r % H);
+    const long long n = r / H;
+    const size_t HW = (size_t)H * W;
+    const float *src = in + ((size_t)n * kC + 4 * c) * HW + (size_t)y * W + x;
+    out[i] = make_float4(__ldg(src), __ldg(src + HW), __ldg(src + 2 * HW), __ldg(src + 3 * HW));
+}
+
+}  // namespace
+
+template <int NSRC>
+__global__ void __launch_bounds__(kThreads32, 1)
+warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                           const __grid_constant__ CUtensorMap tmap2,
+                           const float4 *__restrict__ tex,           // fp32 RCP4 features of all views (the maps' memory)
+                           const float *__restrict__ rt,            // [B*nsrc][12] rot(9) | trans(3)
+                           const float *__restrict__ depth_values,  // [B,D]
+                           float *__restrict__ out,                 // fp32 [B,32,D,H,W]
+                           int V, int nsrc_rt, int nwin, int D, int H, int W, int dchunk, const WinShapes shp, uint32_t win_bytes) {
+    const int nsrc = NSRC > 0 ? NSRC : nsrc_rt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *sp = smem_raw + (size_t)nwin * win_bytes;
+    float4 *s_rt = reinterpret_cast<float4 *>(sp);  // [nsrc][3]: the planner's pre-scaled (r0 r1 r2 t) rows
+    sp += (size_t)nsrc * 48;
+    SegView *s_sv = reinterpret_cast<SegView *>(sp);  // [nsrc]
+    sp += (size_t)nsrc * 16;
+    float4 *s_raw = reinterpret_cast<float4 *>(sp);  // [nsrc][3]: rot | trans as given (exact arithmetic)
+    sp += (size_t)nsrc * 48;
+    uint32_t *s_emp = reinterpret_cast<uint32_t *>(sp);  // [nsrc]
+    sp += (size_t)nsrc * 4;
+    float *s_dep = reinterpret_cast<float *>(sp);  // [dchunk]
+    sp += (size_t)dchunk * 4;
+    sp = smem_raw + (((size_t)(sp - smem_raw) + 15) & ~(size_t)15);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(sp);
+    int *s_seg = reinterpret_cast<int *>(sp + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int phase = (tid >> 7) & 1, half = tid >> 8;
+    const int nchunks = (D + dchunk - 1) / dchunk;
+    const int b = blockIdx.z / nchunks;
+    const int d_begin = (blockIdx.z % nchunks) * dchunk;
+    const int d_end = min(D, d_begin + dchunk);
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int img0 = b * V;
+    const float sx = (float)W / (float)(W - 1), sy = (float)H / (float)(H - 1);
+    const uint32_t bar = ptx::smem_u32(s_bar);
+    const uint32_t win0 = ptx::smem_u32(smem_raw);
+    const uint32_t sv0 = ptx::smem_u32(s_sv);
+    ViewIds vid;
+    vid.n = 0;  // dense images b * V + v
+
+    for (int i = tid; i < nsrc * 3; i += kThreads32) {
+        const float *r = rt + (size_t)(b * nsrc + i / 3) * 12;
+        const int k = i % 3;
+        const float s = k == 0 ? sx : (k == 1 ? sy : 1.0f);
+        s_rt[i] = make_float4(r[3 * k] * s, r[3 * k + 1] * s, r[3 * k + 2] * s, r[9 + k] * s);
+        s_raw[i] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);  // the 12 floats, four at a time
+    }
+    for (int i = tid; i < d_end - d_begin; i += kThreads32) s_dep[i] = __ldg(depth_values + (size_t)b * D + d_begin + i);
+    if (tid == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmap0);
+        ptx::prefetch_tensormap(&tmap1);
+        ptx::prefetch_tensormap(&tmap2);
+    }
+    uint32_t bar_phase = 0;
+    __syncthreads();
+
+    // lane -> pixel: rows of 16 pixels (the block mapping of the fp16 kernel relies on a row pitch of 64 mod 128 bytes,
+    // which 128-byte texels do not give)
+    const int x = tx0 + (tid & 15), y = ty0 + ((tid >> 4) & 7);
+    const bool live = (x < W) & (y < H);
+    const int xc = min(x, W - 1), yc = min(y, H - 1);
+    const float xf = (float)xc, yf = (float)yc;
+    const size_t hw = (size_t)H * W;
+    const float invV = 1.0f / (float)V;
+
+    // this thread's 16 channels of the reference view: chunks 4 * half .. 4 * half + 3
+    float ref[16];
+    {
+        const float4 *rp = tex + (((size_t)img0 * H + yc) * 8 + 4 * half) * W + xc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4 v = __ldg(rp + (size_t)c * W);
+            ref[4 * c] = v.x; ref[4 * c + 1] = v.y; ref[4 * c + 2] = v.z; ref[4 * c + 3] = v.w;
+        }
+    }
+    float *const out_px = out + ((size_t)b * kC + 16 * half) * D * hw + (size_t)yc * W + xc;  // + ch * D*hw + d * hw
+
+    // R.(x, y, 1) per view in the reference's operation order (registers when the view count is a template parameter)
+    float rx[NSRC > 0 ? NSRC : 1], ry[NSRC > 0 ? NSRC : 1], rz[NSRC > 0 ? NSRC : 1];
+    auto rot_exact = [&](int v, float &ox, float &oy, float &oz) {
+        const float *r = reinterpret_cast<const float *>(s_raw + 3 * v);
+        ox = __fadd_rn(__fadd_rn(__fmul_rn(r[0], xf), __fmul_rn(r[1], yf)), r[2]);
+        oy = __fadd_rn(__fadd_rn(__fmul_rn(r[3], xf), __fmul_rn(r[4], yf)), r[5]);
+        oz = __fadd_rn(__fadd_rn(__fmul_rn(r[6], xf), __fmul_rn(r[7], yf)), r[8]);
+    };
+    if constexpr (NSRC > 0) {
+#pragma unroll
+        for (int v = 0; v < NSRC; ++v) rot_exact(v, rx[v], ry[v], rz[v]);
+    }
+
+    auto store_plane = [&](int d, const float *S, const float *Q) {
+        if (!live) return;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float m = S[j] * invV;
+            __stcs(out_px + (size_t)j * D * hw + (size_t)d * hw, fmaf(Q[j], invV, -m * m));  // Q/V - (S/V)^2   (mvsnet.py:177)
+        }
+    };
+
+    int ds = d_begin;
+    while (ds < d_end) {
+        __syncthreads();  // the previous segment's windows and table are no longer read
+        if (warp == 0)
+            plan_segment<128>(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, nwin, s_rt, s_dep, s_sv, s_seg, shp, &tmap0, &tmap1, &tmap2,
+                              win0, win_bytes, bar, vid, img0);
+        else if (warp == 1)
+            mark_empty_planes(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, s_rt, s_dep, s_emp);
+        __syncthreads();
+        const int L = s_seg[0], shape = s_seg[1];
+        const bool windowed = shape >= 0;
+        const int wx = windowed ? shp.wx[shape] : 2;
+        const uint32_t chb = (uint32_t)wx * 16u;   // bytes between the 4-channel chunks of a window row
+        const uint32_t rowb = chb * 8u;            // bytes per window row
+        if (windowed) {
+            ptx::mbar_wait(bar, bar_phase);
+            bar_phase ^= 1;
+        }
+        for (int d = ds + phase; d < ds + L; d += kPhase) {
+            const float dep = s_dep[d - d_begin];
+            const uint32_t dbit = 1u << (d - ds);
+            float S[16], Q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                S[j] = ref[j];
+                Q[j] = ref[j] * ref[j];
+            }
+#pragma unroll
+            for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
+                for (int vr = (NSRC > 0 ? v : 0); vr < (NSRC > 0 ? v + 1 : nsrc); ++vr) {  // runtime view loop when NSRC = 0
+                    // nothing of this view under the tile (CTA-uniform): it adds exact zeros to both sums
+                    if (windowed && (s_emp[vr] & dbit)) continue;
+                    float prx, pry, prz;
+                    if constexpr (NSRC > 0) {
+                        prx = rx[v]; pry = ry[v]; prz = rz[v];
+                    } else {
+                        rot_exact(vr, prx, pry, prz);
+                    }
+                    const float *traw = reinterpret_cast<const float *>(s_raw + 3 * vr) + 9;
+                    float4 f;
+                    int x0, y0;
+                    sample_exact(prx, pry, prz, traw[0], traw[1], traw[2], dep, H, W, f, x0, y0);
+                    const float w00 = f.x * f.z, w01 = f.y * f.z, w10 = f.x * f.w, w11 = f.y * f.w;
+                    if (windowed) {
+                        // window coordinates of the top-left tap; a tap the planner did not cover is outside the image and
+                        // has a zero factor: any in-window address will do for it
+                        const float4 sv = lds_f4(sv0 + 16u * vr);
+                        const int ox = -(int)(sv.x + 0.5f), oy = -(int)(sv.y + 0.5f);   // sv.x = -0.5 - origin
+                        const int col = min(max(min(max(x0, -2), W + 1) - ox, 0), (int)sv.z);
+                        const int row = min(max(min(max(y0, -2), H + 1) - oy, 0), (int)sv.w);
+                        const uint32_t a0 = win0 + (uint32_t)vr * win_bytes + (uint32_t)row * rowb + (uint32_t)col * 16u +
+                                            (uint32_t)(4 * half) * chb;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t a = a0 + (uint32_t)c * chb;
+                            const float4 ta = lds_f4(a), tb = lds_f4(a + 16u), tc = lds_f4(a + rowb), td = lds_f4(a + rowb + 16u);
+                            accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
+                        }
+                    } else {
+                        // gather segment: per-tap global loads at clamped texels (masked factors make the padding)
+                        const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 < 2147483647 ? x0 + 1 : x0, 0), W - 1);
+                        const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 < 2147483647 ? y0 + 1 : y0, 0), H - 1);
+                        const float4 *img = tex + ((size_t)(img0 + 1 + vr) * H) * 8 * W + (size_t)(4 * half) * W;
+                        const float4 *r0 = img + (size_t)cy0 * 8 * W, *r1 = img + (size_t)cy1 * 8 * W;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 ta = __ldg(r0 + c * W + cx0), tb = __ldg(r0 + c * W + cx1);
+                            const float4 tc = __ldg(r1 + c * W + cx0), td = __ldg(r1 + c * W + cx1);
+                            accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
+                        }
+                    }
+                }
+            }
+            store_plane(d, S, Q);
+        }
+        ds += L;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
@@ -594,12 +870,13 @@ struct WinPlan {
 
 // Three shapes with (nearly) the same number of texels: wide for rectified cameras and large disparity steps, tall for
 // rolled cameras.  Every shape holds at least the tile plus the bilinear halo.
-WinPlan plan_windows(int nsrc, int dchunk) {
+// texb: bytes per texel (64: fp16 RCP8, 128: fp32 RCP4); budget: shared memory per CTA; view_bytes: per-view constants
+WinPlan plan_windows(int nsrc, int dchunk, int texb = 64, int budget = kSmemBudget, int view_bytes = 84) {
     WinPlan p = {};
-    const int misc = nsrc * 84 + dchunk * 4 + 64;
+    const int misc = nsrc * view_bytes + dchunk * 4 + 64;
     p.nwin = std::min(nsrc, kMaxWin);
     if (nsrc > kMaxWin) p.nwin = 0;
-    int texels = p.nwin > 0 ? (kSmemBudget - misc) / (p.nwin * 64) : 0;
+    int texels = p.nwin > 0 ? (budget - misc) / (p.nwin * texb) : 0;
     texels = std::min(texels, 1024);  // TMA box: <= 256 elements per dimension, keep windows sane for few views
     if (p.nwin > 0 && texels < (TW + 4) * (TH + 2)) p.nwin = 0;  // too many views for useful windows
     if (p.nwin == 0) {
@@ -620,21 +897,21 @@ WinPlan plan_windows(int nsrc, int dchunk) {
         p.shp.wx[s] = wx;
         p.shp.wy[s] = wy;
     }
-    p.win_bytes = (uint32_t)(((size_t)texels * 64 + 127) / 128 * 128);
-    while ((size_t)p.nwin * p.win_bytes + misc > (size_t)kSmemBudget) p.win_bytes -= 128;
+    p.win_bytes = (uint32_t)(((size_t)texels * texb + 127) / 128 * 128);
+    while ((size_t)p.nwin * p.win_bytes + misc > (size_t)budget) p.win_bytes -= 128;
     for (int s = 0; s < kShapes; ++s)
-        while ((uint32_t)(p.shp.wx[s] * p.shp.wy[s] * 64) > p.win_bytes) p.shp.wx[s] -= 2;
+        while ((uint32_t)(p.shp.wx[s] * p.shp.wy[s] * texb) > p.win_bytes) p.shp.wx[s] -= 2;
     p.smem = (size_t)p.nwin * p.win_bytes + misc;
     return p;
 }
 
-int encode_window_map(CUtensorMap *tmap, const void *tex, int N, int H, int W, int WX, int WY) {
+int encode_window_map(CUtensorMap *tmap, const void *tex, int N, int H, int W, int WX, int WY, int chunks = 4) {
     tmap_encode_fn enc = get_tmap_encode();
     MVS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     // dims (x as uint64 pairs, chunk, y, n): the box lands in smem as [row][chunk][col][16 B]
-    cuuint64_t gdim[4] = {(cuuint64_t)2 * W, 4, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
-    cuuint32_t box[4] = {(cuuint32_t)(2 * WX), 4, (cuuint32_t)WY, 1};
+    cuuint64_t gdim[4] = {(cuuint64_t)2 * W, (cuuint64_t)chunks, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)W * 16 * chunks, (cuuint64_t)H * W * 16 * chunks};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * WX), (cuuint32_t)chunks, (cuuint32_t)WY, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(tex), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -716,6 +993,62 @@ int warp_variance_windows(const void *tex16, const float *rt, const float *depth
         case 3: return launch_win<3>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
         case 4: return launch_win<4>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
         default: return launch_win<0>(maps, p, tex16, rt, depth_values, vol_cp8, B, V, D, H, W, dchunk, vid, st);
+    }
+}
+
+namespace {
+
+constexpr int kSmemBudget32 = 225 * 1024;  // one CTA per SM
+
+template <int NSRC>
+int launch_win32(const CUtensorMap *maps, const WinPlan &p, const void *tex32, const float *rt, const float *depth_values,
+                 float *var, int B, int V, int D, int H, int W, int dchunk, cudaStream_t st) {
+    auto kern = warp_variance_win32_kernel<NSRC>;
+    MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget32));
+    dim3 grid(cdiv(W, TW), cdiv(H, TH), B * cdiv(D, dchunk));
+    kern<<<grid, kThreads32, p.smem, st>>>(maps[0], maps[1], maps[2], (const float4 *)tex32, rt, depth_values, var, V, V - 1, p.nwin,
+                                           D, H, W, dchunk, p.shp, p.win_bytes);
+    MVS_LAUNCH_CHECK(1);
+    return MVS_OK;
+}
+
+}  // namespace
+
+// Strict-fp32 fused warp + variance (mvs_warp_variance_fwd): fea fp32 [B,V,32,H,W] -> var fp32 [B,32,D,H,W].
+// tex32: scratch for the RCP4 copy of all B*V feature maps (B*V*H*W*128 bytes).  Asynchronous on st.
+int warp_variance_windows_f32(const float *fea, void *tex32, const float *rt, const float *depth_values, float *var, int B, int V,
+                              int D, int H, int W, cudaStream_t st) {
+    MVS_REQUIRE(V >= 1, "warp_variance: V=%d", V);
+    const int dchunk = kMaxSeg;
+    MVS_REQUIRE((long long)B * cdiv(D, dchunk) <= 65535, "B*D=%lld too large for one launch", (long long)B * D);
+    MVS_REQUIRE(cdiv(H, TH) <= 65535, "feature map too tall");
+    const int nsrc = V - 1, N = B * V;
+    const long long total = (long long)N * H * 8 * W;
+    nchw_to_rcp4_kernel<<<cdiv(total, 256), 256, 0, st>>>(fea, (float4 *)tex32, H, W, total);
+    MVS_LAUNCH_CHECK(1);
+    struct MapSlot { const void *tex; int n, H, W, nsrc; WinPlan p; CUtensorMap maps[kShapes]; };
+    static thread_local MapSlot cache[4];
+    static thread_local int cache_next = 0;
+    MapSlot *slot = nullptr;
+    for (auto &c : cache)
+        if (c.tex == tex32 && c.n == N && c.H == H && c.W == W && c.nsrc == nsrc) { slot = &c; break; }
+    if (slot == nullptr) {
+        MapSlot &c = cache[cache_next];
+        cache_next = (cache_next + 1) % 4;
+        c.tex = nullptr;
+        c.p = plan_windows(nsrc, dchunk, 128, kSmemBudget32, 132);
+        for (int s = 0; s < kShapes; ++s)
+            if (int rc = encode_window_map(&c.maps[s], tex32, N, H, W, c.p.shp.wx[s], c.p.shp.wy[s], 8)) return rc;
+        c.tex = tex32; c.n = N; c.H = H; c.W = W; c.nsrc = nsrc;
+        slot = &c;
+    }
+    const WinPlan &p = slot->p;
+    switch (p.nwin > 0 ? nsrc : 0) {
+        case 1: return launch_win32<1>(slot->maps, p, tex32, rt, depth_values, var, B, V, D, H, W, dchunk, st);
+        case 2: return launch_win32<2>(slot->maps, p, tex32, rt, depth_values, var, B, V, D, H, W, dchunk, st);
+        case 3: return launch_win32<3>(slot->maps, p, tex32, rt, depth_values, var, B, V, D, H, W, dchunk, st);
+        case 4: return launch_win32<4>(slot->maps, p, tex32, rt, depth_values, var, B, V, D, H, W, dchunk, st);
+        default: return launch_win32<0>(slot->maps, p, tex32, rt, depth_values, var, B, V, D, H, W, dchunk, st);
     }
 }
 
