@@ -99,11 +99,11 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    float acc[4][kCoutT];
+    float2 acc[4][kCoutT / 2];  // packed pairs of output channels (FFMA2: two IEEE fmas per issue slot)
 #pragma unroll
     for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int q = 0; q < kCoutT; ++q) acc[o][q] = 0.f;
+        for (int q = 0; q < kCoutT / 2; ++q) acc[o][q] = make_float2(0.f, 0.f);
 
     issue(0);
     for (int k = 0; k < nchunks; ++k) {
@@ -141,11 +141,14 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
                 for (int kw = 0; kw < K; ++kw) {
                     const float4 w0 = *reinterpret_cast<const float4 *>(wp + kw * kCoutT);
                     const float4 w1 = *reinterpret_cast<const float4 *>(wp + kw * kCoutT + 4);
-                    const float wr[kCoutT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const float2 wr[kCoutT / 2] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                                   make_float2(w1.z, w1.w)};
 #pragma unroll
-                    for (int o = 0; o < 4; ++o)
+                    for (int o = 0; o < 4; ++o) {
+                        const float2 a2 = make_float2(in[o * S + kw], in[o * S + kw]);
 #pragma unroll
-                        for (int q = 0; q < kCoutT; ++q) acc[o][q] = fmaf(in[o * S + kw], wr[q], acc[o][q]);
+                        for (int q = 0; q < kCoutT / 2; ++q) acc[o][q] = __ffma2_rn(a2, wr[q], acc[o][q]);
+                    }
                 }
             }
         }
@@ -161,7 +164,7 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
         float v[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            v[o] = acc[o][q] + sh;
+            v[o] = ((q & 1) ? acc[o][q >> 1].y : acc[o][q >> 1].x) + sh;
             if (relu) v[o] = fmaxf(v[o], 0.f);
         }
         float *op = y + (((size_t)n * Cout + co0 + q) * Ho + oy) * Wo + ox;

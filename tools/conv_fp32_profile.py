@@ -1,5 +1,5 @@
 """Times the strict-fp32 CUDA-core convolution layers of CostRegNet at the C2 shape (the command profiled under ncu).
-    python tools/conv_fp32_profile.py [layer]     layer: conv0 | conv1 | conv2 | conv11 | prob | all"""
+    python tools/conv_fp32_profile.py [layer]     layer: conv0 ... conv7 | conv9 | conv11 | prob | all"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +7,9 @@ from scene_3dreconstruction_mvsnet_b200 import ops
 D, H, W = 192, 288, 400
 layers = {"conv0": (0, 32, 8, D, H, W), "conv1": (1, 8, 16, D, H, W), "conv2": (0, 16, 16, D // 2, H // 2, W // 2),
           "conv3": (1, 16, 32, D // 2, H // 2, W // 2), "conv4": (0, 32, 32, D // 4, H // 4, W // 4),
-          "conv6": (0, 64, 64, D // 8, H // 8, W // 8), "conv11": (2, 16, 8, D // 2, H // 2, W // 2), "prob": (0, 8, 1, D, H, W)}
+          "conv5": (1, 32, 64, D // 4, H // 4, W // 4), "conv6": (0, 64, 64, D // 8, H // 8, W // 8),
+          "conv7": (2, 64, 32, D // 8, H // 8, W // 8), "conv9": (2, 32, 16, D // 4, H // 4, W // 4),
+          "conv11": (2, 16, 8, D // 2, H // 2, W // 2), "prob": (0, 8, 1, D, H, W)}
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 tot = 0.0
 for name, (kind, ci, co, d, h, w) in layers.items():
