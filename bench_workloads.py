@@ -329,7 +329,7 @@ def run_train(args, bench):
                          "achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms else None, "peak": hbm_peak, "unit": "GB/s",
                          "frac": bwd_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak if bwd_ms else None, "traffic": None,
                          "peak_kind": peak_kind},
-            "roofline_fwd": {"kernel": "warp_variance_fwd2_kernel (fp32)", "ms": fwd_ms, "algorithmic_bytes": fwd_bytes,
+            "roofline_fwd": {"kernel": "warp_variance_win32_kernel (fp32)", "ms": fwd_ms, "algorithmic_bytes": fwd_bytes,
                              "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak if fwd_ms else None},
             "collective": {"what": "DDP gradient all-reduce (338,129 fp32 = 1.35 MB, one bucket) over NCCL",
                            "allreduce_ms": allreduce_ms},

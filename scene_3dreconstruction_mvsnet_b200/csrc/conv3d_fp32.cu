@@ -438,6 +438,143 @@ convT3d_fp32_kernel(const float *__restrict__ x, const float *__restrict__ w, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same gather with two x-adjacent low-resolution positions and four output channels per thread.  The one-position form
+// above re-reads all 27 weight vectors per input channel for 216 FMAs -- one broadcast LDS.128 per four FMAs, which is the
+// shared-memory pipe's whole budget (ncu: 20 TFLOP/s).  Two positions share every weight vector (one LDS.128 per eight FMAs)
+// and 4 of their 12 inputs; the FMAs are packed pairs of output channels (FFMA2).  Accumulation order per output element is
+// that of the kernel above (input channel, then input offset): bit-identical results.
+// ------------------------------------------------------------------------------------------------
+template <int CK>
+__global__ void __launch_bounds__(128)
+convT3d_fp32_pair_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ shift, int relu,
+                         const float *__restrict__ skip, float *__restrict__ y, int Cin, int Cout, int D, int H, int W) {
+    constexpr int CT = 4;
+    __shared__ __align__(16) float s_w[CK * 27 * CT];  // [ci][tap][co]
+    const int tid = threadIdx.x;
+    const int cgroups = (Cout + CT - 1) / CT;
+    const int b = blockIdx.z / cgroups;
+    const int co0 = (blockIdx.z % cgroups) * CT;
+    const int z = blockIdx.y;
+    const int Wp = (W + 1) >> 1;  // position pairs per row
+    const int pos = blockIdx.x * 128 + tid;
+    const bool live = pos < H * Wp;
+    const int yy = live ? pos / Wp : 0, xx = live ? 2 * (pos % Wp) : 0;
+    const size_t in_cs = (size_t)D * H * W;
+    const bool hz = z + 1 < D, hy = yy + 1 < H;
+    const bool hx1 = xx + 1 < W, hx2 = xx + 2 < W;
+
+    float2 acc[2][8][CT / 2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int q = 0; q < CT / 2; ++q) acc[j][p][q] = make_float2(0.f, 0.f);
+
+    for (int ci0 = 0; ci0 < Cin; ci0 += CK) {
+        __syncthreads();
+        for (int idx = tid; idx < CK * 27 * CT; idx += 128) {
+            const int co = idx % CT;
+            const int tap = (idx / CT) % 27;
+            const int c = idx / (CT * 27);
+            float v = 0.f;
+            if (co0 + co < Cout && ci0 + c < Cin) v = __ldg(w + ((size_t)(ci0 + c) * Cout + co0 + co) * 27 + tap);
+            s_w[idx] = v;
+        }
+        __syncthreads();
+        if (!live) continue;
+        // the 12 inputs of a channel are loaded one channel ahead: with 3 CTAs of 4 warps per SM nothing else hides their latency
+        auto load_inputs = [&](int ci, float (&v)[2][2][3]) {
+            const float *ip = x + ((size_t)b * Cin + ci) * in_cs + ((size_t)z * H + yy) * W + xx;
+#pragma unroll
+            for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy) {
+                    const bool okr = (ci < Cin) && (!dz || hz) && (!dy || hy);
+                    const float *r = ip + ((size_t)dz * H + dy) * W;
+                    v[dz][dy][0] = okr ? __ldg(r) : 0.f;
+                    v[dz][dy][1] = (okr && hx1) ? __ldg(r + 1) : 0.f;
+                    v[dz][dy][2] = (okr && hx2) ? __ldg(r + 2) : 0.f;
+                }
+        };
+        float nxt[2][2][3];
+        load_inputs(ci0, nxt);
+#pragma unroll 1
+        for (int c = 0; c < CK; ++c) {
+            if (ci0 + c >= Cin) break;
+            float in[2][2][3];  // [dz][dy][column xx + 0..2]
+#pragma unroll
+            for (int i = 0; i < 12; ++i) (&in[0][0][0])[i] = (&nxt[0][0][0])[i];
+            if (c + 1 < CK) load_inputs(ci0 + c + 1, nxt);
+            const float *wc = s_w + c * 27 * CT;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {           // output parity (pz,py,px)
+                const int pz = p >> 2, py = (p >> 1) & 1, px = p & 1;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {       // input offset (dz,dy,dx)
+                    const int dz = n >> 2, dy = (n >> 1) & 1, dx = n & 1;
+                    if ((dz && !pz) || (dy && !py) || (dx && !px)) continue;  // even outputs only see offset 0
+                    const int kd = pz ? (dz ? 0 : 2) : 1;
+                    const int kh = py ? (dy ? 0 : 2) : 1;
+                    const int kw = px ? (dx ? 0 : 2) : 1;
+                    const float4 wt = *reinterpret_cast<const float4 *>(wc + ((kd * 3 + kh) * 3 + kw) * CT);
+                    const float2 w01 = make_float2(wt.x, wt.y), w23 = make_float2(wt.z, wt.w);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float a = in[dz][dy][j + dx];
+                        const float2 a2 = make_float2(a, a);
+                        acc[j][p][0] = __ffma2_rn(a2, w01, acc[j][p][0]);
+                        acc[j][p][1] = __ffma2_rn(a2, w23, acc[j][p][1]);
+                    }
+                }
+            }
+        }
+    }
+    if (!live) return;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const size_t out_cs = (size_t)8 * in_cs;
+#pragma unroll
+    for (int q = 0; q < CT; ++q) {
+        if (co0 + q >= Cout) break;
+        const float sh = __ldg(shift + co0 + q);
+#pragma unroll
+        for (int pzy = 0; pzy < 4; ++pzy) {
+            const int pz = pzy >> 1, py = pzy & 1;
+            const size_t o = ((size_t)b * Cout + co0 + q) * out_cs + ((size_t)(2 * z + pz) * Ho + 2 * yy + py) * Wo + 2 * xx;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    const float2 a = acc[j][pzy * 2 + px][q >> 1];
+                    float t = ((q & 1) ? a.y : a.x) + sh;
+                    if (relu) t = fmaxf(t, 0.f);
+                    v[2 * j + px] = t;
+                }
+            if (hx1 && (W & 1) == 0) {  // four consecutive outputs, 16-byte aligned (xx even, Wo a multiple of 4)
+                if (skip) {  // skip + relu(bn(convT))   (mvsnet.py:69-71)
+                    const float4 sk = __ldg(reinterpret_cast<const float4 *>(skip + o));
+                    v[0] += sk.x; v[1] += sk.y; v[2] += sk.z; v[3] += sk.w;
+                }
+                *reinterpret_cast<float4 *>(y + o) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j == 1 && !hx1) break;
+                    float v0 = v[2 * j], v1 = v[2 * j + 1];
+                    if (skip) {
+                        const float2 sk = __ldg(reinterpret_cast<const float2 *>(skip + o + 2 * j));
+                        v0 += sk.x;
+                        v1 += sk.y;
+                    }
+                    *reinterpret_cast<float2 *>(y + o + 2 * j) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
 int conv3d_fp32(const float *x, const float *w, const float *shift, int relu, float *y, int B, int Cin, int Cout, int D,
                 int H, int W, int stride, cudaStream_t st) {
     if (stride == 1) {
@@ -457,10 +594,10 @@ int convT3d_fp32(const float *x, const float *w, const float *shift, int relu, c
         convT3d_fp32_kernel<1, 16><<<dim3(cdiv((long long)H * W, 128), D, B * cg), 128, 0, st>>>(x, w, shift, relu, skip, y,
                                                                                                Cin, Cout, D, H, W);
     } else {
-        const int cg = cdiv(Cout, 8);
+        const int cg = cdiv(Cout, 4);
         MVS_REQUIRE((long long)B * cg <= 65535, "conv_transpose3d: grid too large");
-        convT3d_fp32_kernel<8, 16><<<dim3(cdiv((long long)H * W, 128), D, B * cg), 128, 0, st>>>(x, w, shift, relu, skip, y,
-                                                                                               Cin, Cout, D, H, W);
+        convT3d_fp32_pair_kernel<16><<<dim3(cdiv((long long)H * ((W + 1) / 2), 128), D, B * cg), 128, 0, st>>>(x, w, shift, relu, skip,
+                                                                                                          y, Cin, Cout, D, H, W);
     }
     MVS_LAUNCH_CHECK(1);
     return MVS_OK;
