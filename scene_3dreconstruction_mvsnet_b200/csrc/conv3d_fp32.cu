@@ -451,6 +451,9 @@ convT3d_fp32_pair_kernel(const float *__restrict__ x, const float *__restrict__ 
                          const float *__restrict__ skip, float *__restrict__ y, int Cin, int Cout, int D, int H, int W) {
     constexpr int CT = 4;
     __shared__ __align__(16) float s_w[CK * 27 * CT];  // [ci][tap][co]
+    // the thread's 16 skip float4 (4 channels x 4 (pz, py) rows), fetched asynchronously before the accumulation and read back
+    // in the epilogue: with 12 warps per SM nothing else hides a DRAM round trip in front of the stores
+    __shared__ __align__(16) float4 s_skip[16][128];
     const int tid = threadIdx.x;
     const int cgroups = (Cout + CT - 1) / CT;
     const int b = blockIdx.z / cgroups;
@@ -463,6 +466,24 @@ convT3d_fp32_pair_kernel(const float *__restrict__ x, const float *__restrict__ 
     const size_t in_cs = (size_t)D * H * W;
     const bool hz = z + 1 < D, hy = yy + 1 < H;
     const bool hx1 = xx + 1 < W, hx2 = xx + 2 < W;
+
+    const int Ho = 2 * H, Wo = 2 * W;
+    const size_t out_cs = (size_t)8 * in_cs;
+    const bool vec4 = hx1 && (W & 1) == 0;  // four consecutive outputs, 16-byte aligned (xx even, Wo a multiple of 4)
+    const bool skip_staged = skip != nullptr && live && vec4;
+    if (skip_staged) {
+#pragma unroll
+        for (int q = 0; q < CT; ++q)
+#pragma unroll
+            for (int pzy = 0; pzy < 4; ++pzy) {
+                const size_t o = ((size_t)b * Cout + min(co0 + q, Cout - 1)) * out_cs +
+                                 ((size_t)(2 * z + (pzy >> 1)) * Ho + 2 * yy + (pzy & 1)) * Wo + 2 * xx;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_skip[q * 4 + pzy][tid])),
+                             "l"(skip + o)
+                             : "memory");
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     float2 acc[2][8][CT / 2];
 #pragma unroll
@@ -532,8 +553,7 @@ convT3d_fp32_pair_kernel(const float *__restrict__ x, const float *__restrict__ 
         }
     }
     if (!live) return;
-    const int Ho = 2 * H, Wo = 2 * W;
-    const size_t out_cs = (size_t)8 * in_cs;
+    if (skip_staged) asm volatile("cp.async.wait_group 0;" ::: "memory");  // own copies only: no barrier needed
 #pragma unroll
     for (int q = 0; q < CT; ++q) {
         if (co0 + q >= Cout) break;
@@ -552,9 +572,9 @@ convT3d_fp32_pair_kernel(const float *__restrict__ x, const float *__restrict__ 
                     if (relu) t = fmaxf(t, 0.f);
                     v[2 * j + px] = t;
                 }
-            if (hx1 && (W & 1) == 0) {  // four consecutive outputs, 16-byte aligned (xx even, Wo a multiple of 4)
+            if (vec4) {
                 if (skip) {  // skip + relu(bn(convT))   (mvsnet.py:69-71)
-                    const float4 sk = __ldg(reinterpret_cast<const float4 *>(skip + o));
+                    const float4 sk = s_skip[q * 4 + pzy][tid];
                     v[0] += sk.x; v[1] += sk.y; v[2] += sk.z; v[3] += sk.w;
                 }
                 *reinterpret_cast<float4 *>(y + o) = make_float4(v[0], v[1], v[2], v[3]);

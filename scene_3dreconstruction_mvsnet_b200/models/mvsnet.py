@@ -269,6 +269,14 @@ class MVSNet(nn.Module):
             f = self._features_eval(x)
         return f.view(B, V, *f.shape[1:])
 
+    def extract_features_fp32(self, imgs):
+        """Strict-fp32 inference: imgs [B,V,3,H,W] -> fp32 features [B,V,32,H/4,W/4] at the reference's precision on our own
+        kernels (fp32 FMA, BN folded: ops.featurenet_fp32).  Shapes whose rows the TMA tensor maps cannot describe (W not a
+        multiple of 16) and featurenet="cudnn" take the cuDNN path."""
+        if self.featurenet != "cudnn" and ops.featurenet_fp32_supported(imgs.shape[-2], imgs.shape[-1]):
+            return ops.featurenet_fp32(imgs.float(), self.feature.native_prepared())
+        return self.extract_features(imgs)
+
     def extract_features_half(self, imgs):
         """Tensor-core mode: imgs [B,V,3,H,W] -> fp16 channels-last features [B,V,H/4,W/4,32]."""
         B, V = imgs.shape[:2]
@@ -306,11 +314,8 @@ class MVSNet(nn.Module):
             imgs = imgs.float() / torch.full((), 255.0, dtype=torch.float32, device=imgs.device)
         if tc_features:
             fea = ops.featurenet_tc(imgs if imgs.dtype == torch.uint8 else imgs.float(), self.feature.native_prepared())
-        elif (infer and self.precision == "fp32" and self.featurenet != "cudnn"
-              and ops.featurenet_fp32_supported(imgs.shape[-2], imgs.shape[-1])):
-            # the reference's precision on our own kernels: fp32 FMA, BN folded (shapes whose rows the TMA tensor maps
-            # cannot describe keep the cuDNN path below)
-            fea = ops.featurenet_fp32(imgs.float(), self.feature.native_prepared())
+        elif infer and self.precision == "fp32":
+            fea = self.extract_features_fp32(imgs)
         elif infer and self.precision == "fast":
             fea = self.extract_features_half(imgs)
         else:

@@ -445,3 +445,11 @@ def test_c3_four_view_grayscale_full_size(weights):
     assert a["depth"].shape == (1, 128, 160)
     assert maxabs(a["depth"], b["depth"]) < 5e-3 * rng             # the one tolerance stated for the tensor-core mode
     assert float((a["depth"] - b["depth"]).abs().mean()) < 5e-4 * rng
+
+
+# ------------------------------------------------------------------------------------------------ entry point
+def test_graft_entry_smoke():
+    """The driver's smoke(): strict-fp32 stages against the oracle and the reference goldens, stage-wise == forward(),
+    the tensor-core mode at its tolerance, the backward kernel against the oracle."""
+    import __graft_entry__ as entry
+    entry.smoke()

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "scene_3dreconstruction_mvsnet_b200", "libmvsnet_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 pats = collections.OrderedDict([("UTC*MMA", r"\bUTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG", r"\bUTMALDG"),
-                                ("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"), ("HFMA2", r"\bHFMA2"), ("HMMA/MMA.SYNC", r"\bHMMA")])
+                                ("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"), ("HFMA2", r"\bHFMA2"), ("FFMA2", r"\bFFMA2"), ("HMMA/MMA.SYNC", r"\bHMMA")])
 cur, counts = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
@@ -25,7 +25,7 @@ print("| kernel | instr | " + " | ".join(pats) + " |")
 print("|---|---|" + "---|" * len(pats))
 tot = collections.Counter()
 for (name, c), d in zip(counts.items(), demangled):
-    short = re.sub(r"\(.*", "", d).replace("void ", "").replace("mvs::", "").replace("(anonymous namespace)::", "")
+    short = re.sub(r"\(.*", "", d.replace("(anonymous namespace)::", "")).replace("void ", "").replace("mvs::", "")
     print("| `%s` | %d | " % (short[:70], c["instr"]) + " | ".join(str(c[k]) for k in pats) + " |")
     tot.update(c)
 print("| **total** | %d | " % tot["instr"] + " | ".join(str(tot[k]) for k in pats) + " |")
