@@ -30,7 +30,7 @@ def _nvcc():
 def _deps(src):
     return [os.path.join(CSRC, src), os.path.join(CSRC, "common.cuh"),
             os.path.join(os.path.dirname(HERE), "include", "mvsnet_b200.h")] + \
-        [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+        [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))]
 
 
 def _compile(nvcc, src, verbose):

@@ -192,151 +192,6 @@ struct SegView {
     float hix, hiy;  // samples are clamped to [0, hi]: the planner guarantees every in-image sample is inside already
 };
 
-// ------------------------------------------------------------------------------------------------
-// Window planner (one warp, once per segment): the longest run of planes starting at ds whose footprint, in every view,
-// fits one of the window shapes; issues one TMA box per view and fills the segment table.  TEXB: bytes per texel of the
-// feature tensor behind the maps (64: fp16 RCP8, 128: fp32 RCP4; both are [n][y][chunk][x][16 B], so the box coordinates
-// are the same).  s_seg[0] = planes in the segment, s_seg[1] = window shape or -1 (gather from global memory).
-// ------------------------------------------------------------------------------------------------
-template <int TEXB>
-__device__ __forceinline__ void plan_segment(int lane, int ds, int d_begin, int d_end, int tx0, int ty0, int H, int W, int nsrc,
-                                             int nwin, const float4 *s_rt, const float *s_dep, SegView *s_sv, int *s_seg,
-                                             const WinShapes &shp, const CUtensorMap *tmap0p, const CUtensorMap *tmap1p,
-                                             const CUtensorMap *tmap2p, uint32_t win0, uint32_t win_bytes, uint32_t bar,
-                                             const ViewIds &vid, int img0) {
-    // ---- plan: the longest run of planes starting at ds whose footprint, in every view, fits one of the shapes
-    const int corner = lane & 7, vsub = lane >> 3;
-    const float cxp = (corner & 1) ? (float)min(tx0 + TW - 1, W - 1) : (float)tx0;
-    const float cyp = (corner & 2) ? (float)min(ty0 + TH - 1, H - 1) : (float)ty0;
-    int L = min(d_end - ds, kMaxSeg);
-    int shape = -1;
-    int ex0[kMaxWin / 4], ey0[kMaxWin / 4];
-    while (true) {
-        float dlo = 3.0e38f, dhi = -3.0e38f;
-        for (int i = lane; i < L; i += 32) {
-            const float dv = s_dep[ds - d_begin + i];
-            dlo = fminf(dlo, dv);
-            dhi = fmaxf(dhi, dv);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            dlo = fminf(dlo, __shfl_xor_sync(0xffffffffu, dlo, o));
-            dhi = fmaxf(dhi, __shfl_xor_sync(0xffffffffu, dhi, o));
-        }
-        const bool dep_ok = (dlo > 0.f) && (dhi < 3.0e38f);  // also false for NaN depths
-        const float cd = (corner & 4) ? dhi : dlo;
-        unsigned fitmask = (nsrc <= nwin) ? (1u << kShapes) - 1u : 0u;  // more views than windows: gather
-#pragma unroll
-        for (int it = 0; it < kMaxWin / 4; ++it) {
-            if (it * 4 >= nsrc) break;  // warp-uniform: no second pass (12 shuffles, 3 votes) for up to 4 views
-            const int v = it * 4 + vsub;
-            const bool valid = v < nsrc && v < nwin;
-            const int vv = valid ? v : 0;
-            const float4 c0 = s_rt[3 * vv], c1 = s_rt[3 * vv + 1], c2 = s_rt[3 * vv + 2];
-            const float qz = fmaf(fmaf(c2.x, cxp, fmaf(c2.y, cyp, c2.z)), cd, c2.w);
-            const float iz = rcp_approx(qz);
-            const float ix = fmaf(fmaf(fmaf(c0.x, cxp, fmaf(c0.y, cyp, c0.z)), cd, c0.w), iz, -0.5f);
-            const float iy = fmaf(fmaf(fmaf(c1.x, cxp, fmaf(c1.y, cyp, c1.z)), cd, c1.w), iz, -0.5f);
-            bool ok = dep_ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e8f) && (fabsf(iy) < 1.0e8f);
-            float x_lo = ok ? ix : 0.f, x_hi = x_lo, y_lo = ok ? iy : 0.f, y_hi = y_lo;
-#pragma unroll
-            for (int o = 4; o; o >>= 1) {
-                x_lo = fminf(x_lo, __shfl_xor_sync(0xffffffffu, x_lo, o));
-                x_hi = fmaxf(x_hi, __shfl_xor_sync(0xffffffffu, x_hi, o));
-                y_lo = fminf(y_lo, __shfl_xor_sync(0xffffffffu, y_lo, o));
-                y_hi = fmaxf(y_hi, __shfl_xor_sync(0xffffffffu, y_hi, o));
-            }
-            const unsigned okb = __ballot_sync(0xffffffffu, ok);
-            ok = ((okb >> (vsub * 8)) & 0xffu) == 0xffu;
-            // needed texel columns / rows, clipped to the part that can be non-zero: [-1, W] x [-1, H]
-            const int e0 = max((int)floorf(x_lo - 0.02f), -1), e1 = min((int)floorf(x_hi + 0.02f) + 1, W);
-            const int f0 = max((int)floorf(y_lo - 0.02f), -1), f1 = min((int)floorf(y_hi + 0.02f) + 1, H);
-            ex0[it] = e0;
-            ey0[it] = f0;
-#pragma unroll
-            for (int s = 0; s < kShapes; ++s) {
-                // two columns / rows of slack: element 0 is the first needed texel, the 2x2 footprint of a sample
-                // clamped to the last needed texel still ends inside the window
-                const bool fit = !valid || (ok && (e1 - e0 <= shp.wx[s] - 2) && (f1 - f0 <= shp.wy[s] - 2));
-                if (!__all_sync(0xffffffffu, fit)) fitmask &= ~(1u << s);
-            }
-        }
-        if (fitmask) {
-            shape = __ffs(fitmask) - 1;
-            break;
-        }
-        if (L == 1) break;
-        L = (L + 1) >> 1;
-    }
-    if (shape >= 0) {
-        const int wx = shp.wx[shape], wy = shp.wy[shape];
-        const CUtensorMap *tm = shape == 0 ? tmap0p : (shape == 1 ? tmap1p : tmap2p);
-        // one barrier for all windows (a barrier per window, waited on just before the view's first use, measured
-        // slower: 0.83 vs 0.79 ms -- the wait sits in the innermost view loop)
-        if (lane == 0) ptx::mbar_arrive_expect_tx(bar, (uint32_t)nsrc * (uint32_t)(wx * wy * TEXB));
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < kMaxWin / 4; ++it) {
-            const int v = it * 4 + vsub;
-            if (corner == 0 && v < nsrc) {
-                // an empty clipped range (footprint entirely outside) gives any origin: every sample clamps onto
-                // zero fill
-                const int ox = max(min(ex0[it], W), -wx), oy = max(min(ey0[it], H), -wy);
-                SegView sv;
-                sv.cx = -0.5f - (float)ox;
-                sv.cy = -0.5f - (float)oy;
-                sv.hix = (float)min(wx - 2, W - ox);
-                sv.hiy = (float)min(wy - 2, H - oy);
-                s_sv[v] = sv;
-                ptx::tma_load_4d(win0 + (uint32_t)v * win_bytes, tm, bar, 2 * ox, 0, oy,
-                                 vid.n ? vid.id[img0 + 1 + v] : img0 + 1 + v);
-            }
-        }
-    }
-    if (lane == 0) {
-        s_seg[0] = L;
-        s_seg[1] = shape;
-    }
-}
-
-// In parallel with the planner (a second warp): per plane (lane) and view, is the tile's footprint entirely outside the
-// source image?  Bit i of s_emp[v] = plane ds + i of the segment is empty in view v.
-__device__ __forceinline__ void mark_empty_planes(int lane, int ds, int d_begin, int d_end, int tx0, int ty0, int H, int W, int nsrc,
-                                                  const float4 *s_rt, const float *s_dep, uint32_t *s_emp) {
-    // ---- in parallel with the planner: per plane (lane) and view, is the tile's footprint entirely outside the
-    // source image?  At a fixed depth the map is a homography, the tile's image is the convex quadrilateral of its
-    // 4 corners (q_z > 0), and a sample with ix <= -1, ix >= W, iy <= -1 or iy >= H touches no texel.  Such
-    // (view, plane) pairs skip the loads and the interpolation (DTU-like baselines: a fifth of all samples).
-    // Computed for the longest possible segment; the planner may choose a shorter one.
-    const int Lmax = min(d_end - ds, kMaxSeg);
-    const float x0f = (float)tx0, x1f = (float)min(tx0 + TW - 1, W - 1);
-    const float y0f = (float)ty0, y1f = (float)min(ty0 + TH - 1, H - 1);
-    const float dep = s_dep[ds - d_begin + min(lane, Lmax - 1)];
-    for (int v = 0; v < nsrc; ++v) {
-        const float4 c0 = s_rt[3 * v], c1 = s_rt[3 * v + 1], c2 = s_rt[3 * v + 2];
-        float x_lo = 3.0e38f, x_hi = -3.0e38f, y_lo = 3.0e38f, y_hi = -3.0e38f;
-        bool ok = (lane < Lmax) && (dep > 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float xx = (k & 1) ? x1f : x0f, yy = (k & 2) ? y1f : y0f;
-            const float qz = fmaf(fmaf(c2.x, xx, fmaf(c2.y, yy, c2.z)), dep, c2.w);
-            const float iz = rcp_approx(qz);
-            const float ix = fmaf(fmaf(fmaf(c0.x, xx, fmaf(c0.y, yy, c0.z)), dep, c0.w), iz, -0.5f);
-            const float iy = fmaf(fmaf(fmaf(c1.x, xx, fmaf(c1.y, yy, c1.z)), dep, c1.w), iz, -0.5f);
-            ok = ok && (qz > 1e-20f) && (fabsf(ix) < 1.0e5f) && (fabsf(iy) < 1.0e5f);  // false for NaN
-            x_lo = fminf(x_lo, ix);
-            x_hi = fmaxf(x_hi, ix);
-            y_lo = fminf(y_lo, iy);
-            y_hi = fmaxf(y_hi, iy);
-        }
-        // margins far above the error of the approximate reciprocal (2^-22 relative, coordinates below 1e5)
-        const bool empty = ok && ((x_hi < -1.05f) || (x_lo > (float)W + 0.05f) || (y_hi < -1.05f) ||
-                                  (y_lo > (float)H + 0.05f));
-        const unsigned m = __ballot_sync(0xffffffffu, empty);
-        if (lane == 0) s_emp[v] = m;
-    }
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -471,11 +326,9 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
     int ds = d_begin;
     while (ds < d_end) {
         __syncthreads();  // the previous segment's windows and table are no longer read
-        if (warp == 0)
-            plan_segment<64>(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, nwin, s_rt, s_dep, s_sv, s_seg, shp, &tmap0, &tmap1, &tmap2,
-                             win0, win_bytes, bar, vid, img0);
-        else if (warp == 1)
-            mark_empty_planes(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, s_rt, s_dep, s_emp);
+#define WARP_PLAN_TEXEL_BYTES 64
+#include "warp_window_plan.inc"
+#undef WARP_PLAN_TEXEL_BYTES
         __syncthreads();
         const int L = s_seg[0], shape = s_seg[1];
         if (shape >= 0) {
@@ -778,11 +631,9 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
     int ds = d_begin;
     while (ds < d_end) {
         __syncthreads();  // the previous segment's windows and table are no longer read
-        if (warp == 0)
-            plan_segment<128>(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, nwin, s_rt, s_dep, s_sv, s_seg, shp, &tmap0, &tmap1, &tmap2,
-                              win0, win_bytes, bar, vid, img0);
-        else if (warp == 1)
-            mark_empty_planes(lane, ds, d_begin, d_end, tx0, ty0, H, W, nsrc, s_rt, s_dep, s_emp);
+#define WARP_PLAN_TEXEL_BYTES 128
+#include "warp_window_plan.inc"
+#undef WARP_PLAN_TEXEL_BYTES
         __syncthreads();
         const int L = s_seg[0], shape = s_seg[1];
         const bool windowed = shape >= 0;
