@@ -463,7 +463,7 @@ warp_variance_win_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid
 // only decides WHERE the windows go (approximate arithmetic, generous margins); what a thread computes from a window is
 // bit-identical to what the per-tap global gathers of warp_variance_fwd2_kernel compute.
 // One CTA of 512 threads per SM (windows of 128-byte texels need all of shared memory): thread = pixel x 16 channels,
-// tid bit 7 = plane phase, bit 8 = channel half.
+// a warp = 16 pixels x 2 channel halves, which share the sample positions through shuffles (each half computes every other view).
 // ================================================================================================
 namespace {
 
@@ -553,7 +553,9 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
     int *s_seg = reinterpret_cast<int *>(sp + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int phase = (tid >> 7) & 1, half = tid >> 8;
+    // a warp = the 16 pixels of one tile row x the two channel halves (lane bit 4): the halves of a pixel share the sample
+    // positions through shuffles; warps 0-7 take the even planes of a segment, 8-15 the odd ones
+    const int phase = warp >> 3, half = lane >> 4;
     const int nchunks = (D + dchunk - 1) / dchunk;
     const int b = blockIdx.z / nchunks;
     const int d_begin = (blockIdx.z % nchunks) * dchunk;
@@ -587,7 +589,7 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
 
     // lane -> pixel: rows of 16 pixels (the block mapping of the fp16 kernel relies on a row pitch of 64 mod 128 bytes,
     // which 128-byte texels do not give)
-    const int x = tx0 + (tid & 15), y = ty0 + ((tid >> 4) & 7);
+    const int x = tx0 + (lane & 15), y = ty0 + (warp & 7);
     const bool live = (x < W) & (y < H);
     const int xc = min(x, W - 1), yc = min(y, H - 1);
     const float xf = (float)xc, yf = (float)yc;
@@ -607,7 +609,12 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
     float *const out_px = out + ((size_t)b * kC + 16 * half) * D * hw + (size_t)yc * W + xc;  // + ch * D*hw + d * hw
 
     // R.(x, y, 1) per view in the reference's operation order (registers when the view count is a template parameter)
-    float rx[NSRC > 0 ? NSRC : 1], ry[NSRC > 0 ? NSRC : 1], rz[NSRC > 0 ? NSRC : 1];
+    // The two channel halves of a pixel need the same sample positions: half h computes views h, h + 2, ... (slot s = view
+    // 2 s + h; an odd view count repeats the last view in the spare slot) and every lane fetches a view's result from its
+    // owner with six shuffles -- the exact projection (four IEEE divisions) is ~135 instructions, more than the 96 FMAs it
+    // feeds in a 16-channel thread.
+    constexpr int NS = NSRC > 0 ? (NSRC + 1) / 2 : 1;
+    float rx[NS], ry[NS], rz[NS];
     auto rot_exact = [&](int v, float &ox, float &oy, float &oz) {
         const float *r = reinterpret_cast<const float *>(s_raw + 3 * v);
         ox = __fadd_rn(__fadd_rn(__fmul_rn(r[0], xf), __fmul_rn(r[1], yf)), r[2]);
@@ -616,7 +623,7 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
     };
     if constexpr (NSRC > 0) {
 #pragma unroll
-        for (int v = 0; v < NSRC; ++v) rot_exact(v, rx[v], ry[v], rz[v]);
+        for (int sl = 0; sl < NS; ++sl) rot_exact(min(2 * sl + half, NSRC - 1), rx[sl], ry[sl], rz[sl]);
     }
 
     auto store_plane = [&](int d, const float *S, const float *Q) {
@@ -653,50 +660,73 @@ warp_variance_win32_kernel(const __grid_constant__ CUtensorMap tmap0, const __gr
                 S[j] = ref[j];
                 Q[j] = ref[j] * ref[j];
             }
+            // one view's contribution from its masked factors f and top-left texel (x0, y0)
+            auto add_view = [&](int vr, const float4 f, int x0, int y0) {
+                const float w00 = f.x * f.z, w01 = f.y * f.z, w10 = f.x * f.w, w11 = f.y * f.w;
+                if (windowed) {
+                    // window coordinates of the top-left tap; a tap the planner did not cover is outside the image and
+                    // has a zero factor: any in-window address will do for it
+                    const float4 sv = lds_f4(sv0 + 16u * vr);
+                    const int ox = -(int)(sv.x + 0.5f), oy = -(int)(sv.y + 0.5f);   // sv.x = -0.5 - origin
+                    const int col = min(max(min(max(x0, -2), W + 1) - ox, 0), (int)sv.z);
+                    const int row = min(max(min(max(y0, -2), H + 1) - oy, 0), (int)sv.w);
+                    const uint32_t a0 = win0 + (uint32_t)vr * win_bytes + (uint32_t)row * rowb + (uint32_t)col * 16u +
+                                        (uint32_t)(4 * half) * chb;
 #pragma unroll
-            for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
-                for (int vr = (NSRC > 0 ? v : 0); vr < (NSRC > 0 ? v + 1 : nsrc); ++vr) {  // runtime view loop when NSRC = 0
-                    // nothing of this view under the tile (CTA-uniform): it adds exact zeros to both sums
-                    if (windowed && (s_emp[vr] & dbit)) continue;
-                    float prx, pry, prz;
-                    if constexpr (NSRC > 0) {
-                        prx = rx[v]; pry = ry[v]; prz = rz[v];
-                    } else {
-                        rot_exact(vr, prx, pry, prz);
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t a = a0 + (uint32_t)c * chb;
+                        const float4 ta = lds_f4(a), tb = lds_f4(a + 16u), tc = lds_f4(a + rowb), td = lds_f4(a + rowb + 16u);
+                        accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
                     }
+                } else {
+                    // gather segment: per-tap global loads at clamped texels (masked factors make the padding)
+                    const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 + 1, 0), W - 1);   // |x0| < 2^31 - 128: no overflow
+                    const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 + 1, 0), H - 1);
+                    const float4 *img = tex + ((size_t)(img0 + 1 + vr) * H) * 8 * W + (size_t)(4 * half) * W;
+                    const float4 *r0 = img + (size_t)cy0 * 8 * W, *r1 = img + (size_t)cy1 * 8 * W;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 ta = __ldg(r0 + c * W + cx0), tb = __ldg(r0 + c * W + cx1);
+                        const float4 tc = __ldg(r1 + c * W + cx0), td = __ldg(r1 + c * W + cx1);
+                        accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
+                    }
+                }
+            };
+            if constexpr (NSRC > 0) {
+#pragma unroll
+                for (int sl = 0; sl < NS; ++sl) {
+                    const int k0 = 2 * sl, k1 = min(2 * sl + 1, NSRC - 1);
+                    // a view with nothing under the tile in this plane (CTA-uniform) adds exact zeros to both sums
+                    const bool e0 = (s_emp[k0] & dbit) != 0, e1 = (2 * sl + 1 >= NSRC) || (s_emp[k1] & dbit) != 0;
+                    if (e0 && e1) continue;
+                    const int kown = min(2 * sl + half, NSRC - 1);
+                    const float *traw = reinterpret_cast<const float *>(s_raw + 3 * kown) + 9;
+                    float4 f;
+                    int x0, y0;
+                    sample_exact(rx[sl], ry[sl], rz[sl], traw[0], traw[1], traw[2], dep, H, W, f, x0, y0);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j ? e1 : e0) continue;
+                        const int src = (lane & 15) | (j << 4);   // the lane of this pixel in the half that owns view 2 sl + j
+                        float4 fk;
+                        fk.x = __shfl_sync(0xffffffffu, f.x, src);
+                        fk.y = __shfl_sync(0xffffffffu, f.y, src);
+                        fk.z = __shfl_sync(0xffffffffu, f.z, src);
+                        fk.w = __shfl_sync(0xffffffffu, f.w, src);
+                        const int xk = __shfl_sync(0xffffffffu, x0, src), yk = __shfl_sync(0xffffffffu, y0, src);
+                        add_view(2 * sl + j, fk, xk, yk);
+                    }
+                }
+            } else {
+                for (int vr = 0; vr < nsrc; ++vr) {  // any number of views: every lane computes every view
+                    if (s_emp[vr] & dbit) continue;
+                    float prx, pry, prz;
+                    rot_exact(vr, prx, pry, prz);
                     const float *traw = reinterpret_cast<const float *>(s_raw + 3 * vr) + 9;
                     float4 f;
                     int x0, y0;
                     sample_exact(prx, pry, prz, traw[0], traw[1], traw[2], dep, H, W, f, x0, y0);
-                    const float w00 = f.x * f.z, w01 = f.y * f.z, w10 = f.x * f.w, w11 = f.y * f.w;
-                    if (windowed) {
-                        // window coordinates of the top-left tap; a tap the planner did not cover is outside the image and
-                        // has a zero factor: any in-window address will do for it
-                        const float4 sv = lds_f4(sv0 + 16u * vr);
-                        const int ox = -(int)(sv.x + 0.5f), oy = -(int)(sv.y + 0.5f);   // sv.x = -0.5 - origin
-                        const int col = min(max(min(max(x0, -2), W + 1) - ox, 0), (int)sv.z);
-                        const int row = min(max(min(max(y0, -2), H + 1) - oy, 0), (int)sv.w);
-                        const uint32_t a0 = win0 + (uint32_t)vr * win_bytes + (uint32_t)row * rowb + (uint32_t)col * 16u +
-                                            (uint32_t)(4 * half) * chb;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t a = a0 + (uint32_t)c * chb;
-                            const float4 ta = lds_f4(a), tb = lds_f4(a + 16u), tc = lds_f4(a + rowb), td = lds_f4(a + rowb + 16u);
-                            accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
-                        }
-                    } else {
-                        // gather segment: per-tap global loads at clamped texels (masked factors make the padding)
-                        const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x0 < 2147483647 ? x0 + 1 : x0, 0), W - 1);
-                        const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y0 < 2147483647 ? y0 + 1 : y0, 0), H - 1);
-                        const float4 *img = tex + ((size_t)(img0 + 1 + vr) * H) * 8 * W + (size_t)(4 * half) * W;
-                        const float4 *r0 = img + (size_t)cy0 * 8 * W, *r1 = img + (size_t)cy1 * 8 * W;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 ta = __ldg(r0 + c * W + cx0), tb = __ldg(r0 + c * W + cx1);
-                            const float4 tc = __ldg(r1 + c * W + cx0), td = __ldg(r1 + c * W + cx1);
-                            accumulate4(ta, tb, tc, td, w00, w01, w10, w11, S + 4 * c, Q + 4 * c);
-                        }
-                    }
+                    add_view(vr, f, x0, y0);
                 }
             }
             store_plane(d, S, Q);
