@@ -74,8 +74,10 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
     const CUtensorMap *const tm = &tmap;
 
     if (tid == 0) {
-        ptx::mbar_init(bar0, 1);
-        ptx::mbar_init(bar0 + 8, 1);
+        // a stage is complete when the TMA box has landed (one arrival + its bytes) and every thread's weight copies have
+        // (cp.async.mbarrier.arrive.noinc: one arrival per thread when its earlier cp.async are done)
+        ptx::mbar_init(bar0, 1 + kThreads2d);
+        ptx::mbar_init(bar0 + 8, 1 + kThreads2d);
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(tm);
     }
@@ -96,7 +98,7 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
             const bool ok = co0 + co < Cout && ci0 + c < Cin;
             cp_async4_zfill(dw + idx, w + (ok ? ((size_t)(co0 + co) * Cin + ci0 + c) * (K * K) + tap : 0), ok ? 4 : 0);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * st) : "memory");
     };
 
     float2 acc[4][kCoutT / 2];  // packed pairs of output channels (FFMA2: two IEEE fmas per issue slot)
@@ -108,14 +110,8 @@ conv2d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
     issue(0);
     for (int k = 0; k < nchunks; ++k) {
         const int st = k & 1;
-        if (k + 1 < nchunks) {
-            issue(k + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        ptx::mbar_wait(bar0 + 8 * st, (uint32_t)((k >> 1) & 1));
-        __syncthreads();  // every thread's weight copies of this chunk have landed
+        if (k + 1 < nchunks) issue(k + 1);  // into the other stage: its readers finished behind the barrier that ended chunk k - 1
+        ptx::mbar_wait(bar0 + 8 * st, (uint32_t)((k >> 1) & 1));  // tile and weights of this chunk are in shared memory
         const float *tin = s_in + st * kTile, *tw = s_w + st * kW;
 #pragma unroll 1
         for (int c = 0; c < CK; ++c) {

@@ -254,8 +254,10 @@ conv3d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
     const uint32_t bar0 = ptx::smem_u32(s_bar), in0 = ptx::smem_u32(s_in);
 
     if (tid == 0) {
-        ptx::mbar_init(bar0, 1);
-        ptx::mbar_init(bar0 + 8, 1);
+        // a stage is complete when the TMA box has landed (one arrival + its bytes) and every thread's weight copies have
+        // (cp.async.mbarrier.arrive.noinc: one arrival per thread when its earlier cp.async are done)
+        ptx::mbar_init(bar0, 1 + T::THREADS);
+        ptx::mbar_init(bar0 + 8, 1 + T::THREADS);
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmap);
     }
@@ -277,7 +279,7 @@ conv3d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
             const bool ok = co0 + co < Cout && ci0 + c < Cin;
             cp_async4(dw + idx, w + (ok ? ((size_t)(co0 + co) * Cin + ci0 + c) * 27 + tap : 0), ok ? 4 : 0);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * st) : "memory");
     };
 
     float2 acc[4][(COUT_T + 1) / 2];
@@ -289,14 +291,8 @@ conv3d_fp32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__
     issue(0);
     for (int k = 0; k < nchunks; ++k) {
         const int st = k & 1;
-        if (k + 1 < nchunks) {
-            issue(k + 1);  // into the other stage: its readers finished behind the barrier that ended chunk k - 1
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        ptx::mbar_wait(bar0 + 8 * st, (uint32_t)((k >> 1) & 1));
-        __syncthreads();  // every thread's weight copies of this chunk have landed
+        if (k + 1 < nchunks) issue(k + 1);  // into the other stage: its readers finished behind the barrier that ended chunk k - 1
+        ptx::mbar_wait(bar0 + 8 * st, (uint32_t)((k >> 1) & 1));  // tile and weights of this chunk are in shared memory
         conv_chunk<S, CK, TZ, TY, COUT_T, kXO>(s_in + st * kTile, s_w + st * kW, tx, ty, tz, acc);
         __syncthreads();  // the stage may be refilled
     }
