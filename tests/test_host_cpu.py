@@ -139,3 +139,43 @@ def test_folded_weight_cache_keys_on_cpu():
     assert torch.allclose(r.folded_params()[0][0], 3.0 * w0) and torch.allclose(cr.folded_params()[0][0], w0)
     m.double()
     assert cr.folded_params()[0][0].dtype == torch.float64
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="the reference checkout only exists in the build container")
+def test_public_surface_matches_the_reference_package():
+    """Drop-in boundary: everything the reference's drivers import from `models` / `models.module`
+    (train.py:15, eval.py:14, evalDTU.py:14; mvsnet.py:4) exists here under the same name with the reference's parameters in
+    the reference's order (extra keyword parameters of ours come after them and have defaults)."""
+    import inspect
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from make_golden import import_reference
+    ref_mvsnet, ref_module = import_reference()
+    import models as ours                      # the top-level shim a driver picks up through PYTHONPATH
+    import models.module as ours_module
+
+    def params(fn):
+        return [p for p in inspect.signature(fn).parameters.values() if p.name != "self"]
+
+    def check(ref_fn, our_fn, what):
+        rp, op = params(ref_fn), params(our_fn)
+        assert [p.name for p in op[:len(rp)]] == [p.name for p in rp], what
+        for r, o in zip(rp, op):
+            assert (r.default is inspect.Parameter.empty) == (o.default is inspect.Parameter.empty), (what, r.name)
+            if r.default is not inspect.Parameter.empty:
+                assert r.default == o.default, (what, r.name)
+        assert all(p.default is not inspect.Parameter.empty for p in op[len(rp):]), what
+
+    for name in ("MVSNet", "mvsnet_loss"):
+        assert hasattr(ours, name), name
+    check(ref_mvsnet.MVSNet.__init__, ours.MVSNet.__init__, "MVSNet.__init__")
+    check(ref_mvsnet.MVSNet.forward, ours.MVSNet.forward, "MVSNet.forward")
+    check(ref_mvsnet.mvsnet_loss, ours.mvsnet_loss, "mvsnet_loss")
+    for name in ("homo_warping", "depth_regression"):
+        check(getattr(ref_module, name), getattr(ours_module, name), name)
+    for name in ("ConvBnReLU", "ConvBnReLU3D"):
+        check(getattr(ref_module, name).__init__, getattr(ours_module, name).__init__, name)
+    # same sub-module names, so checkpoints and code that reaches into the model (model.feature, ...) keep working
+    ref_children = [n for n, _ in ref_mvsnet.MVSNet(refine=False).named_children()]
+    our_children = [n for n, _ in ours.MVSNet(refine=False).named_children()]
+    assert ref_children == our_children
